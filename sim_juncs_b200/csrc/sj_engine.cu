@@ -1,0 +1,645 @@
+// sj_engine.cu -- host runtime of the sim_juncs_b200 engine: grid/PML/source/monitor set-up
+// (what meep::structure / meep::fields do at construction for the reference, SURVEY.md 8a rows
+// A7, A8, M4, M8), device memory, and the step loop of bound_geom::run (src/disp.cpp:719-741).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <complex>
+
+#include "sj_kernels.cuh"
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            s->err = b_;                                                                           \
+            return SJ_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+static int fail(sj_sim *s, int code, const char *msg) {
+    if (s) s->err = msg; else g_create_err = msg;
+    return code;
+}
+
+extern "C" int sj_version(void) { return 100; }
+extern "C" const char *sj_last_error(const sj_sim *s) { return s ? s->err.c_str() : g_create_err.c_str(); }
+
+// meep structure_chunk::use_pml: quadratic profile, sigma sampled per half pixel, sig = sigma dt/2
+static void build_pml_table(std::vector<double> &sig, int n, double a, double dt, double thick, double R) {
+    sig.assign(2 * n + 2, 0.0);
+    if (thick <= 0) return;
+    const double inva = 1.0 / a;
+    const double prefac = -log(R) / (4 * thick * (1.0 / 3.0));
+    const double bloc[2] = {0.0, (2 * n) * (0.5 * inva)};
+    for (int side = 0; side < 2; ++side)
+        for (int i = 0; i < 2 * n + 2; ++i) {
+            const double here = i * 0.5 * inva;
+            const double x = thick - (0.5 * inva) * ((int)(fabs(bloc[side] - here) * a * 2 + 0.5));
+            if (x > 0) {
+                const double u = x / thick;
+                sig[i] = 0.5 * dt * (prefac * u * u);
+            }
+        }
+}
+
+template <typename T>
+static int upload_vec(sj_sim *s, const std::vector<double> &v, void **dev) {
+    std::vector<T> tmp(v.size());
+    for (size_t i = 0; i < v.size(); ++i) tmp[i] = (T)v[i];
+    CK(cudaMalloc(dev, std::max<size_t>(tmp.size(), 1) * sizeof(T)));
+    if (!tmp.empty()) CK(cudaMemcpy(*dev, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+static int upload_sig(sj_sim *s, int d) {
+    return s->prec == SJ_F64 ? upload_vec<double>(s, s->sig[d], &s->sigd[d]) : upload_vec<float>(s, s->sig[d], &s->sigd[d]);
+}
+
+static int alloc_zero(sj_sim *s, void **p, size_t bytes) {
+    CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    CK(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+    return 0;
+}
+
+extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
+    if (!g || !out) return fail(NULL, SJ_ERR_ARG, "null argument");
+    if (g->n[0] < 2 || g->n[1] < 2 || g->n[2] < 2 || g->a <= 0) return fail(NULL, SJ_ERR_ARG, "bad grid");
+    if (g->n_sets < 1 || g->n_sets > 64) return fail(NULL, SJ_ERR_ARG, "n_sets out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(NULL, SJ_ERR_CUDA, "no CUDA device: libsimjuncs_b200 has no CPU fallback");
+    sj_sim *s = new sj_sim();
+    s->g = *g;
+    if (g->device >= 0 && cudaSetDevice(g->device) != cudaSuccess) { delete s; return fail(NULL, SJ_ERR_CUDA, "cudaSetDevice failed"); }
+    s->prec = g->precision == SJ_F32 ? SJ_F32 : SJ_F64;
+    s->esz = s->prec == SJ_F64 ? 8 : 4;
+    s->g.courant = g->courant > 0 ? g->courant : 0.5;
+    s->g.pml_R = g->pml_R > 0 ? g->pml_R : 1e-15;
+    s->inva = 1.0 / g->a;
+    s->dt = s->g.courant * s->inva;
+    s->kz0 = g->kz0; s->kz1 = g->kz1;
+    if (s->kz0 == 0 && s->kz1 == 0) s->kz1 = g->n[2] + 1;
+    if (s->kz0 < 0 || s->kz1 > g->n[2] + 1 || s->kz0 >= s->kz1) { delete s; return fail(NULL, SJ_ERR_ARG, "bad z-slab"); }
+    s->pitch = ((g->n[0] + 1 + 31) / 32) * 32;
+    s->rows = g->n[1] + 1;
+    s->nzl = s->kz1 - s->kz0 + 2;
+    s->plane = (long long)s->pitch * s->rows;
+    s->set_stride = s->plane * s->nzl;
+    s->materials_set = false; s->n_slots = 0; s->drive = NULL; s->drive_steps = 0; s->drive_dirty = true;
+    s->n_mon = 0; s->mon_idx = NULL; s->mon_w = NULL; s->series = NULL; s->series_cap = 0; s->n_samples = 0;
+    s->steps_done = 0; s->launches = 0; s->pole_points = 0; s->pml_cells = 0;
+    s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
+    for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = NULL; }
+    for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) s->PA[q][c] = s->PB[q][c] = NULL;
+    for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) s->srcw[q][c] = NULL;
+    *out = s;
+
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const int n[3] = {g->n[0], g->n[1], g->n[2]};
+    for (int d = 0; d < 3; ++d) {
+        build_pml_table(s->sig[d], n[d], g->a, s->dt, g->pml_thickness, s->g.pml_R);
+        int rc = upload_sig(s, d); if (rc) return rc;
+        // interior = index range where both half-pixel samples have sigma == 0 and every
+        // component is updatable with all neighbours in range: [max(.,1), min(., n))
+        int lo = 1, hi = n[d];
+        while (lo < n[d] && (s->sig[d][2 * lo] != 0.0 || s->sig[d][2 * lo + 1] != 0.0)) ++lo;
+        while (hi > lo && (s->sig[d][2 * (hi - 1)] != 0.0 || s->sig[d][2 * (hi - 1) + 1] != 0.0)) --hi;
+        if (d == 0) { lo = ((lo + 3) / 4) * 4; hi = (hi / 4) * 4; if (hi < lo) hi = lo; }
+        s->lo[d] = lo; s->hi[d] = hi;
+    }
+    const size_t fbytes = (size_t)s->set_stride * g->n_sets * s->esz;
+    for (int c = 0; c < 3; ++c) {
+        int rc = alloc_zero(s, &s->E[c], fbytes); if (rc) return rc;
+        rc = alloc_zero(s, &s->H[c], fbytes); if (rc) return rc;
+        rc = alloc_zero(s, (void **)&s->mat[c], (size_t)s->set_stride); if (rc) return rc;
+    }
+    // PML shell boxes (global index boxes [lo,hi), k clipped to the owned slab)
+    {
+        const int L[3] = {s->lo[0], s->lo[1], s->lo[2]}, Hh[3] = {s->hi[0], s->hi[1], s->hi[2]};
+        const int N1[3] = {n[0] + 1, n[1] + 1, n[2] + 1};
+        int bl[SJ_N_PML_BOX][3], bh[SJ_N_PML_BOX][3];
+        // z-low, z-high: full xy ; y-low, y-high: z interior ; x-low, x-high: y,z interior
+        int q = 0;
+        bl[q][0] = 0; bh[q][0] = N1[0]; bl[q][1] = 0; bh[q][1] = N1[1]; bl[q][2] = 0; bh[q][2] = L[2]; ++q;
+        bl[q][0] = 0; bh[q][0] = N1[0]; bl[q][1] = 0; bh[q][1] = N1[1]; bl[q][2] = Hh[2]; bh[q][2] = N1[2]; ++q;
+        bl[q][0] = 0; bh[q][0] = N1[0]; bl[q][1] = 0; bh[q][1] = L[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
+        bl[q][0] = 0; bh[q][0] = N1[0]; bl[q][1] = Hh[1]; bh[q][1] = N1[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
+        bl[q][0] = 0; bh[q][0] = L[0]; bl[q][1] = L[1]; bh[q][1] = Hh[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
+        bl[q][0] = Hh[0]; bh[q][0] = N1[0]; bl[q][1] = L[1]; bh[q][1] = Hh[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
+        for (int b = 0; b < SJ_N_PML_BOX; ++b) {
+            sj_sim::Box B;
+            for (int d = 0; d < 3; ++d) { B.lo[d] = bl[b][d]; B.hi[d] = bh[b][d]; }
+            B.lo[2] = std::max(B.lo[2], s->kz0); B.hi[2] = std::min(B.hi[2], s->kz1);
+            B.bx = B.hi[0] - B.lo[0]; B.by = B.hi[1] - B.lo[1]; B.bz = B.hi[2] - B.lo[2];
+            if (B.bx <= 0 || B.by <= 0 || B.bz <= 0) continue;
+            B.bpitch = ((B.bx + 3) / 4) * 4;
+            B.bplane = (long long)B.bpitch * B.by;
+            B.bset = B.bplane * B.bz;
+            const size_t bytes = (size_t)B.bset * g->n_sets * s->esz;
+            for (int c = 0; c < 3; ++c) {
+                int rc = alloc_zero(s, &B.D[c], bytes); if (rc) return rc;
+                rc = alloc_zero(s, &B.B[c], bytes); if (rc) return rc;
+                rc = alloc_zero(s, &B.UD[c], bytes); if (rc) return rc;
+                rc = alloc_zero(s, &B.UB[c], bytes); if (rc) return rc;
+            }
+            s->pml_cells += (double)B.bx * B.by * B.bz;
+            s->boxes.push_back(B);
+        }
+    }
+    // default material table: vacuum
+    {
+        sj_material vac; memset(&vac, 0, sizeof vac); vac.eps_inf = 1.0;
+        int rc = sj_set_materials(s, 1, &vac, NULL, NULL, NULL); if (rc) return rc;
+        s->materials_set = false;
+    }
+    int rc = alloc_zero(s, (void **)&s->step_dev, sizeof(long long)); if (rc) return rc;
+    rc = alloc_zero(s, (void **)&s->flags, 4 * sizeof(int)); if (rc) return rc;
+    return SJ_OK;
+}
+
+extern "C" void sj_destroy(sj_sim *s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->stream);
+    for (int c = 0; c < 3; ++c) { cudaFree(s->E[c]); cudaFree(s->H[c]); cudaFree(s->mat[c]); cudaFree(s->masks[c]); cudaFree(s->sigd[c]); }
+    for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { cudaFree(s->PA[q][c]); cudaFree(s->PB[q][c]); }
+    for (auto &B : s->boxes) for (int c = 0; c < 3; ++c) { cudaFree(B.D[c]); cudaFree(B.B[c]); cudaFree(B.UD[c]); cudaFree(B.UB[c]); }
+    for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
+    cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
+    cudaFree(s->mon_idx); cudaFree(s->mon_w); cudaFree(s->series); cudaFree(s->step_dev); cudaFree(s->flags);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+// ---- materials -----------------------------------------------------------------------------
+// ADE coefficients folded in fp64 on the host (SURVEY hard part H4), following
+// meep lorentzian_susceptibility::update_P:
+//   P+ = g1inv * (P (2 - w0^2 dt^2 [lorentz]) - g1 P- + w0^2 dt^2 sigma E)
+static int upload_material_table(sj_sim *s) {
+    std::vector<double> chi(SJ_MAX_MAT, 1.0), coef((size_t)SJ_MAX_MAT * SJ_MAX_POLES * 3, 0.0);
+    std::vector<int> np(SJ_MAX_MAT, 0);
+    int slots = 0;
+    for (size_t m = 0; m < s->mats.size(); ++m) {
+        const sj_material &M = s->mats[m];
+        chi[m] = 1.0 / M.eps_inf;
+        np[m] = M.n_poles;
+        slots = std::max(slots, M.n_poles);
+        for (int q = 0; q < M.n_poles; ++q) {
+            const sj_pole &P = M.poles[q];
+            const double omega2pi = 2 * M_PI * P.omega0, g2pi = P.gamma * 2 * M_PI;
+            const double omega0dtsqr = omega2pi * omega2pi * s->dt * s->dt;
+            const double gamma1inv = 1 / (1 + g2pi * s->dt / 2), gamma1 = (1 - g2pi * s->dt / 2);
+            const double denom = P.drude ? 0 : omega0dtsqr;
+            double *cf = &coef[(m * SJ_MAX_POLES + q) * 3];
+            cf[0] = gamma1inv * (2 - denom);
+            cf[1] = -gamma1inv * gamma1;
+            cf[2] = gamma1inv * omega0dtsqr * P.sigma;
+        }
+    }
+    cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np);
+    s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
+    int rc;
+    if (s->prec == SJ_F64) { rc = upload_vec<double>(s, chi, &s->mt_chi); if (rc) return rc; rc = upload_vec<double>(s, coef, &s->mt_coef); }
+    else { rc = upload_vec<float>(s, chi, &s->mt_chi); if (rc) return rc; rc = upload_vec<float>(s, coef, &s->mt_coef); }
+    if (rc) return rc;
+    CK(cudaMalloc((void **)&s->mt_np, SJ_MAX_MAT * sizeof(int)));
+    CK(cudaMemcpy(s->mt_np, np.data(), SJ_MAX_MAT * sizeof(int), cudaMemcpyHostToDevice));
+    // polarisation slots (dense over the slab; loads are skipped where the material has no pole)
+    const size_t bytes = (size_t)s->set_stride * s->g.n_sets * s->esz;
+    for (int q = s->n_slots; q < slots; ++q)
+        for (int c = 0; c < 3; ++c) {
+            rc = alloc_zero(s, &s->PA[q][c], bytes); if (rc) return rc;
+            rc = alloc_zero(s, &s->PB[q][c], bytes); if (rc) return rc;
+        }
+    s->n_slots = std::max(s->n_slots, slots);
+    return 0;
+}
+
+__global__ void count_pole_points(const uint8_t *mat, const int *np, long long plane, int pitch, int rows, int n0,
+                                  int kl0, int kl1, unsigned long long *out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = plane * (kl1 - kl0);
+    unsigned long long acc = 0;
+    for (; t < tot; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % pitch);
+        if (i <= n0) acc += np[mat[(long long)kl0 * plane + t]];
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+int sj_finish_materials(sj_sim *s) {
+    int rc = upload_material_table(s); if (rc) return rc;
+    unsigned long long *cnt; rc = alloc_zero(s, (void **)&cnt, 8); if (rc) return rc;
+    for (int c = 0; c < 3; ++c)
+        count_pole_points<<<296, 256, 0, s->stream>>>(s->mat[c], s->mt_np, s->plane, s->pitch, s->rows, s->g.n[0], 1,
+                                                       s->nzl - 1, cnt);
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(cnt);
+    s->pole_points = (double)h;
+    s->materials_set = true;
+    return 0;
+}
+
+extern "C" int sj_set_materials(sj_sim *s, int32_t n_mat, const sj_material *mats, const uint8_t *ix, const uint8_t *iy,
+                                const uint8_t *iz) {
+    if (!s || n_mat < 1 || n_mat > SJ_MAX_MAT || !mats) return fail(s, SJ_ERR_ARG, "bad material table");
+    for (int m = 0; m < n_mat; ++m)
+        if (mats[m].n_poles < 0 || mats[m].n_poles > SJ_MAX_POLES || !(mats[m].eps_inf > 0))
+            return fail(s, SJ_ERR_ARG, "material with bad eps_inf or pole count");
+    s->mats.assign(mats, mats + n_mat);
+    const uint8_t *src[3] = {ix, iy, iz};
+    const int nx1 = s->g.n[0] + 1, ny1 = s->g.n[1] + 1;
+    for (int c = 0; c < 3; ++c) {
+        if (!src[c]) { CK(cudaMemset(s->mat[c], 0, (size_t)s->set_stride)); continue; }
+        // owned planes plus halos (clipped to the global grid) from the dense global host array
+        for (int kl = 0; kl < s->nzl; ++kl) {
+            const int k = s->kz0 - 1 + kl;
+            if (k < 0 || k > s->g.n[2]) continue;
+            CK(cudaMemcpy2D(s->mat[c] + (size_t)kl * s->plane, s->pitch, src[c] + (size_t)k * nx1 * ny1, nx1, nx1, ny1,
+                            cudaMemcpyHostToDevice));
+        }
+    }
+    return sj_finish_materials(s);
+}
+
+extern "C" int sj_get_material_table(sj_sim *s, int32_t *n_mat, sj_material *out, int32_t cap) {
+    if (!s || !n_mat) return SJ_ERR_ARG;
+    *n_mat = (int32_t)s->mats.size();
+    for (int i = 0; i < *n_mat && i < cap && out; ++i) out[i] = s->mats[i];
+    return SJ_OK;
+}
+
+extern "C" int sj_get_region_masks(sj_sim *s, int comp, uint8_t *out) {
+    if (!s || comp < 0 || comp > 2 || !out) return SJ_ERR_ARG;
+    const uint8_t *src = s->masks[comp] ? s->masks[comp] : s->mat[comp];
+    const int nx1 = s->g.n[0] + 1, ny1 = s->g.n[1] + 1;
+    CK(cudaStreamSynchronize(s->stream));
+    for (int k = s->kz0; k < s->kz1; ++k)
+        CK(cudaMemcpy2D(out + (size_t)(k - s->kz0) * nx1 * ny1, nx1, src + (size_t)(k - s->kz0 + 1) * s->plane, s->pitch,
+                        nx1, ny1, cudaMemcpyDeviceToHost));
+    return SJ_OK;
+}
+
+// ---- sources -------------------------------------------------------------------------------
+// gaussian_src_time_phase (reference src/disp.cpp:378-400) evaluated on the host in fp64
+static std::complex<double> src_dipole(const HostSource &g, double time) {
+    const double tt = time - g.peak;
+    if (float(fabs(tt)) > g.cutoff) return 0.0;
+    return exp(-tt * tt / (2 * g.width * g.width)) * std::polar(1.0, -g.omega * tt - g.phi) *
+           std::complex<double>(g.amp_t_re, g.amp_t_im);
+}
+
+extern "C" double sj_last_source_time(const sj_sim *s) {
+    double t = 0;
+    for (const auto &g : s->srcs) t = std::max(t, (double)float(g.peak + g.cutoff));
+    return t;
+}
+
+// meep fields::add_volume_source + loop_in_chunks end-point weights for one direction
+static int source_axis(const sj_sim *s, int comp, int d, double lo, double hi, int &a0, int &a1, std::vector<double> &w,
+                       bool &delta) {
+    const double a = s->g.a, inva = s->inva;
+    const int n = s->g.n[d];
+    const int sh = (d == comp) ? 1 : 0, iyc = 1 - sh;
+    const double yc = iyc * (0.5 * inva);
+    const int is = 1 + 2 * (int)floor((lo + yc) * a - .5) - iyc;
+    const int ie = 1 + 2 * (int)ceil((hi + yc) * a - .5) - iyc;
+    const double w0 = 1. - lo * a + 0.5 * is, w1 = 1. + hi * a - 0.5 * ie;
+    double s0, s1, e0, e1;
+    delta = (lo == hi);
+    if (ie >= is + 6) { s0 = w0 * w0 / 2; s1 = 1 - (1 - w0) * (1 - w0) / 2; e0 = w1 * w1 / 2; e1 = 1 - (1 - w1) * (1 - w1) / 2; }
+    else if (ie == is + 4) { s0 = w0 * w0 / 2; s1 = 1 - (1 - w0) * (1 - w0) / 2 - (1 - w1) * (1 - w1) / 2; e0 = w1 * w1 / 2; e1 = s1; }
+    else if (lo == hi) { s0 = w0; s1 = w1; e0 = w1; e1 = w0; }
+    else if (ie == is + 2) { s0 = w0 * w0 / 2 - (1 - w1) * (1 - w1) / 2; e0 = w1 * w1 / 2 - (1 - w0) * (1 - w0) / 2; s1 = e0; e1 = s0; }
+    else return -1;
+    const int own_lo = sh ? 0 : 1, own_hi = n - 1;  // index n is zeroed by the metallic wall
+    const int i0 = (is - sh) / 2, i1 = (ie - sh) / 2;
+    a0 = std::max(i0, own_lo); a1 = std::min(i1, own_hi);
+    w.clear();
+    for (int i = a0; i <= a1; ++i) {
+        const int h = 2 * i + sh;
+        w.push_back(h == is ? s0 : h == is + 2 ? s1 : h == ie ? e0 : h == ie - 2 ? e1 : 1.0);
+    }
+    return 0;
+}
+
+extern "C" int sj_add_gaussian_source(sj_sim *s, int comp, const double lo[3], const double hi[3], double amp_re,
+                                      double amp_im, double freq, double width, double phase, double t_start,
+                                      double t_end, int integrated, const double *set_phase) {
+    if (!s || comp < 0 || comp > 2 || !lo || !hi) return fail(s, SJ_ERR_ARG, "bad source arguments (E components only)");
+    if ((int)s->srcs.size() >= SJ_MAX_SRC) return fail(s, SJ_ERR_ARG, "too many sources");
+    HostSource g;
+    g.comp = comp; g.integrated = integrated;
+    g.omega = 2 * M_PI * freq; g.width = width; g.phi = phase + M_PI;
+    g.peak = 0.5 * (t_start + t_end); g.cutoff = (t_end - t_start) * 0.5;
+    std::complex<double> at = 1.0 / std::complex<double>(0, -g.omega);
+    g.amp_t_re = at.real(); g.amp_t_im = at.imag();
+    while (exp(-g.cutoff * g.cutoff / (2 * g.width * g.width)) < 1e-100) g.cutoff *= 0.9;
+    g.cutoff = float(g.cutoff);
+    std::complex<double> amp(amp_re, amp_im);
+    for (int d = 0; d < 3; ++d) {
+        bool delta;
+        if (source_axis(s, comp, d, lo[d], hi[d], g.lo[d], g.hi[d], g.w[d], delta)) return fail(s, SJ_ERR_ARG, "bad source volume");
+        if (delta) amp *= s->g.a;
+    }
+    g.amp_re = amp.real(); g.amp_im = amp.imag();
+    if (set_phase) g.set_phase.assign(set_phase, set_phase + s->g.n_sets);
+    const int q = (int)s->srcs.size();
+    for (int d = 0; d < 3; ++d) {
+        int rc = s->prec == SJ_F64 ? upload_vec<double>(s, g.w[d], &s->srcw[q][d]) : upload_vec<float>(s, g.w[d], &s->srcw[q][d]);
+        if (rc) return rc;
+    }
+    s->srcs.push_back(g);
+    s->drive_dirty = true;
+    return SJ_OK;
+}
+
+// drive table [step][src][set][2]: {S_n, dt*J_n}; S_n = Re/Im(amp * dipole(n dt)) for integrated
+// sources (meep update_eh), dt*J_n = Re/Im(amp * dt * current(n dt + dt/2)) otherwise (step_source)
+static int ensure_drive(sj_sim *s, long long upto) {
+    if (!s->drive_dirty && upto + 2 <= s->drive_steps) return 0;
+    const long long steps = std::max<long long>(upto + 2, 2 * s->drive_steps);
+    const int ns = (int)s->srcs.size(), nq = s->g.n_sets;
+    std::vector<double> tab((size_t)steps * std::max(ns, 1) * nq * 2, 0.0);
+    for (long long n = 0; n < steps; ++n)
+        for (int q = 0; q < ns; ++q) {
+            const HostSource &g = s->srcs[q];
+            const std::complex<double> amp(g.amp_re, g.amp_im);
+            std::complex<double> S = 0.0, J = 0.0;
+            if (g.integrated) S = src_dipole(g, n * s->dt);
+            else {
+                const double tm = n * s->dt + 0.5 * s->dt;
+                J = ((src_dipole(g, tm + s->dt) - src_dipole(g, tm)) / s->dt) * s->dt;
+            }
+            for (int e = 0; e < nq; ++e) {
+                double *o = &tab[(((size_t)n * ns + q) * nq + e) * 2];
+                if (!g.set_phase.empty()) {
+                    const std::complex<double> ph = std::polar(1.0, -g.set_phase[e]);
+                    o[0] = (amp * S * ph).real(); o[1] = (amp * J * ph).real();
+                } else if (e == 0) { o[0] = (amp * S).real(); o[1] = (amp * J).real(); }
+                else if (e == 1) { o[0] = (amp * S).imag(); o[1] = (amp * J).imag(); }
+            }
+        }
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->drive); s->drive = NULL;
+    int rc = s->prec == SJ_F64 ? upload_vec<double>(s, tab, &s->drive) : upload_vec<float>(s, tab, &s->drive);
+    if (rc) return rc;
+    s->drive_steps = steps; s->drive_dirty = false;
+    return 0;
+}
+
+// ---- monitors --------------------------------------------------------------------------------
+// meep grid_volume::interpolate: linear weights between the two bracketing Yee points per direction
+extern "C" int sj_add_monitors(sj_sim *s, int comp, int32_t n, const double *xyz) {
+    if (!s || comp < 0 || comp > 5 || n < 0 || (n && !xyz)) return fail(s, SJ_ERR_ARG, "bad monitor arguments");
+    if (s->n_mon) return fail(s, SJ_ERR_STATE, "monitors already added");
+    s->n_mon = n; s->mon_comp = comp;
+    s->mon_xyz.assign(xyz, xyz + 3 * (size_t)n);
+    std::vector<long long> idx((size_t)n * 8, -1);
+    std::vector<double> w((size_t)n * 8, 0.0);
+    s->mon_owned.assign(n, 0);
+    const int cdir = comp % 3; const bool isH = comp >= 3;
+    for (int m = 0; m < n; ++m) {
+        int mid[3], sh[3]; double dv[3];
+        for (int d = 0; d < 3; ++d) {
+            sh[d] = isH ? (d != cdir) : (d == cdir);
+            const double pc = xyz[3 * m + d];
+            const double p = (pc - sh[d] * (0.5 * s->inva)) * s->g.a;
+            mid[d] = ((int)floor(p)) * 2 + 1 + sh[d];
+            const double midv = mid[d] * (0.5 * s->inva);
+            dv[d] = (pc - midv) * (2 * s->g.a);
+        }
+        // the rank owning the lower bracketing z plane evaluates the whole stencil (upper plane may be its halo)
+        const int klow = (mid[2] - 1 - sh[2]) / 2;
+        const int kown = std::min(std::max(klow, 0), s->g.n[2]);
+        const bool mine = (kown >= s->kz0 && kown < s->kz1);
+        s->mon_owned[m] = mine;
+        if (!mine) continue;
+        for (int q = 0; q < 8; ++q) {
+            double wt = 1.0; long long lin = 0; bool ok = true;
+            for (int d = 0; d < 3; ++d) {
+                const int up = (q >> d) & 1;
+                const int h = mid[d] + (up ? 1 : -1);
+                wt *= up ? 0.5 * (1.0 + dv[d]) : 0.5 * (1.0 - dv[d]);
+                const int i = (h - sh[d]) / 2;
+                if (h - sh[d] < 0 || i > s->g.n[d]) { ok = false; continue; }
+                if (d == 0) lin += i; else if (d == 1) lin += (long long)i * s->pitch;
+                else { const int kl = i - s->kz0 + 1; if (kl < 0 || kl >= s->nzl) ok = false; else lin += (long long)kl * s->plane; }
+            }
+            if (wt < 0.0) wt = 0.0;
+            if (!ok) wt = 0.0;
+            idx[(size_t)m * 8 + q] = ok ? lin : 0;   // >= 0 marks "owned"; weight 0 drops the point
+            w[(size_t)m * 8 + q] = wt;
+        }
+    }
+    CK(cudaMalloc((void **)&s->mon_idx, std::max<size_t>(idx.size(), 1) * sizeof(long long)));
+    CK(cudaMalloc((void **)&s->mon_w, std::max<size_t>(w.size(), 1) * sizeof(double)));
+    if (n) {
+        CK(cudaMemcpy(s->mon_idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->mon_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return SJ_OK;
+}
+
+static int ensure_series(sj_sim *s, int need) {
+    if (need <= s->series_cap || s->n_mon == 0) return 0;
+    const int cap = std::max(need, 2 * s->series_cap);
+    double *nw;
+    const size_t row = (size_t)s->n_mon * s->g.n_sets;
+    CK(cudaMalloc((void **)&nw, cap * row * sizeof(double)));
+    CK(cudaMemsetAsync(nw, 0, cap * row * sizeof(double), s->stream));
+    if (s->series) CK(cudaMemcpyAsync(nw, s->series, (size_t)s->n_samples * row * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->series);
+    s->series = nw; s->series_cap = cap;
+    return 0;
+}
+
+// ---- kernel parameter assembly + launches ------------------------------------------------------
+template <typename T>
+static void fill_params(const sj_sim *s, KParams<T> &p) {
+    memset(&p, 0, sizeof p);
+    for (int d = 0; d < 3; ++d) p.n[d] = s->g.n[d];
+    p.pitch = s->pitch; p.rows = s->rows; p.plane = s->plane; p.set_stride = s->set_stride;
+    p.kz0 = s->kz0; p.nzl = s->nzl; p.n_sets = s->g.n_sets;
+    for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; }
+    for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { p.PA[q][c] = (T *)s->PA[q][c]; p.PB[q][c] = (T *)s->PB[q][c]; }
+    p.n_slots = s->n_slots;
+    p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef;
+    p.courant = (T)s->g.courant;
+    p.n_src = (int)s->srcs.size();
+    for (int q = 0; q < p.n_src; ++q) {
+        const HostSource &g = s->srcs[q];
+        p.src[q].comp = g.comp;
+        for (int d = 0; d < 3; ++d) { p.src[q].lo[d] = g.lo[d]; p.src[q].hi[d] = g.hi[d]; p.src[q].w[d] = (const T *)s->srcw[q][d]; }
+        p.src[q].amp_re = (T)g.amp_re; p.src[q].amp_im = (T)g.amp_im;
+    }
+    p.drive = (const T *)s->drive;
+    p.step = s->step_dev;
+}
+
+template <typename T>
+static void fill_box(const sj_sim::Box &B, PmlBox<T> &b) {
+    for (int d = 0; d < 3; ++d) { b.lo[d] = B.lo[d]; b.hi[d] = B.hi[d]; }
+    b.bx = B.bx; b.by = B.by; b.bpitch = B.bpitch; b.bplane = B.bplane; b.bset = B.bset;
+    for (int c = 0; c < 3; ++c) { b.D[c] = (T *)B.D[c]; b.B[c] = (T *)B.B[c]; b.UD[c] = (T *)B.UD[c]; b.UB[c] = (T *)B.UB[c]; }
+}
+
+template <typename T, int V>
+static int launch_pass(sj_sim *s, int which, int k_begin, int k_end, cudaStream_t st) {
+    KParams<T> p; fill_params(s, p);
+    k_begin = std::max(k_begin, s->kz0); k_end = std::min(k_end, s->kz1);
+    if (k_begin >= k_end) return 0;
+    // interior box
+    {
+        const int kl = std::max(k_begin, s->lo[2]), kh = std::min(k_end, s->hi[2]);
+        const int ni = s->hi[0] - s->lo[0], nj = s->hi[1] - s->lo[1];
+        if (kl < kh && ni > 0 && nj > 0) {
+            const int by = 8, zchunk = 16;
+            const int nzc = (kh - kl + zchunk - 1) / zchunk;
+            dim3 blk(32, by), grd((ni + 32 * V - 1) / (32 * V), (nj + by - 1) / by, nzc * s->g.n_sets);
+            if (which == 0) h_interior<T, V><<<grd, blk, 0, st>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
+            else e_interior<T, V><<<grd, blk, 0, st>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
+            s->launches++;
+        }
+    }
+    for (const auto &B : s->boxes) {
+        const int kl = std::max(k_begin, B.lo[2]), kh = std::min(k_end, B.hi[2]);
+        if (kl >= kh) continue;
+        PmlBox<T> b; fill_box(B, b);
+        const long long nt = (long long)B.bx * B.by * (kh - kl) * s->g.n_sets;
+        const int grd = (int)((nt + 255) / 256);
+        if (which == 0) h_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
+        else e_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
+        s->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int do_pass(sj_sim *s, int which, int k0, int k1, cudaStream_t st) {
+    return s->prec == SJ_F64 ? launch_pass<double, 2>(s, which, k0, k1, st) : launch_pass<float, 4>(s, which, k0, k1, st);
+}
+
+static int do_sample(sj_sim *s, cudaStream_t st, long long base_step, int base_cursor, int span) {
+    if (s->n_mon == 0) return 0;
+    MonDev m; m.n_mon = s->n_mon; m.comp = s->mon_comp; m.idx = s->mon_idx; m.w = s->mon_w; m.series = s->series; m.flags = s->flags;
+    const int nt = s->n_mon * s->g.n_sets;
+    if (s->prec == SJ_F64) { KParams<double> p; fill_params(s, p); sample_monitors<double><<<(nt + 127) / 128, 128, 0, st>>>(p, m, base_step, base_cursor, span); }
+    else { KParams<float> p; fill_params(s, p); sample_monitors<float><<<(nt + 127) / 128, 128, 0, st>>>(p, m, base_step, base_cursor, span); }
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sj_pass(sj_sim *s, int which, int32_t k0, int32_t k1, void *stream) {
+    if (!s) return SJ_ERR_ARG;
+    int rc = ensure_drive(s, s->steps_done + 1); if (rc) return rc;
+    return do_pass(s, which, k0, k1, stream ? (cudaStream_t)stream : s->stream);
+}
+extern "C" int sj_tick(sj_sim *s, void *stream) {
+    if (!s) return SJ_ERR_ARG;
+    tick_kernel<<<1, 1, 0, stream ? (cudaStream_t)stream : s->stream>>>(s->step_dev);
+    s->steps_done++; s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int sj_sample(sj_sim *s, void *stream) {
+    if (!s) return SJ_ERR_ARG;
+    int rc = ensure_series(s, s->n_samples + 1); if (rc) return rc;
+    rc = do_sample(s, stream ? (cudaStream_t)stream : s->stream, s->steps_done, s->n_samples, 1); if (rc) return rc;
+    s->n_samples++;
+    return 0;
+}
+
+// bound_geom::run loop body (reference src/disp.cpp:719-741)
+extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
+    if (!s || n_steps < 0) return fail(s, SJ_ERR_ARG, "bad step count");
+    if (save_span <= 0) save_span = 1;
+    int rc = ensure_drive(s, s->steps_done + n_steps); if (rc) return rc;
+    const int n_new = (int)((n_steps + save_span - 1) / save_span);
+    rc = ensure_series(s, s->n_samples + n_new); if (rc) return rc;
+    const long long base_step = s->steps_done; const int base_cursor = s->n_samples;
+    for (int64_t i = 0; i < n_steps; ++i) {
+        if (i % save_span == 0) { rc = do_sample(s, s->stream, base_step, base_cursor, save_span); if (rc) return rc; s->n_samples++; }
+        rc = do_pass(s, 0, s->kz0, s->kz1, s->stream); if (rc) return rc;
+        rc = do_pass(s, 1, s->kz0, s->kz1, s->stream); if (rc) return rc;
+        tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev);
+        s->steps_done++; s->launches++;
+    }
+    CK(cudaGetLastError());
+    return SJ_OK;
+}
+
+extern "C" int sj_sync(sj_sim *s) {
+    if (!s) return SJ_ERR_ARG;
+    CK(cudaStreamSynchronize(s->stream));
+    int fl[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(fl, s->flags, sizeof fl, cudaMemcpyDeviceToHost));
+    if (fl[0]) return fail(s, SJ_ERR_DIVERGED, "monitor sample exceeded 1000 or is not finite (divergence)");
+    return SJ_OK;
+}
+extern "C" int64_t sj_steps_done(const sj_sim *s) { return s ? s->steps_done : -1; }
+extern "C" int32_t sj_n_samples(const sj_sim *s) { return s ? s->n_samples : -1; }
+extern "C" double sj_dt(const sj_sim *s) { return s ? s->dt : 0.0; }
+
+extern "C" int sj_read_monitors(sj_sim *s, double *out) {
+    if (!s || !out) return SJ_ERR_ARG;
+    CK(cudaStreamSynchronize(s->stream));
+    const size_t cnt = (size_t)s->n_samples * s->n_mon * s->g.n_sets;
+    if (cnt) CK(cudaMemcpy(out, s->series, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    return SJ_OK;
+}
+
+extern "C" int sj_plane_ptr(sj_sim *s, int comp, int set, int32_t k, void **ptr, size_t *bytes) {
+    if (!s || comp < 0 || comp > 5 || set < 0 || set >= s->g.n_sets || !ptr) return SJ_ERR_ARG;
+    const int kl = k - s->kz0 + 1;
+    if (kl < 0 || kl >= s->nzl) return fail(s, SJ_ERR_ARG, "plane outside local slab");
+    char *base = (char *)(comp < 3 ? s->E[comp] : s->H[comp - 3]);
+    *ptr = base + ((size_t)set * s->set_stride + (size_t)kl * s->plane) * s->esz;
+    if (bytes) *bytes = (size_t)s->plane * s->esz;
+    return SJ_OK;
+}
+
+extern "C" int sj_get_field(sj_sim *s, int comp, int set, double *out) {
+    if (!s || comp < 0 || comp > 5 || set < 0 || set >= s->g.n_sets || !out) return SJ_ERR_ARG;
+    CK(cudaStreamSynchronize(s->stream));
+    const int nx1 = s->g.n[0] + 1, ny1 = s->g.n[1] + 1, nk = s->kz1 - s->kz0;
+    const char *base = (const char *)(comp < 3 ? s->E[comp] : s->H[comp - 3]) + ((size_t)set * s->set_stride + s->plane) * s->esz;
+    if (s->prec == SJ_F64) {
+        for (int k = 0; k < nk; ++k)
+            CK(cudaMemcpy2D(out + (size_t)k * nx1 * ny1, nx1 * 8, base + (size_t)k * s->plane * 8, s->pitch * 8, nx1 * 8, ny1, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<float> tmp((size_t)nx1 * ny1);
+        for (int k = 0; k < nk; ++k) {
+            CK(cudaMemcpy2D(tmp.data(), nx1 * 4, base + (size_t)k * s->plane * 4, s->pitch * 4, nx1 * 4, ny1, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < tmp.size(); ++i) out[(size_t)k * nx1 * ny1 + i] = tmp[i];
+        }
+    }
+    return SJ_OK;
+}
+
+extern "C" int sj_get_stats(const sj_sim *s, int64_t *launches, double *reserved) {
+    if (!s) return SJ_ERR_ARG;
+    if (launches) *launches = s->launches;
+    if (reserved) *reserved = 0.0;
+    return SJ_OK;
+}
+
+// Algorithmic bytes per time step: every field array once per pass
+// (18 s per cell), one material byte per E component, 3 s per pole per E-component point,
+// and ~8 s per PML cell for the auxiliaries; all per field set.
+extern "C" double sj_bytes_per_step(const sj_sim *s) {
+    if (!s) return 0.0;
+    const double cells = (double)s->g.n[0] * s->g.n[1] * (double)std::min(s->kz1 - s->kz0, s->g.n[2]);
+    const double sz = (double)s->esz;
+    return s->g.n_sets * (cells * (18.0 * sz + 3.0) + 3.0 * sz * s->pole_points + 8.0 * sz * s->pml_cells);
+}

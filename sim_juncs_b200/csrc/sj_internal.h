@@ -1,0 +1,126 @@
+// sj_internal.h -- shared declarations of the sim_juncs_b200 engine (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sim_juncs_b200.h"
+
+#define SJ_MAX_SRC 4
+#define SJ_MAX_MAT 256
+#define SJ_N_PML_BOX 6
+
+// ---- kernel parameter blocks (passed by value) ---------------------------------------------
+template <typename T>
+struct SrcDev {
+    int comp;
+    int lo[3], hi[3];     // inclusive index ranges of the component grid (global indices)
+    const T *w[3];        // per-direction weights, w[d][idx - lo[d]]
+    T amp_re, amp_im;     // user amplitude * a^(zero-size dims)
+};
+
+template <typename T>
+struct KParams {
+    int n[3];             // global cells
+    int pitch;            // row pitch in elements
+    int rows;             // n[1] + 1
+    long long plane;      // pitch * rows
+    long long set_stride; // plane * nzl
+    int kz0;              // global k of local plane 1 (local plane 0 is the lower halo)
+    int nzl;              // local planes including both halos
+    int n_sets;
+    T *E[3];
+    T *H[3];
+    const uint8_t *mat[3];
+    T *PA[SJ_MAX_POLES][3];
+    T *PB[SJ_MAX_POLES][3];
+    int n_slots;
+    const T *mt_chi;      // [SJ_MAX_MAT] 1/eps_inf
+    const int *mt_np;     // [SJ_MAX_MAT] number of poles
+    const T *mt_coef;     // [SJ_MAX_MAT][SJ_MAX_POLES][3] a1,a2,a3
+    const T *sig[3];      // PML sigma*dt/2 per half-pixel index, length 2n+2
+    T courant;
+    int n_src;
+    SrcDev<T> src[SJ_MAX_SRC];
+    const T *drive;       // [step][src][set][2] = {S (integrated dipole), dt*current}
+    const long long *step;// device step counter
+};
+
+template <typename T>
+struct PmlBox {
+    int lo[3], hi[3];     // global index box [lo,hi) ; k clipped to the local slab
+    int bx, by;           // box extents in x, y
+    int bpitch;           // row pitch of aux arrays
+    long long bplane;     // bpitch * by
+    long long bset;       // elements per set
+    T *D[3], *B[3], *UD[3], *UB[3];
+};
+
+struct MonDev {
+    int n_mon;
+    int comp;
+    const long long *idx; // [n_mon][8] local linear indices (-1 = skip)
+    const double *w;      // [n_mon][8]
+    double *series;       // [cap][n_mon][n_sets]
+    int *flags;           // [0] = diverged
+};
+
+// ---- host-side state -------------------------------------------------------------------
+struct HostSource {
+    int comp, integrated;
+    double omega, width, phi, peak, cutoff;
+    double amp_t_re, amp_t_im;    // 1/(-i omega)
+    double amp_re, amp_im;
+    int lo[3], hi[3];
+    std::vector<double> w[3];
+    std::vector<double> set_phase;
+};
+
+struct sj_sim {
+    sj_grid g;
+    int prec;                 // SJ_F64 / SJ_F32
+    size_t esz;
+    double inva, dt;
+    int pitch, rows, nzl;
+    long long plane, set_stride;
+    int kz0, kz1;
+    int lo[3], hi[3];         // interior box [lo,hi) in global indices (x aligned)
+    std::vector<double> sig[3];
+
+    void *E[3], *H[3];        // device, [set][local plane][row][pitch]
+    uint8_t *mat[3];
+    uint8_t *masks[3];        // region masks from the rasterizer (same layout)
+    void *PA[SJ_MAX_POLES][3], *PB[SJ_MAX_POLES][3];
+    int n_slots;
+    void *mt_chi, *mt_coef; int *mt_np;
+    void *sigd[3];
+    bool materials_set;
+    std::vector<sj_material> mats;
+
+    struct Box { int lo[3], hi[3]; int bx, by, bz, bpitch; long long bplane, bset; void *D[3], *B[3], *UD[3], *UB[3]; };
+    std::vector<Box> boxes;
+
+    std::vector<HostSource> srcs;
+    void *srcw[SJ_MAX_SRC][3];
+    void *drive; long long drive_steps; bool drive_dirty;
+
+    int n_mon, mon_comp;
+    std::vector<double> mon_xyz;
+    long long *mon_idx; double *mon_w; double *series; int series_cap; int n_samples;
+    std::vector<char> mon_owned;
+    int *flags;
+
+    long long *step_dev;
+    long long steps_done;
+    cudaStream_t stream;
+    long long launches;
+    double pole_points;       // sum over E component points of n_poles (owned slab)
+    double pml_cells;
+    std::string err;
+};
+
+int sj_finish_materials(sj_sim *s);
+// sj_raster.cu
+int sj_raster_launch(sj_sim *s, double ambient_eps, int n_nodes, const sj_csg_node *nodes, int n_regions,
+                     const sj_region *regions);

@@ -1,0 +1,176 @@
+"""Object wrapper over the C ABI (one `Sim` = one sj_sim handle = one GPU, one z-slab)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SjCsgNode, SjGrid, SjMaterial, SjPole, SjRegion
+
+
+class SjError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_pole(omega0, gamma, sigma, drude):
+    p = SjPole()
+    p.omega0, p.gamma, p.sigma, p.drude = float(omega0), float(gamma), float(sigma), int(bool(drude))
+    return p
+
+
+class Sim:
+    def __init__(self, n, a, pml=0.0, courant=0.5, R=1e-15, precision="f64", n_sets=1, kz=None, device=-1):
+        self.L = _lib.load()
+        g = SjGrid()
+        g.n[:] = [int(x) for x in n]
+        g.a, g.courant, g.pml_thickness, g.pml_R = float(a), float(courant), float(pml), float(R)
+        g.precision = _lib.SJ_F32 if precision in ("f32", "fp32", 1) else _lib.SJ_F64
+        g.n_sets = int(n_sets)
+        g.kz0, g.kz1 = (0, 0) if kz is None else (int(kz[0]), int(kz[1]))
+        g.device = int(device)
+        self.n = tuple(int(x) for x in n)
+        self.n_sets = int(n_sets)
+        self.kz = (0, self.n[2] + 1) if kz is None else (int(kz[0]), int(kz[1]))
+        self.h = C.c_void_p()
+        rc = self.L.sj_create(C.byref(g), C.byref(self.h))
+        if rc:
+            msg = self.L.sj_last_error(self.h if self.h else None)
+            if self.h:
+                self.L.sj_destroy(self.h)
+                self.h = None
+            raise SjError("sj_create failed (%d): %s" % (rc, msg.decode() if msg else ""))
+        self.n_mon = 0
+        self.shape = (self.kz[1] - self.kz[0], self.n[1] + 1, self.n[0] + 1)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sj_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise SjError("libsimjuncs_b200 error %d: %s" % (rc, self.L.sj_last_error(self.h).decode()))
+
+    @property
+    def dt(self):
+        return self.L.sj_dt(self.h)
+
+    # ---- materials ----
+    def set_materials(self, mats, idx=None):
+        """mats: list of (eps_inf, [(omega0,gamma,sigma,drude),...]); idx: 3 uint8 arrays over the GLOBAL grid."""
+        arr = (SjMaterial * len(mats))()
+        for m, (eps, poles) in enumerate(mats):
+            arr[m].eps_inf = float(eps)
+            arr[m].n_poles = len(poles)
+            for q, p in enumerate(poles):
+                arr[m].poles[q] = make_pole(*p)
+        ptrs = [None, None, None]
+        keep = []
+        if idx is not None:
+            gshape = (self.n[2] + 1, self.n[1] + 1, self.n[0] + 1)
+            for c in range(3):
+                a = np.ascontiguousarray(idx[c], dtype=np.uint8).reshape(gshape)
+                keep.append(a)
+                ptrs[c] = a.ctypes.data_as(C.POINTER(C.c_uint8))
+        self._ck(self.L.sj_set_materials(self.h, len(mats), arr, ptrs[0], ptrs[1], ptrs[2]))
+
+    def rasterize(self, ambient_eps, nodes, regions):
+        """nodes: ctypes array of SjCsgNode; regions: list of (root, eps, poles)."""
+        reg = (SjRegion * max(len(regions), 1))()
+        for r, (root, eps, poles) in enumerate(regions):
+            reg[r].root = int(root)
+            reg[r].eps = float(eps)
+            reg[r].n_poles = len(poles)
+            for q, p in enumerate(poles):
+                reg[r].poles[q] = make_pole(*p)
+        self._ck(self.L.sj_rasterize(self.h, float(ambient_eps), len(nodes), nodes, len(regions), reg))
+
+    def region_masks(self, comp):
+        out = np.zeros(self.shape, dtype=np.uint8)
+        self._ck(self.L.sj_get_region_masks(self.h, comp, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def material_table(self):
+        n = C.c_int32()
+        arr = (SjMaterial * 256)()
+        self._ck(self.L.sj_get_material_table(self.h, C.byref(n), arr, 256))
+        return [(arr[i].eps_inf, [(arr[i].poles[q].omega0, arr[i].poles[q].gamma, arr[i].poles[q].sigma,
+                                   arr[i].poles[q].drude) for q in range(arr[i].n_poles)]) for i in range(n.value)]
+
+    # ---- sources / monitors ----
+    def add_gaussian_source(self, comp, lo, hi, amp, freq, width, phase, t_start, t_end, integrated=True,
+                            set_phase=None):
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        amp = complex(amp)
+        sp = None
+        if set_phase is not None:
+            spa = np.ascontiguousarray(set_phase, dtype=np.float64)
+            assert spa.size == self.n_sets
+            sp = _dp(spa)
+        self._ck(self.L.sj_add_gaussian_source(self.h, comp, _dp(lo), _dp(hi), amp.real, amp.imag, freq, width, phase,
+                                               t_start, t_end, int(integrated), sp))
+
+    def last_source_time(self):
+        return self.L.sj_last_source_time(self.h)
+
+    def add_monitors(self, xyz, comp=0):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self.n_mon = xyz.shape[0]
+        self._ck(self.L.sj_add_monitors(self.h, comp, self.n_mon, _dp(xyz)))
+
+    # ---- stepping ----
+    def run(self, n_steps, save_span=1, sync=True):
+        self._ck(self.L.sj_run(self.h, int(n_steps), int(save_span)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._ck(self.L.sj_sync(self.h))
+
+    def monitors(self):
+        ns = self.L.sj_n_samples(self.h)
+        out = np.zeros((ns, self.n_mon, self.n_sets))
+        if ns and self.n_mon:
+            self._ck(self.L.sj_read_monitors(self.h, _dp(out)))
+        return out
+
+    def field(self, comp, iset=0):
+        out = np.zeros(self.shape)
+        self._ck(self.L.sj_get_field(self.h, comp, iset, _dp(out)))
+        return out
+
+    def h_pass(self, k0, k1, stream=None):
+        self._ck(self.L.sj_pass(self.h, 0, k0, k1, stream))
+
+    def e_pass(self, k0, k1, stream=None):
+        self._ck(self.L.sj_pass(self.h, 1, k0, k1, stream))
+
+    def tick(self, stream=None):
+        self._ck(self.L.sj_tick(self.h, stream))
+
+    def sample(self, stream=None):
+        self._ck(self.L.sj_sample(self.h, stream))
+
+    def plane_ptr(self, comp, iset, k):
+        p = C.c_void_p()
+        nb = C.c_size_t()
+        self._ck(self.L.sj_plane_ptr(self.h, comp, iset, k, C.byref(p), C.byref(nb)))
+        return p.value, nb.value
+
+    def launches(self):
+        n = C.c_int64()
+        self.L.sj_get_stats(self.h, C.byref(n), None)
+        return n.value
+
+    def bytes_per_step(self):
+        return self.L.sj_bytes_per_step(self.h)
+
+    def steps_done(self):
+        return self.L.sj_steps_done(self.h)
