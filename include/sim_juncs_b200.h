@@ -148,9 +148,25 @@ int sj_sample(sj_sim *sim, void *cuda_stream);      /* sample monitors now */
  * component array of field set `set`. */
 int sj_plane_ptr(sj_sim *sim, int comp, int set, int32_t k, void **dev_ptr, size_t *bytes);
 
+/* Single-process helper for two slabs that are stacked in z (lower.kz1 == upper.kz0), on the same or
+ * on peer devices: which = 0 copies the top owned Hx,Hy planes of `lower` into the lower halo of
+ * `upper` (after an H-pass); which = 1 copies the bottom owned Ex,Ey planes of `upper` into the upper
+ * halo of `lower` (after an E-pass).  Stream-ordered on both simulations' streams. */
+int sj_halo_exchange(sj_sim *lower, sj_sim *upper, int which);
+
 /* ---- inspection ------------------------------------------------------------------------- */
 /* Copy a whole component (owned planes [kz0,kz1), dense (n0+1)(n1+1) rows) to the host as doubles. */
 int sj_get_field(sj_sim *sim, int comp, int set, double *out);
+/* sj_run bracketed by CUDA events on the simulation's stream; *ms = device time of the n_steps. */
+int sj_run_timed(sj_sim *sim, int64_t n_steps, int32_t save_span, double *ms);
+/* Average device time (ms, CUDA events, `reps` back-to-back launches each) of the four kernel
+ * families over the owned slab: out[0] H interior, out[1] E interior, out[2] H PML boxes (all),
+ * out[3] E PML boxes (all).  Advances nothing logically (call on a scratch simulation). */
+int sj_profile_kernels(sj_sim *sim, int32_t reps, double out[4]);
+/* out[0] owned cells, out[1] interior-kernel cells, out[2] PML-kernel cells, out[3] pole-points
+ * (sum over E-component points of n_poles) in the slab, out[4] pole-points inside the interior
+ * box, out[5] true PML cells (any sigma != 0). */
+int sj_get_counts(sj_sim *sim, double out[6]);
 /* Per-run statistics for bench.py: kernels launched and device-timed milliseconds so far. */
 int sj_get_stats(const sj_sim *sim, int64_t *kernel_launches, double *reserved);
 /* Algorithmic bytes one full step moves for this configuration. */

@@ -192,14 +192,17 @@ int main(int argc, char** argv) {
     scene problem(geom, make_context(pml, len, um, out_dir, opts), &er);
     std::vector<composite_object*> roots = problem.get_roots();
 
-    // reference src/disp.cpp:518-525: make_2d roots are rescaled along z before any inside test
+    // reference src/disp.cpp:518-525: make_2d roots are rescaled along z before any inside test.
+    // Only the `points` mode bakes this in (it needs the resolution); `dump` reports the raw tree
+    // plus the make_2d flag and leaves the rescale to the consumer.
     std::vector<double> thick(roots.size(), 1.0);
-    for (size_t i = 0; i < roots.size(); ++i) {
-        if (roots[i]->has_metadata("make_2d") && roots[i]->fetch_metadata("make_2d").val.x != 0) {
-            thick[i] = THICK_SCALE / resolution;
-            roots[i]->rescale(vec3(1.0, 1.0, thick[i]));
+    if (strcmp(mode, "points") == 0)
+        for (size_t i = 0; i < roots.size(); ++i) {
+            if (roots[i]->has_metadata("make_2d") && roots[i]->fetch_metadata("make_2d").val.x != 0) {
+                thick[i] = THICK_SCALE / resolution;
+                roots[i]->rescale(vec3(1.0, 1.0, thick[i]));
+            }
         }
-    }
 
     if (strcmp(mode, "dump") == 0) {
         FILE* fp = payload;

@@ -64,7 +64,11 @@ SYMBOLS = {
     "sj_tick": (C.c_int, [_vp, _vp]),
     "sj_sample": (C.c_int, [_vp, _vp]),
     "sj_plane_ptr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "sj_halo_exchange": (C.c_int, [_vp, _vp, C.c_int]),
     "sj_get_field": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "sj_run_timed": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
+    "sj_profile_kernels": (C.c_int, [_vp, C.c_int32, _dp]),
+    "sj_get_counts": (C.c_int, [_vp, _dp]),
     "sj_get_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), _dp]),
     "sj_bytes_per_step": (C.c_double, [_vp]),
 }

@@ -1,0 +1,141 @@
+"""BoundGeom: host-side mirror of the reference's `bound_geom` (src/disp.hpp:142-200) on top of the
+C ABI.  Same construction order, same unit conversions, same run-loop cadence; the meep objects
+(structure, fields) are replaced by one sj_sim handle."""
+import math
+import os
+import time
+
+import numpy as np
+
+from .engine import Sim
+from .scene import COMPONENTS, LIGHT_SPEED, THICK_SCALE, Scene
+
+
+class BoundGeom:
+    def __init__(self, settings, scene, precision="f64", n_sets=2, integrated=True, device=-1, kz=None,
+                 verbose=False):
+        """settings: ParseSettings (after correct_defaults); scene: Scene or path to a scene JSON.
+        n_sets = 2 reproduces meep's complex fields (the reference never calls use_real_fields)."""
+        if isinstance(scene, str):
+            scene = Scene.load(scene)
+        if scene.ercode != 0:
+            raise RuntimeError("Scene parsing failed (parse_ercode %d)" % scene.ercode)   # disp.cpp:562-565
+        self.problem = scene
+        self.settings = settings
+        self.um_scale = settings.um_scale
+        self.pml_thickness = settings.pml_thickness
+        self.len = settings.len
+        self.save_span = settings.save_span
+        self.dump_raw = bool(settings.dump_raw)
+        self.post_source_t = settings.post_source_t
+        self.n_sets = n_sets
+        if settings.n_dims != 3:
+            raise NotImplementedError("only dimensions = 3 is supported (all shipped junction confs)")
+        if settings.smooth_n != 0:
+            raise NotImplementedError("smooth_n > 0 (stochastic supersampling, disp.cpp:56-112) is not implemented")
+
+        # ---- structure_from_settings (disp.cpp:482-550) ----
+        n = settings.grid_cells()
+        a = settings.resolution
+        self.sim = Sim((n, n, n), a, pml=settings.pml_thickness, precision=precision, n_sets=n_sets, device=device,
+                       kz=kz)
+        nodes = scene.node_array()
+        regions = []
+        self.thicknesses = []
+        for reg in scene.regions:
+            thick = 1.0
+            if reg.make_2d:
+                thick = THICK_SCALE / settings.resolution
+                M = nodes[reg.root].M          # rescale(): trans_mat = trans_mat * diag(1, 1, thick)
+                for i in range(3):
+                    M[3 * i + 0] = M[3 * i + 0] * 1.0
+                    M[3 * i + 1] = M[3 * i + 1] * 1.0
+                    M[3 * i + 2] = M[3 * i + 2] * thick
+            self.thicknesses.append(thick)
+            eps = reg.eps if reg.eps is not None else settings.ambient_eps      # add_region, disp.cpp:249-262
+            poles = [(w0 / settings.um_scale, g / settings.um_scale, sg / thick, not use_denom)
+                     for (w0, g, sg, use_denom) in reg.poles_raw]               # disp.cpp:539-541
+            regions.append((reg.root, eps, poles))
+        t0 = time.time()
+        self.sim.rasterize(settings.ambient_eps, nodes, regions)
+        self.t_raster = time.time() - t0
+
+        # ---- sources and monitors (disp.cpp:584-639) ----
+        self.sources = []
+        self.ttot = 0.0
+        c_by_a = LIGHT_SPEED * settings.um_scale
+        for info, (p1, p2) in zip(scene.sources, scene.source_boxes):
+            lo = [min(p1[d], p2[d]) for d in range(3)]
+            hi = [max(p1[d], p2[d]) for d in range(3)]
+            frequency = 1 / (info.wavelen * settings.um_scale)
+            width = info.width * c_by_a
+            start_time = info.start_time * c_by_a
+            end_time = info.end_time * c_by_a
+            if info.type != "gaussian":
+                raise NotImplementedError("CW_source is not implemented in the CUDA engine yet")
+            if info.component > 2:
+                raise NotImplementedError("magnetic-current sources (%s) are not implemented" % COMPONENTS[info.component])
+            if verbose:
+                print("Adding Gaussian envelope: f=%f, w=%f, t_0=%f, t_f=%f (meep units)" % (frequency, width, start_time, end_time))
+            self.sim.add_gaussian_source(info.component, lo, hi, info.amplitude, frequency, width, info.phase,
+                                         start_time, end_time, integrated)
+            self.sources.append(info)
+            self.ttot = self.sim.last_source_time() + self.post_source_t * LIGHT_SPEED * settings.um_scale
+        self.monitor_locs = [tuple(p) for p in scene.monitor_locs]
+        self.monitor_clusters = list(scene.monitor_clusters)
+        if self.monitor_locs:
+            self.sim.add_monitors(np.array(self.monitor_locs), comp=0)      # always Ex (disp.cpp:724)
+        self.field_times = []
+        self.n_t_pts = 0
+
+    # ---- getters (disp.hpp:146-149) ----
+    def get_monitor_locs(self):
+        return self.monitor_locs
+
+    def get_field_times(self):
+        return self.field_times
+
+    def get_sources(self):
+        return self.sources
+
+    def get_n_monitor_clusters(self):
+        return len(self.monitor_clusters)
+
+    def fs_to_meep_time(self, t):
+        return t * LIGHT_SPEED * self.um_scale
+
+    def meep_time_to_fs(self, t):
+        return t / (LIGHT_SPEED * self.um_scale)
+
+    # ---- run (disp.cpp:690-749) ----
+    def run(self, fname_prefix=None, verbose=False):
+        if self.save_span == 0:
+            self.save_span = 1
+        dt = self.sim.dt
+        self.n_t_pts = int((self.ttot + dt / 2) / dt)
+        t0 = time.time()
+        self.sim.run(self.n_t_pts, self.save_span, sync=False)
+        try:
+            self.sim.sync()
+        except Exception as err:                     # divergence is reported, the save still happens
+            print("error on step %d: %s" % (self.n_t_pts, err))
+        self.t_run = time.time() - t0
+        series = self.sim.monitors()                 # [n_saves][n_mon][n_sets]
+        if self.n_sets >= 2:
+            cplx = series[:, :, 0] + 1j * series[:, :, 1]
+        else:
+            cplx = series[:, :, 0].astype(np.complex128)
+        self.field_times = [cplx[:, j].copy() for j in range(cplx.shape[1])]
+        if verbose:
+            print("Simulations completed")
+
+    def time_bounds(self):
+        """/info/time_bounds (disp.cpp:817-825)."""
+        ttot_fs = self.meep_time_to_fs(self.ttot)
+        return [0.0, ttot_fs, ttot_fs * self.save_span / self.n_t_pts if self.n_t_pts else 0.0]
+
+    def save_field_times(self, fname_prefix):
+        """disp.cpp:758-923.  HDF5 is not available in this image yet: the same datasets
+        are written to <prefix>/field_samples.npz with '/'-separated HDF5 paths as keys."""
+        from .output import save_field_samples
+        return save_field_samples(self, fname_prefix)

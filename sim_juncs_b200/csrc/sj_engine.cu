@@ -77,6 +77,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     sj_sim *s = new sj_sim();
     s->g = *g;
     if (g->device >= 0 && cudaSetDevice(g->device) != cudaSuccess) { delete s; return fail(NULL, SJ_ERR_CUDA, "cudaSetDevice failed"); }
+    if (g->device < 0) cudaGetDevice(&s->g.device);
     s->prec = g->precision == SJ_F32 ? SJ_F32 : SJ_F64;
     s->esz = s->prec == SJ_F64 ? 8 : 4;
     s->g.courant = g->courant > 0 ? g->courant : 0.5;
@@ -101,6 +102,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     *out = s;
 
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
     const int n[3] = {g->n[0], g->n[1], g->n[2]};
     for (int d = 0; d < 3; ++d) {
         build_pml_table(s->sig[d], n[d], g->a, s->dt, g->pml_thickness, s->g.pml_R);
@@ -172,6 +175,7 @@ extern "C" void sj_destroy(sj_sim *s) {
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
     cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
     cudaFree(s->mon_idx); cudaFree(s->mon_w); cudaFree(s->series); cudaFree(s->step_dev); cudaFree(s->flags);
+    cudaEventDestroy(s->ev_a); cudaEventDestroy(s->ev_b);
     cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -220,36 +224,47 @@ static int upload_material_table(sj_sim *s) {
     return 0;
 }
 
-__global__ void count_pole_points(const uint8_t *mat, const int *np, long long plane, int pitch, int rows, int n0,
-                                  int kl0, int kl1, unsigned long long *out) {
+__global__ void count_pole_points(const uint8_t *mat, const int *np, long long plane, int pitch, int i0, int i1, int j0,
+                                  int j1, int kl0, int kl1, unsigned long long *out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long tot = plane * (kl1 - kl0);
     unsigned long long acc = 0;
     for (; t < tot; t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t % pitch);
-        if (i <= n0) acc += np[mat[(long long)kl0 * plane + t]];
+        const int j = (int)((t / pitch) % (plane / pitch));
+        if (i >= i0 && i < i1 && j >= j0 && j < j1) acc += np[mat[(long long)kl0 * plane + t]];
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
-int sj_finish_materials(sj_sim *s) {
-    int rc = upload_material_table(s); if (rc) return rc;
-    unsigned long long *cnt; rc = alloc_zero(s, (void **)&cnt, 8); if (rc) return rc;
+static int count_box(sj_sim *s, int i0, int i1, int j0, int j1, int k0, int k1, double *res) {
+    *res = 0;
+    k0 = std::max(k0, s->kz0); k1 = std::min(k1, s->kz1);
+    if (k0 >= k1) return 0;
+    unsigned long long *cnt; int rc = alloc_zero(s, (void **)&cnt, 8); if (rc) return rc;
     for (int c = 0; c < 3; ++c)
-        count_pole_points<<<296, 256, 0, s->stream>>>(s->mat[c], s->mt_np, s->plane, s->pitch, s->rows, s->g.n[0], 1,
-                                                       s->nzl - 1, cnt);
+        count_pole_points<<<296, 256, 0, s->stream>>>(s->mat[c], s->mt_np, s->plane, s->pitch, i0, i1, j0, j1,
+                                                       k0 - s->kz0 + 1, k1 - s->kz0 + 1, cnt);
     unsigned long long h = 0;
     CK(cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     cudaFree(cnt);
-    s->pole_points = (double)h;
+    *res = (double)h;
+    return 0;
+}
+
+int sj_finish_materials(sj_sim *s) {
+    int rc = upload_material_table(s); if (rc) return rc;
+    rc = count_box(s, 0, s->g.n[0] + 1, 0, s->g.n[1] + 1, s->kz0, s->kz1, &s->pole_points); if (rc) return rc;
+    rc = count_box(s, s->lo[0], s->hi[0], s->lo[1], s->hi[1], s->lo[2], s->hi[2], &s->pole_points_int); if (rc) return rc;
     s->materials_set = true;
     return 0;
 }
 
 extern "C" int sj_set_materials(sj_sim *s, int32_t n_mat, const sj_material *mats, const uint8_t *ix, const uint8_t *iy,
                                 const uint8_t *iz) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s || n_mat < 1 || n_mat > SJ_MAX_MAT || !mats) return fail(s, SJ_ERR_ARG, "bad material table");
     for (int m = 0; m < n_mat; ++m)
         if (mats[m].n_poles < 0 || mats[m].n_poles > SJ_MAX_POLES || !(mats[m].eps_inf > 0))
@@ -278,6 +293,7 @@ extern "C" int sj_get_material_table(sj_sim *s, int32_t *n_mat, sj_material *out
 }
 
 extern "C" int sj_get_region_masks(sj_sim *s, int comp, uint8_t *out) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s || comp < 0 || comp > 2 || !out) return SJ_ERR_ARG;
     const uint8_t *src = s->masks[comp] ? s->masks[comp] : s->mat[comp];
     const int nx1 = s->g.n[0] + 1, ny1 = s->g.n[1] + 1;
@@ -399,6 +415,7 @@ static int ensure_drive(sj_sim *s, long long upto) {
 // ---- monitors --------------------------------------------------------------------------------
 // meep grid_volume::interpolate: linear weights between the two bracketing Yee points per direction
 extern "C" int sj_add_monitors(sj_sim *s, int comp, int32_t n, const double *xyz) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s || comp < 0 || comp > 5 || n < 0 || (n && !xyz)) return fail(s, SJ_ERR_ARG, "bad monitor arguments");
     if (s->n_mon) return fail(s, SJ_ERR_STATE, "monitors already added");
     s->n_mon = n; s->mon_comp = comp;
@@ -541,11 +558,13 @@ static int do_sample(sj_sim *s, cudaStream_t st, long long base_step, int base_c
 }
 
 extern "C" int sj_pass(sj_sim *s, int which, int32_t k0, int32_t k1, void *stream) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s) return SJ_ERR_ARG;
     int rc = ensure_drive(s, s->steps_done + 1); if (rc) return rc;
     return do_pass(s, which, k0, k1, stream ? (cudaStream_t)stream : s->stream);
 }
 extern "C" int sj_tick(sj_sim *s, void *stream) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s) return SJ_ERR_ARG;
     tick_kernel<<<1, 1, 0, stream ? (cudaStream_t)stream : s->stream>>>(s->step_dev);
     s->steps_done++; s->launches++;
@@ -553,6 +572,7 @@ extern "C" int sj_tick(sj_sim *s, void *stream) {
     return 0;
 }
 extern "C" int sj_sample(sj_sim *s, void *stream) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s) return SJ_ERR_ARG;
     int rc = ensure_series(s, s->n_samples + 1); if (rc) return rc;
     rc = do_sample(s, stream ? (cudaStream_t)stream : s->stream, s->steps_done, s->n_samples, 1); if (rc) return rc;
@@ -562,6 +582,7 @@ extern "C" int sj_sample(sj_sim *s, void *stream) {
 
 // bound_geom::run loop body (reference src/disp.cpp:719-741)
 extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s || n_steps < 0) return fail(s, SJ_ERR_ARG, "bad step count");
     if (save_span <= 0) save_span = 1;
     int rc = ensure_drive(s, s->steps_done + n_steps); if (rc) return rc;
@@ -579,7 +600,96 @@ extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
     return SJ_OK;
 }
 
+extern "C" int sj_run_timed(sj_sim *s, int64_t n_steps, int32_t save_span, double *ms) {
+    if (!s || !ms) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
+    int rc = ensure_drive(s, s->steps_done + n_steps); if (rc) return rc;
+    rc = ensure_series(s, s->n_samples + (int)((n_steps + std::max(save_span, 1) - 1) / std::max(save_span, 1))); if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventRecord(e0, s->stream));
+    rc = sj_run(s, n_steps, save_span);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    CK(cudaEventRecord(e1, s->stream));
+    CK(cudaEventSynchronize(e1));
+    float f = 0; CK(cudaEventElapsedTime(&f, e0, e1));
+    *ms = f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return SJ_OK;
+}
+
+template <typename T, int V>
+static int profile_impl(sj_sim *s, int reps, double out[4]) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int rc = ensure_drive(s, s->steps_done + 1); if (rc) return rc;
+    KParams<T> p; fill_params(s, p);
+    const int by = 8, zchunk = 16;
+    const int kl = std::max(s->kz0, s->lo[2]), kh = std::min(s->kz1, s->hi[2]);
+    const int ni = s->hi[0] - s->lo[0], nj = s->hi[1] - s->lo[1];
+    for (int fam = 0; fam < 4; ++fam) {
+        out[fam] = 0.0;
+        for (int rep = -2; rep < reps; ++rep) {          // two untimed warm-up launches
+            if (rep == 0) CK(cudaEventRecord(e0, s->stream));
+            if (fam < 2) {
+                if (kl < kh && ni > 0 && nj > 0) {
+                    const int nzc = (kh - kl + zchunk - 1) / zchunk;
+                    dim3 blk(32, by), grd((ni + 32 * V - 1) / (32 * V), (nj + by - 1) / by, nzc * s->g.n_sets);
+                    if (fam == 0) h_interior<T, V><<<grd, blk, 0, s->stream>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
+                    else e_interior<T, V><<<grd, blk, 0, s->stream>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
+                    s->launches++;
+                }
+            } else {
+                for (const auto &B : s->boxes) {
+                    PmlBox<T> b; fill_box(B, b);
+                    const long long nt = (long long)B.bx * B.by * B.bz * s->g.n_sets;
+                    const int grd = (int)((nt + 255) / 256);
+                    if (fam == 2) h_pml<T><<<grd, 256, 0, s->stream>>>(p, b, B.lo[2], B.hi[2]);
+                    else e_pml<T><<<grd, 256, 0, s->stream>>>(p, b, B.lo[2], B.hi[2]);
+                    s->launches++;
+                }
+            }
+        }
+        CK(cudaEventRecord(e1, s->stream));
+        CK(cudaEventSynchronize(e1));
+        float f = 0; CK(cudaEventElapsedTime(&f, e0, e1));
+        out[fam] = f / std::max(reps, 1);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    return SJ_OK;
+}
+
+extern "C" int sj_profile_kernels(sj_sim *s, int32_t reps, double out[4]) {
+    if (!s || !out || reps < 1) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
+    return s->prec == SJ_F64 ? profile_impl<double, 2>(s, reps, out) : profile_impl<float, 4>(s, reps, out);
+}
+
+extern "C" int sj_get_counts(sj_sim *s, double out[6]) {
+    if (!s || !out) return SJ_ERR_ARG;
+    const int nk = s->kz1 - s->kz0;
+    out[0] = (double)(s->g.n[0] + 1) * (s->g.n[1] + 1) * nk;
+    const int kl = std::max(s->kz0, s->lo[2]), kh = std::min(s->kz1, s->hi[2]);
+    out[1] = (double)std::max(0, s->hi[0] - s->lo[0]) * std::max(0, s->hi[1] - s->lo[1]) * std::max(0, kh - kl);
+    out[2] = s->pml_cells;
+    out[3] = s->pole_points;
+    out[4] = s->pole_points_int;
+    // true PML cells: any of the two half-pixel samples of the index has sigma != 0 in some direction
+    double inter[3];
+    for (int d = 0; d < 3; ++d) {
+        int cnt = 0;
+        const int a0 = d == 2 ? s->kz0 : 0, a1 = d == 2 ? s->kz1 : s->g.n[d] + 1;
+        for (int i = a0; i < a1; ++i) if (s->sig[d][2 * i] == 0.0 && s->sig[d][2 * i + 1] == 0.0) ++cnt;
+        inter[d] = cnt;
+    }
+    out[5] = out[0] - inter[0] * inter[1] * inter[2];
+    return SJ_OK;
+}
+
 extern "C" int sj_sync(sj_sim *s) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s) return SJ_ERR_ARG;
     CK(cudaStreamSynchronize(s->stream));
     int fl[4] = {0, 0, 0, 0};
@@ -592,6 +702,7 @@ extern "C" int32_t sj_n_samples(const sj_sim *s) { return s ? s->n_samples : -1;
 extern "C" double sj_dt(const sj_sim *s) { return s ? s->dt : 0.0; }
 
 extern "C" int sj_read_monitors(sj_sim *s, double *out) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s || !out) return SJ_ERR_ARG;
     CK(cudaStreamSynchronize(s->stream));
     const size_t cnt = (size_t)s->n_samples * s->n_mon * s->g.n_sets;
@@ -609,7 +720,30 @@ extern "C" int sj_plane_ptr(sj_sim *s, int comp, int set, int32_t k, void **ptr,
     return SJ_OK;
 }
 
+extern "C" int sj_halo_exchange(sj_sim *lo, sj_sim *up, int which) {
+    if (!lo || !up || lo->kz1 != up->kz0 || lo->plane != up->plane || lo->esz != up->esz || lo->g.n_sets != up->g.n_sets)
+        return fail(lo ? lo : up, SJ_ERR_ARG, "slabs are not stacked / incompatible");
+    sj_sim *s = lo;
+    cudaSetDevice(which == 0 ? up->g.device : lo->g.device);
+    sj_sim *src = which == 0 ? lo : up, *dst = which == 0 ? up : lo;
+    const int k = which == 0 ? lo->kz1 - 1 : up->kz0;     // global plane that travels
+    const size_t bytes = (size_t)lo->plane * lo->esz;
+    CK(cudaEventRecord(src->ev_a, src->stream));
+    CK(cudaStreamWaitEvent(dst->stream, src->ev_a, 0));
+    for (int set = 0; set < lo->g.n_sets; ++set)
+        for (int c = 0; c < 2; ++c) {
+            void *ps, *pd;
+            int rc = sj_plane_ptr(src, which == 0 ? 3 + c : c, set, k, &ps, NULL); if (rc) return rc;
+            rc = sj_plane_ptr(dst, which == 0 ? 3 + c : c, set, k, &pd, NULL); if (rc) return rc;
+            CK(cudaMemcpyPeerAsync(pd, dst->g.device, ps, src->g.device, bytes, dst->stream));
+        }
+    CK(cudaEventRecord(dst->ev_b, dst->stream));
+    CK(cudaStreamWaitEvent(src->stream, dst->ev_b, 0));
+    return SJ_OK;
+}
+
 extern "C" int sj_get_field(sj_sim *s, int comp, int set, double *out) {
+    if (s) cudaSetDevice(s->g.device);
     if (!s || comp < 0 || comp > 5 || set < 0 || set >= s->g.n_sets || !out) return SJ_ERR_ARG;
     CK(cudaStreamSynchronize(s->stream));
     const int nx1 = s->g.n[0] + 1, ny1 = s->g.n[1] + 1, nk = s->kz1 - s->kz0;
@@ -641,5 +775,6 @@ extern "C" double sj_bytes_per_step(const sj_sim *s) {
     if (!s) return 0.0;
     const double cells = (double)s->g.n[0] * s->g.n[1] * (double)std::min(s->kz1 - s->kz0, s->g.n[2]);
     const double sz = (double)s->esz;
-    return s->g.n_sets * (cells * (18.0 * sz + 3.0) + 3.0 * sz * s->pole_points + 8.0 * sz * s->pml_cells);
+    double cnt[6]; sj_get_counts((sj_sim *)s, cnt);
+    return s->g.n_sets * (cells * (18.0 * sz + 3.0) + 3.0 * sz * s->pole_points + 8.0 * sz * cnt[5]);
 }

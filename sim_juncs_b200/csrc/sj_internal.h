@@ -114,8 +114,10 @@ struct sj_sim {
     long long *step_dev;
     long long steps_done;
     cudaStream_t stream;
+    cudaEvent_t ev_a, ev_b;
     long long launches;
     double pole_points;       // sum over E component points of n_poles (owned slab)
+    double pole_points_int;   // same, restricted to the interior-kernel box
     double pml_cells;
     std::string err;
 };

@@ -208,5 +208,6 @@ int sj_raster_launch(sj_sim *s, double ambient_eps, int n_nodes, const sj_csg_no
 extern "C" int sj_rasterize(sj_sim *s, double ambient_eps, int32_t n_nodes, const sj_csg_node *nodes, int32_t n_regions,
                             const sj_region *regions) {
     if (!s || (n_nodes && !nodes) || (n_regions && !regions)) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
     return sj_raster_launch(s, ambient_eps, n_nodes, nodes, n_regions, regions);
 }

@@ -164,6 +164,28 @@ class Sim:
         self._ck(self.L.sj_plane_ptr(self.h, comp, iset, k, C.byref(p), C.byref(nb)))
         return p.value, nb.value
 
+    @staticmethod
+    def halo_exchange(lower, upper, which):
+        rc = lower.L.sj_halo_exchange(lower.h, upper.h, int(which))
+        if rc:
+            raise SjError("sj_halo_exchange failed %d: %s" % (rc, lower.L.sj_last_error(lower.h).decode()))
+
+    def run_timed(self, n_steps, save_span=1):
+        ms = C.c_double()
+        self._ck(self.L.sj_run_timed(self.h, int(n_steps), int(save_span), C.byref(ms)))
+        return ms.value
+
+    def profile_kernels(self, reps=5):
+        out = (C.c_double * 4)()
+        self._ck(self.L.sj_profile_kernels(self.h, int(reps), out))
+        return dict(h_interior=out[0], e_interior=out[1], h_pml=out[2], e_pml=out[3])
+
+    def counts(self):
+        out = (C.c_double * 6)()
+        self._ck(self.L.sj_get_counts(self.h, out))
+        return dict(cells=out[0], interior_cells=out[1], pml_kernel_cells=out[2], pole_points=out[3],
+                    pole_points_interior=out[4], pml_cells=out[5])
+
     def launches(self):
         n = C.c_int64()
         self.L.sj_get_stats(self.h, C.byref(n), None)

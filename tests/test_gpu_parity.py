@@ -1,0 +1,249 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances (north_star): bit-exact for the voxelization (integer masks); monitor time series
+<= 1e-9 relative L2 in fp64 and <= 1e-4 in fp32.  The fp64 engine is in practice at 1e-13 of the
+oracle, so the fp64 bound asserted here is 1e-11."""
+import numpy as np
+import pytest
+
+from helpers import oracle_bound_geom, region_tables, rel_l2, settings_from_doc
+from oracle.oracle import OracleSim
+from sim_juncs_b200 import Sim
+from sim_juncs_b200.bound_geom import BoundGeom
+from sim_juncs_b200.materials import materials_from_regions
+from sim_juncs_b200.scene import LIGHT_SPEED, Scene
+
+pytestmark = pytest.mark.gpu
+TOL = {"f64": 1e-11, "f32": 1e-4}
+
+
+# ---------------------------------------------------------------- voxelization: bit exact
+@pytest.mark.parametrize("name", ["tests_run_slabs", "Au_SiO2_box", "Au_SiO2_bowtie", "Au_graphene_box"])
+def test_rasterizer_bit_exact(name, scene_json, golden):
+    g = np.load(golden + "/masks_%s.npz" % name)
+    st = settings_from_doc(scene_json(name))
+    bg = BoundGeom(st, scene_json(name), n_sets=1)
+    for comp, key in enumerate(("ex", "ey", "ez")):
+        got = bg.sim.region_masks(comp)
+        assert np.array_equal(got, g[key]), "%s: %d points differ" % (key, int((got != g[key]).sum()))
+    # material table follows in_bound(): ambient counted once per region
+    nreg = len(bg.problem.regions)
+    tab = bg.sim.material_table()
+    assert len(tab) == 1 << nreg and tab[0][0] == st.ambient_eps * max(nreg, 1)
+
+
+def test_rasterizer_slab_equals_global(scene_json, golden):
+    g = np.load(golden + "/masks_Au_graphene_box.npz")
+    st = settings_from_doc(scene_json("Au_graphene_box"))
+    bg = BoundGeom(st, scene_json("Au_graphene_box"), n_sets=1, kz=(60, 121))
+    for comp, key in enumerate(("ex", "ey", "ez")):
+        assert np.array_equal(bg.sim.region_masks(comp), g[key][60:121])
+
+
+# ---------------------------------------------------------------- stepping vs oracle
+def _masks(n, a):
+    shape = (n[2] + 1, n[1] + 1, n[0] + 1)
+    k, j, i = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    ms = []
+    for c in range(3):
+        x = (i + 0.5 * (c == 0)) / a
+        z = (k + 0.5 * (c == 2)) / a
+        r0 = (z > 0.55 * n[2] / a)
+        r1 = (x < 0.45 * n[0] / a) & (z > 0.3 * n[2] / a) & (z <= 0.62 * n[2] / a)
+        ms.append(r0.astype(np.uint8) | (r1.astype(np.uint8) << 1))
+    return ms
+
+
+def _run_pair(n, a, pml, nsets, comp, lo, hi, mats, steps, prec, integrated=True, span=1, probe_step=None):
+    o = OracleSim(n, a, pml=pml, nsets=nsets)
+    g = Sim(n, a, pml=pml, n_sets=nsets, precision=prec)
+    if mats is not None:
+        amb, reps, rpoles, masks = mats
+        o.set_regions(amb, reps, rpoles, masks)
+        g.set_materials(materials_from_regions(amb, reps, rpoles), masks)
+    src = (1.0, 0.4, 1.5, 0.3, 1.0, 1.0 + 12 * 1.5, integrated)
+    o.add_gaussian_source(comp, lo, hi, *src)
+    g.add_gaussian_source(comp, lo, hi, *src)
+    L = [x / a for x in n]
+    mon = [[L[0] / 2, L[1] / 2, L[2] / 2], [L[0] * 0.31, L[1] * 0.77, L[2] * 0.6], [L[0] / 3, L[1], L[2] / 3],
+           [0.01, 0.02, 0.03], [L[0] * 0.5, L[1] * 0.5, 1.0]]
+    o.add_monitors(mon, comp)
+    g.add_monitors(mon, comp)
+    probe_step = probe_step or steps
+    o.run(probe_step, span)
+    g.run(probe_step, span)
+    # whole-field comparison while the pulse is inside the box, each component normalised by the
+    # largest component of its kind (symmetry-forbidden components are pure round-off)
+    ferr = 0.0
+    for kind, off in (("E", 0), ("H", 3)):
+        for q in range(nsets):
+            scale = max(np.linalg.norm(o.field(kind, c, q)) for c in range(3))
+            for c in range(3):
+                ferr = max(ferr, np.linalg.norm(g.field(off + c, q) - o.field(kind, c, q)) / scale)
+    if steps > probe_step:
+        o.run(steps - probe_step, span)
+        g.run(steps - probe_step, span)
+    mo, mg = o.monitors()[:, :, :nsets], g.monitors()
+    assert mo.shape == mg.shape and np.abs(mo).max() > 1e-3
+    return rel_l2(mg, mo), ferr
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("integrated", [True, False])
+def test_vacuum_pml_c1(prec, integrated):
+    # config C1 (tests/run at the unit-test override): 20^3, a = 5, pml 1, Ey plane at z = 1, complex fields
+    merr, ferr = _run_pair((20, 20, 20), 5.0, 1.0, 2, 1, [0, 0, 1], [4, 4, 1], None, 234, prec, integrated, probe_step=80)
+    assert merr < TOL[prec] and ferr < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_dispersive_pml_noncubic(prec):
+    n, a = (44, 36, 40), 8.0
+    lor, dru = (1.1, 0.05, 1.3, 0), (1e-10, 0.04, 2.0e19, 1)
+    mats = (1.0, [2.25, 1.0], [[lor], [dru, (0.9, 0.2, 0.7, 0)]], _masks(n, a))
+    merr, ferr = _run_pair(n, a, 1.0, 2, 0, [0, 0, 1.0], [n[0] / a, n[1] / a, 1.0], mats, 400, prec, span=3, probe_step=150)
+    assert merr < TOL[prec] and ferr < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_dispersive_no_pml_volume_source(prec):
+    n, a = (44, 36, 40), 8.0
+    mats = (1.0, [2.25, 1.0], [[(1.1, 0.05, 1.3, 0)], [(1e-10, 0.04, 2.0e19, 1)]], _masks(n, a))
+    merr, ferr = _run_pair(n, a, 0.0, 1, 2, [1.0, 1.0, 1.0], [2.0, 3.0, 2.2], mats, 150, prec)
+    assert merr < TOL[prec] and ferr < TOL[prec]
+
+
+def test_ragged_grid_sizes():
+    # odd / non-multiple-of-anything extents exercise every tile edge
+    for n in [(21, 23, 25), (33, 20, 47), (70, 21, 22)]:
+        merr, ferr = _run_pair(n, 6.0, 1.0, 1, 0, [0, 0, 1.2], [n[0] / 6.0, n[1] / 6.0, 1.2], None, 120, "f64", probe_step=60)
+        assert merr < 1e-11 and ferr < 1e-11, n
+
+
+# ---------------------------------------------------------------- bound_geom level, reference configs
+def _bound_geom_pair(name, scene_json, prec, max_steps=None):
+    st = settings_from_doc(scene_json(name))
+    sc = Scene.load(scene_json(name))
+    bg = BoundGeom(st, scene_json(name), precision=prec, n_sets=2)
+    masks = [bg.sim.region_masks(c) for c in range(3)]       # bit-exactness is asserted separately
+    o, n_t = oracle_bound_geom(sc, st, masks, nsets=2)
+    dt = bg.sim.dt
+    assert int((bg.ttot + dt / 2) / dt) == n_t
+    if max_steps:
+        n_t = min(n_t, max_steps)
+        bg.ttot = (n_t - 0.25) * dt
+    bg.run()
+    assert bg.n_t_pts == n_t
+    o.run(n_t, st.save_span)
+    series = np.array(bg.get_field_times()).T                  # [saves][mon]
+    mo = o.monitors()
+    return series, mo[:, :, 0] + 1j * mo[:, :, 1], bg
+
+
+def test_tests_run_config(scene_json):
+    """The reference's own end-to-end case (src/main_test.cpp:1884-2028): 20^3, 2 monitors, save_span 1.
+    The reference only pins structure; it records Ex, which is identically zero for its Ey source."""
+    series, ref, bg = _bound_geom_pair("tests_run", scene_json, "f64")
+    assert len(bg.get_field_times()) == 2 == len(bg.get_monitor_locs())
+    assert bg.n_t_pts == 234 and series.shape == (234, 2)          # 234 steps
+    tb = bg.time_bounds()
+    assert tb[0] == 0.0 and tb[0] < tb[2] < tb[1]
+    assert np.abs(series).max() < 1e-12 and np.abs(ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_run_slabs_config(prec, scene_json):
+    """C1': the intended geometry of tests/run.geom (two eps = 3.5 slabs), Ey source; the Ey series is
+    compared because the reference's Ex monitors are identically zero here."""
+    name = "tests_run_slabs"
+    st = settings_from_doc(scene_json(name))
+    sc = Scene.load(scene_json(name))
+    bg = BoundGeom(st, scene_json(name), precision=prec, n_sets=2)          # GPU rasterization
+    masks = [bg.sim.region_masks(c) for c in range(3)]
+    o, n_t = oracle_bound_geom(sc, st, masks, nsets=2, mon_comp=1)
+    s2 = Sim((20, 20, 20), st.resolution, pml=st.pml_thickness, n_sets=2, precision=prec)
+    amb, reps, rpoles = region_tables(sc, st)
+    s2.set_materials(materials_from_regions(amb, reps, rpoles), masks)
+    info, (p1, p2) = sc.sources[0], sc.source_boxes[0]
+    cba = LIGHT_SPEED * st.um_scale
+    s2.add_gaussian_source(info.component, p1, p2, info.amplitude, 1 / (info.wavelen * st.um_scale), info.width * cba,
+                           info.phase, info.start_time * cba, info.end_time * cba, True)
+    s2.add_monitors(np.array(sc.monitor_locs), comp=1)
+    s2.run(n_t, 1)
+    o.run(n_t, 1)
+    mo, mg = o.monitors(), s2.monitors()
+    assert np.abs(mo).max() > 0.05
+    assert rel_l2(mg, mo) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_au_graphene_box_short(prec, scene_json):
+    """configs[1] at its production grid (181^3, Drude Au + graphene sheet + Lorentz SiO2), first 24 steps
+    against the oracle (the oracle needs ~1 s per step at this size)."""
+    series, ref, bg = _bound_geom_pair("Au_graphene_box", scene_json, prec, max_steps=24)
+    assert series.shape == ref.shape and series.shape[1] == 50
+    assert np.abs(ref).max() > 0
+    assert rel_l2(series, ref) < TOL[prec]
+
+
+# ---------------------------------------------------------------- size-independent properties at full size
+def test_slab_decomposition_is_bitwise(scene_json):
+    """Two stacked z-slabs on one GPU with explicit halo exchange == the single-slab run, bit for bit
+    (fields and monitors): the N-GPU path cannot change results."""
+    name = "Au_graphene_box"
+    st = settings_from_doc(scene_json(name))
+    whole = BoundGeom(st, scene_json(name), n_sets=1)
+    n = st.grid_cells()
+    cut = 97
+    lo = BoundGeom(st, scene_json(name), n_sets=1, kz=(0, cut))
+    up = BoundGeom(st, scene_json(name), n_sets=1, kz=(cut, n + 1))
+    steps = 30
+    whole.sim.run(steps, 5)
+    for i in range(steps):
+        if i % 5 == 0:
+            lo.sim.sample()
+            up.sim.sample()
+        for s_ in (lo.sim, up.sim):
+            s_.h_pass(0, n + 1)
+        Sim.halo_exchange(lo.sim, up.sim, 0)
+        for s_ in (lo.sim, up.sim):
+            s_.e_pass(0, n + 1)
+        Sim.halo_exchange(lo.sim, up.sim, 1)
+        lo.sim.tick()
+        up.sim.tick()
+    lo.sim.sync()
+    up.sim.sync()
+    for comp in range(6):
+        w = whole.sim.field(comp)
+        assert np.array_equal(w[:cut], lo.sim.field(comp)) and np.array_equal(w[cut:], up.sim.field(comp)), comp
+    m = lo.sim.monitors() + up.sim.monitors()          # each rank fills the monitors it owns, 0 elsewhere
+    assert np.array_equal(m, whole.sim.monitors())
+
+
+def test_quadrature_sets_are_phase_shifted_copies(scene_json):
+    """Linearity: the Im field set is the Re set of the same run with the source phase
+    shifted by +pi/2."""
+    name = "Au_SiO2_box"
+    st = settings_from_doc(scene_json(name))
+    a = BoundGeom(st, scene_json(name), n_sets=2)
+    sc = Scene.load(scene_json(name))
+    sc.sources[0].phase += np.pi / 2
+    b = BoundGeom(st, sc, n_sets=1)
+    for bg in (a, b):
+        bg.sim.run(700, 20)
+    ma, mb = a.sim.monitors(), b.sim.monitors()
+    assert np.abs(ma[:, :, 1]).max() > 1e-6
+    assert rel_l2(mb[:, :, 0], ma[:, :, 1]) < 1e-12
+
+
+def test_full_run_decays_and_stays_finite(scene_json):
+    """Au_SiO2_box production run (217^3, 3506 steps, 1600 monitors): finite, bounded, and the monitor
+    signal after the pulse has left is far below its peak (PML + lossy media absorb)."""
+    name = "Au_SiO2_box"
+    st = settings_from_doc(scene_json(name))
+    bg = BoundGeom(st, scene_json(name), precision="f32", n_sets=2)
+    bg.run()
+    assert bg.n_t_pts == 3506 and len(bg.get_field_times()) == 1600
+    s = np.abs(np.array(bg.get_field_times()))
+    assert np.isfinite(s).all() and s.max() < 1000
+    assert s[:, -3:].max() < 0.2 * s.max()
