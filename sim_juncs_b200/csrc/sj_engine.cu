@@ -3,6 +3,7 @@
 // A7, A8, M4, M8), device memory, and the step loop of bound_geom::run (src/disp.cpp:719-741).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,6 +59,10 @@ static int upload_vec(sj_sim *s, const std::vector<double> &v, void **dev) {
     return 0;
 }
 static int upload_sig(sj_sim *s, int d) {
+    std::vector<double> inv(s->sig[d].size());
+    for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1 / (1.0 + s->sig[d][i]);   // meep: siginv = 1/(kap+sig)
+    int rc = s->prec == SJ_F64 ? upload_vec<double>(s, inv, &s->siginvd[d]) : upload_vec<float>(s, inv, &s->siginvd[d]);
+    if (rc) return rc;
     return s->prec == SJ_F64 ? upload_vec<double>(s, s->sig[d], &s->sigd[d]) : upload_vec<float>(s, s->sig[d], &s->sigd[d]);
 }
 
@@ -96,7 +101,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->n_mon = 0; s->mon_idx = NULL; s->mon_w = NULL; s->series = NULL; s->series_cap = 0; s->n_samples = 0;
     s->steps_done = 0; s->launches = 0; s->pole_points = 0; s->pml_cells = 0;
     s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
-    for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = NULL; }
+    for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = s->siginvd[c] = NULL; }
+    s->items_wide = s->items_narrow = NULL; s->n_items_wide = s->n_items_narrow = 0;
     for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) s->PA[q][c] = s->PB[q][c] = NULL;
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) s->srcw[q][c] = NULL;
     *out = s;
@@ -155,6 +161,29 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
             s->boxes.push_back(B);
         }
     }
+    // work lists of the tiled PML kernels: one entry per thread block
+    {
+        const int V = s->prec == SJ_F64 ? 2 : 4;
+        std::vector<WorkItem> wide, narrow;
+        const int zchunk = 16;
+        for (size_t bi = 0; bi < s->boxes.size(); ++bi) {
+            const sj_sim::Box &B = s->boxes[bi];
+            const bool nar = (B.bx <= 8 * V);
+            const int tw = (nar ? 8 : 32) * V, th = (nar ? 4 : 1) * 8;
+            for (int q = 0; q < g->n_sets; ++q)
+                for (int kb = B.lo[2]; kb < B.hi[2]; kb += zchunk)
+                    for (int j0 = B.lo[1]; j0 < B.hi[1]; j0 += th)
+                        for (int i0 = B.lo[0]; i0 < B.hi[0]; i0 += tw) {
+                            WorkItem w = {(int)bi, q, i0, j0, kb, std::min(kb + zchunk, B.hi[2])};
+                            (nar ? narrow : wide).push_back(w);
+                        }
+        }
+        s->n_items_wide = (int)wide.size(); s->n_items_narrow = (int)narrow.size();
+        CK(cudaMalloc((void **)&s->items_wide, std::max<size_t>(wide.size(), 1) * sizeof(WorkItem)));
+        CK(cudaMalloc((void **)&s->items_narrow, std::max<size_t>(narrow.size(), 1) * sizeof(WorkItem)));
+        if (!wide.empty()) CK(cudaMemcpy(s->items_wide, wide.data(), wide.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+        if (!narrow.empty()) CK(cudaMemcpy(s->items_narrow, narrow.data(), narrow.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    }
     // default material table: vacuum
     {
         sj_material vac; memset(&vac, 0, sizeof vac); vac.eps_inf = 1.0;
@@ -169,7 +198,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
 extern "C" void sj_destroy(sj_sim *s) {
     if (!s) return;
     cudaStreamSynchronize(s->stream);
-    for (int c = 0; c < 3; ++c) { cudaFree(s->E[c]); cudaFree(s->H[c]); cudaFree(s->mat[c]); cudaFree(s->masks[c]); cudaFree(s->sigd[c]); }
+    for (int c = 0; c < 3; ++c) { cudaFree(s->E[c]); cudaFree(s->H[c]); cudaFree(s->mat[c]); cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
+    cudaFree(s->items_wide); cudaFree(s->items_narrow);
     for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { cudaFree(s->PA[q][c]); cudaFree(s->PB[q][c]); }
     for (auto &B : s->boxes) for (int c = 0; c < 3; ++c) { cudaFree(B.D[c]); cudaFree(B.B[c]); cudaFree(B.UD[c]); cudaFree(B.UB[c]); }
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
@@ -487,7 +517,7 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     for (int d = 0; d < 3; ++d) p.n[d] = s->g.n[d];
     p.pitch = s->pitch; p.rows = s->rows; p.plane = s->plane; p.set_stride = s->set_stride;
     p.kz0 = s->kz0; p.nzl = s->nzl; p.n_sets = s->g.n_sets;
-    for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; }
+    for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; p.siginv[c] = (const T *)s->siginvd[c]; }
     for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { p.PA[q][c] = (T *)s->PA[q][c]; p.PB[q][c] = (T *)s->PB[q][c]; }
     p.n_slots = s->n_slots;
     p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef;
@@ -528,15 +558,32 @@ static int launch_pass(sj_sim *s, int which, int k_begin, int k_end, cudaStream_
             s->launches++;
         }
     }
-    for (const auto &B : s->boxes) {
-        const int kl = std::max(k_begin, B.lo[2]), kh = std::min(k_end, B.hi[2]);
-        if (kl >= kh) continue;
-        PmlBox<T> b; fill_box(B, b);
-        const long long nt = (long long)B.bx * B.by * (kh - kl) * s->g.n_sets;
-        const int grd = (int)((nt + 255) / 256);
-        if (which == 0) h_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
-        else e_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
-        s->launches++;
+    static const bool simple = getenv("SJ_PML_SIMPLE") != NULL;   // per-cell reference kernels (debug A/B)
+    if (simple) {
+        for (const auto &B : s->boxes) {
+            const int kl = std::max(k_begin, B.lo[2]), kh = std::min(k_end, B.hi[2]);
+            if (kl >= kh) continue;
+            PmlBox<T> b; fill_box(B, b);
+            const long long nt = (long long)B.bx * B.by * (kh - kl) * s->g.n_sets;
+            const int grd = (int)((nt + 255) / 256);
+            if (which == 0) h_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
+            else e_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
+            s->launches++;
+        }
+    } else {
+        PmlBoxSet<T> bs;
+        memset(&bs, 0, sizeof bs);
+        for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi]);
+        if (s->n_items_wide) {
+            if (which == 0) h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end);
+            else e_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end);
+            s->launches++;
+        }
+        if (s->n_items_narrow) {
+            if (which == 0) h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end);
+            else e_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end);
+            s->launches++;
+        }
     }
     CK(cudaGetLastError());
     return 0;
@@ -641,12 +688,17 @@ static int profile_impl(sj_sim *s, int reps, double out[4]) {
                     s->launches++;
                 }
             } else {
-                for (const auto &B : s->boxes) {
-                    PmlBox<T> b; fill_box(B, b);
-                    const long long nt = (long long)B.bx * B.by * B.bz * s->g.n_sets;
-                    const int grd = (int)((nt + 255) / 256);
-                    if (fam == 2) h_pml<T><<<grd, 256, 0, s->stream>>>(p, b, B.lo[2], B.hi[2]);
-                    else e_pml<T><<<grd, 256, 0, s->stream>>>(p, b, B.lo[2], B.hi[2]);
+                PmlBoxSet<T> bs;
+                memset(&bs, 0, sizeof bs);
+                for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi]);
+                if (s->n_items_wide) {
+                    if (fam == 2) h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, s->stream>>>(p, bs, s->items_wide, s->kz0, s->kz1);
+                    else e_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, s->stream>>>(p, bs, s->items_wide, s->kz0, s->kz1);
+                    s->launches++;
+                }
+                if (s->n_items_narrow) {
+                    if (fam == 2) h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, s->stream>>>(p, bs, s->items_narrow, s->kz0, s->kz1);
+                    else e_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, s->stream>>>(p, bs, s->items_narrow, s->kz0, s->kz1);
                     s->launches++;
                 }
             }

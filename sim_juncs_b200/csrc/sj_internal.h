@@ -40,6 +40,7 @@ struct KParams {
     const int *mt_np;     // [SJ_MAX_MAT] number of poles
     const T *mt_coef;     // [SJ_MAX_MAT][SJ_MAX_POLES][3] a1,a2,a3
     const T *sig[3];      // PML sigma*dt/2 per half-pixel index, length 2n+2
+    const T *siginv[3];   // 1/(1+sig), meep's siginv table (kappa == 1)
     T courant;
     int n_src;
     SrcDev<T> src[SJ_MAX_SRC];
@@ -56,6 +57,12 @@ struct PmlBox {
     long long bset;       // elements per set
     T *D[3], *B[3], *UD[3], *UB[3];
 };
+
+template <typename T>
+struct PmlBoxSet { PmlBox<T> b[SJ_N_PML_BOX]; };
+
+// one thread block of a PML tile kernel: a (tile_w x tile_h) column of box `box`, planes [kb,ke)
+struct WorkItem { int box, set, i0, j0, kb, ke; };
 
 struct MonDev {
     int n_mon;
@@ -94,7 +101,8 @@ struct sj_sim {
     void *PA[SJ_MAX_POLES][3], *PB[SJ_MAX_POLES][3];
     int n_slots;
     void *mt_chi, *mt_coef; int *mt_np;
-    void *sigd[3];
+    void *sigd[3], *siginvd[3];
+    WorkItem *items_wide, *items_narrow; int n_items_wide, n_items_narrow;
     bool materials_set;
     std::vector<sj_material> mats;
 

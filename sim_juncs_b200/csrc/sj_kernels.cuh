@@ -338,6 +338,215 @@ __global__ void __launch_bounds__(256) e_pml(KParams<T> p, PmlBox<T> b, int k_lo
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// PML shell, tiled: same z-marching / 128-bit / shuffle structure as the interior kernels, plus
+// the box-local auxiliary arrays (D or B always, U where two sigmas overlap) and meep's
+// step_curl / step_update_EDHB arithmetic with the sig / siginv tables.  LX = lanes of a warp
+// along x (32 for the wide z- and y-boxes, 8 for the narrow x-boxes: 4 rows per warp).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu, T *U, long long xb) {
+    if (su != T(0) && sk != T(0)) {
+        const T uo = U[xb];
+        const T un = ((T(1) - sk) * uo - curl) * ik;
+        U[xb] = un;
+        return ((T(1) - su) * fold + (un - uo)) * iu;
+    }
+    if (su != T(0)) return ((T(1) - su) * fold - curl) * iu;
+    return ((T(1) - sk) * fold - curl) * ik;
+}
+
+template <typename T>
+__device__ __forceinline__ void pml_e_elem(const KParams<T> &p, int c, T &e, T &d, T curl, T sk, T ik, T su, T iu, T sw,
+                                           T *U, long long xb, long long x, long long xl, int i, int j, int k, int set,
+                                           long long step, int parity) {
+    const T dold = d;
+    T dnew = pml_step_db(dold, curl, sk, ik, su, iu, U, xb);
+    T S0 = T(0), S1 = T(0), J = T(0);
+    if (p.n_src) source_parts(p, c, i, j, k, set, step, S0, S1, J);
+    dnew -= J;
+    d = dnew;
+    const int m = p.mat[c][xl];
+    const T chi = p.mt_chi[m];
+    T pold = T(0), pnew = T(0);
+    T wold = chi * (dold - S0);
+    const int np = p.mt_np[m];
+    if (np) {
+        T so_ = T(0);
+        for (int s = 0; s < np; ++s) so_ += (parity ? p.PB[s][c] : p.PA[s][c])[x];
+        wold = chi * ((dold - so_) - S0);
+        ade_update(p, c, m, x, parity, wold, &pold, &pnew);
+    }
+    const T wnew = chi * ((dnew - pnew) - S1);
+    e = (sw != T(0)) ? e + (T(1) + sw) * wnew - (T(1) - sw) * wold : wnew;
+}
+
+template <typename T, int V, int LX>
+__global__ void __launch_bounds__(256) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+                                                  int k_lo, int k_hi) {
+    const WorkItem it = items[blockIdx.x];
+    const PmlBox<T> &b = bs.b[it.box];
+    constexpr int RW = 32 / LX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane % LX, ly = lane / LX;
+    const int i0 = it.i0 + lx * V;
+    const int j = it.j0 + warp * RW + ly;
+    const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
+    if (kb >= ke) return;
+    const bool act = (j < b.hi[1]) && (i0 < b.hi[0]);
+    const bool rowp = act && (j + 1 <= p.n[1]);
+    const T C = p.courant;
+    const int set = it.set;
+    const long long so = (long long)set * p.set_stride;
+    const T *Ex = p.E[0] + so, *Ey = p.E[1] + so, *Ez = p.E[2] + so;
+    T *Hx = p.H[0] + so, *Hy = p.H[1] + so, *Hz = p.H[2] + so;
+    long long x = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    long long xb = (long long)set * b.bset + (long long)(kb - b.lo[2]) * b.bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
+    // per-thread PML coefficients along x (per element) and y
+    T sxi[V], ixi[V], sxh[V], ixh[V];
+    T syi = T(0), iyi = T(1), syh = T(0), iyh = T(1);
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int h = 2 * (i0 + v);
+            sxi[v] = p.sig[0][h]; ixi[v] = p.siginv[0][h]; sxh[v] = p.sig[0][h + 1]; ixh[v] = p.siginv[0][h + 1];
+        }
+        syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1];
+    }
+    Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz;
+    if (act) { ex0.load(Ex + x); ey0.load(Ey + x); } else { ex0.zero(); ey0.zero(); }
+    for (int k = kb; k < ke; ++k, x += p.plane, xb += b.bplane) {
+        if (act) {
+            ex1.load(Ex + x + p.plane); ey1.load(Ey + x + p.plane); ez0.load(Ez + x);
+            hx.load(Hx + x); hy.load(Hy + x); hz.load(Hz + x);
+            bx.load(b.B[0] + xb); by.load(b.B[1] + xb); bz.load(b.B[2] + xb);
+        } else { ex1.zero(); ey1.zero(); ez0.zero(); }
+        if (rowp) { ezj.load(Ez + x + p.pitch); exj.load(Ex + x + p.pitch); } else { ezj.zero(); exj.zero(); }
+        T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
+        T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
+        if (act && (lx == LX - 1 || i0 + V >= b.hi[0])) {
+            const bool ok = (i0 + V < p.pitch);
+            ez_n = ok ? Ez[x + V] : T(0);
+            ey_n = ok ? Ey[x + V] : T(0);
+        }
+        if (act) {
+            const T szi = p.sig[2][2 * k], szh = p.sig[2][2 * k + 1], izh = p.siginv[2][2 * k + 1];
+            const bool kok = (k <= p.n[2] - 1), jok = (j <= p.n[1] - 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int i = i0 + v;
+                const T ezi = (v < V - 1) ? ez0.v[v + 1 < V ? v + 1 : v] : ez_n;
+                const T eyi = (v < V - 1) ? ey0.v[v + 1 < V ? v + 1 : v] : ey_n;
+                const bool iok = (i <= p.n[0] - 1);
+                if (i >= 1 && iok && jok && kok) {       // Hx: k-dir y, u-dir z, w-dir x
+                    const T curl = C * (((ezj.v[v] - ez0.v[v]) + ey0.v[v]) - ey1.v[v]);
+                    const T bo = bx.v[v];
+                    const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, b.UB[0], xb + v);
+                    bx.v[v] = bn;
+                    hx.v[v] = (sxi[v] != T(0)) ? hx.v[v] + (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo : bn;
+                }
+                if (j >= 1 && jok && iok && kok) {       // Hy: k-dir z, u-dir x, w-dir y
+                    const T curl = C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
+                    const T bo = by.v[v];
+                    const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], b.UB[1], xb + v);
+                    by.v[v] = bn;
+                    hy.v[v] = (syi != T(0)) ? hy.v[v] + (T(1) + syi) * bn - (T(1) - syi) * bo : bn;
+                }
+                if (k >= 1 && kok && iok && jok) {       // Hz: k-dir x, u-dir y, w-dir z
+                    const T curl = C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
+                    const T bo = bz.v[v];
+                    const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, b.UB[2], xb + v);
+                    bz.v[v] = bn;
+                    hz.v[v] = (szi != T(0)) ? hz.v[v] + (T(1) + szi) * bn - (T(1) - szi) * bo : bn;
+                }
+            }
+            hx.store(Hx + x); hy.store(Hy + x); hz.store(Hz + x);
+            bx.store(b.B[0] + xb); by.store(b.B[1] + xb); bz.store(b.B[2] + xb);
+        }
+        ex0 = ex1; ey0 = ey1;
+    }
+    (void)iyi; (void)ixi;
+}
+
+template <typename T, int V, int LX>
+__global__ void __launch_bounds__(256) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+                                                  int k_lo, int k_hi) {
+    const WorkItem it = items[blockIdx.x];
+    const PmlBox<T> &b = bs.b[it.box];
+    constexpr int RW = 32 / LX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane % LX, ly = lane / LX;
+    const int i0 = it.i0 + lx * V;
+    const int j = it.j0 + warp * RW + ly;
+    const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
+    if (kb >= ke) return;
+    const bool act = (j < b.hi[1]) && (i0 < b.hi[0]);
+    const bool rowm = act && (j >= 1);
+    const T C = p.courant;
+    const int set = it.set;
+    const long long step = *p.step;
+    const int parity = (int)(step & 1);
+    const long long so = (long long)set * p.set_stride;
+    T *Ex = p.E[0] + so, *Ey = p.E[1] + so, *Ez = p.E[2] + so;
+    const T *Hx = p.H[0] + so, *Hy = p.H[1] + so, *Hz = p.H[2] + so;
+    long long x = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    long long xb = (long long)set * b.bset + (long long)(kb - b.lo[2]) * b.bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
+    T sxi[V], ixi[V], sxh[V];
+    T syi = T(0), iyi = T(1), syh = T(0);
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int h = 2 * (i0 + v);
+            sxi[v] = p.sig[0][h]; ixi[v] = p.siginv[0][h]; sxh[v] = p.sig[0][h + 1];
+        }
+        syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1];
+    }
+    Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez, dx, dy, dz;
+    if (act) { hxm.load(Hx + x - p.plane); hym.load(Hy + x - p.plane); } else { hxm.zero(); hym.zero(); }
+    for (int k = kb; k < ke; ++k, x += p.plane, xb += b.bplane) {
+        if (act) {
+            hx0.load(Hx + x); hy0.load(Hy + x); hz0.load(Hz + x);
+            ex.load(Ex + x); ey.load(Ey + x); ez.load(Ez + x);
+            dx.load(b.D[0] + xb); dy.load(b.D[1] + xb); dz.load(b.D[2] + xb);
+        } else { hx0.zero(); hy0.zero(); hz0.zero(); }
+        if (rowm) { hzj.load(Hz + x - p.pitch); hxj.load(Hx + x - p.pitch); } else { hzj.zero(); hxj.zero(); }
+        T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
+        T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
+        if (act && (lx == 0 || i0 == b.lo[0])) {
+            hz_p = (i0 > 0) ? Hz[x - 1] : T(0);
+            hy_p = (i0 > 0) ? Hy[x - 1] : T(0);
+        }
+        if (act) {
+            const T szi = p.sig[2][2 * k], izi = p.siginv[2][2 * k], szh = p.sig[2][2 * k + 1];
+            const bool kin = (k >= 1 && k <= p.n[2] - 1), jin = (j >= 1 && j <= p.n[1] - 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int i = i0 + v;
+                const T hzi = (v > 0) ? hz0.v[v > 0 ? v - 1 : 0] : hz_p;
+                const T hyi = (v > 0) ? hy0.v[v > 0 ? v - 1 : 0] : hy_p;
+                const bool iin = (i >= 1 && i <= p.n[0] - 1);
+                const long long xg = so + x + v, xl = x + v;
+                if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
+                    const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
+                    pml_e_elem(p, 0, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], b.UD[0], xb + v, xg, xl, i, j, k, set, step, parity);
+                }
+                if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
+                    const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
+                    pml_e_elem(p, 1, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, b.UD[1], xb + v, xg, xl, i, j, k, set, step, parity);
+                }
+                if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
+                    const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
+                    pml_e_elem(p, 2, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, b.UD[2], xb + v, xg, xl, i, j, k, set, step, parity);
+                }
+            }
+            ex.store(Ex + x); ey.store(Ey + x); ez.store(Ez + x);
+            dx.store(b.D[0] + xb); dy.store(b.D[1] + xb); dz.store(b.D[2] + xb);
+        }
+        hxm = hx0; hym = hy0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // monitors (fields.get_field -> linear interpolation of <= 8 Yee points), step counter
 // ------------------------------------------------------------------------------------------

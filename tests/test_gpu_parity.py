@@ -148,7 +148,9 @@ def test_tests_run_config(scene_json):
     assert bg.n_t_pts == 234 and series.shape == (234, 2)          # 234 steps
     tb = bg.time_bounds()
     assert tb[0] == 0.0 and tb[0] < tb[2] < tb[1]
-    assert np.abs(series).max() < 1e-12 and np.abs(ref).max() < 1e-12
+    # Ex is symmetry-suppressed (only edge/PML effects of the finite plane source feed it): tiny but not 0
+    assert np.abs(ref).max() < 1e-4
+    assert rel_l2(series, ref) < 1e-9
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
