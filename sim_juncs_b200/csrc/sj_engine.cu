@@ -103,6 +103,9 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
     for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = s->siginvd[c] = NULL; }
     s->items_wide = s->items_narrow = NULL; s->n_items_wide = s->n_items_narrow = 0;
+    s->flags_wide = s->flags_narrow = s->flags_int = NULL;
+    for (int a = 0; a < 2; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; for (int b = 0; b < 2; ++b) { s->il_pml[a][b].dev = NULL; s->il_pml[a][b].n = 0; } } s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
+    for (int i = 0; i < 256; ++i) s->lut_inv[i] = (uint8_t)i;
     for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) s->PA[q][c] = s->PB[q][c] = NULL;
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) s->srcw[q][c] = NULL;
     *out = s;
@@ -121,6 +124,17 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
         while (hi > lo && (s->sig[d][2 * (hi - 1)] != 0.0 || s->sig[d][2 * (hi - 1) + 1] != 0.0)) --hi;
         if (d == 0) { lo = ((lo + 3) / 4) * 4; hi = (hi / 4) * 4; if (hi < lo) hi = lo; }
         s->lo[d] = lo; s->hi[d] = hi;
+    }
+    {   // interior tiling: lanes along x per warp chosen to waste the fewest lanes
+        const int V = s->prec == SJ_F64 ? 2 : 4, ni = std::max(s->hi[0] - s->lo[0], 1);
+        double best = -1;
+        for (int lx = 32; lx >= 8; lx /= 2) {
+            const int tw = lx * V;
+            const double eff = (double)ni / (double)(((ni + tw - 1) / tw) * tw);
+            if (eff > best + 0.04) { best = eff; s->int_lx = lx; }
+        }
+        if (getenv("SJ_INT_LX")) s->int_lx = atoi(getenv("SJ_INT_LX"));
+        if (getenv("SJ_ZCHUNK")) s->int_zchunk = atoi(getenv("SJ_ZCHUNK"));
     }
     const size_t fbytes = (size_t)s->set_stride * g->n_sets * s->esz;
     for (int c = 0; c < 3; ++c) {
@@ -174,11 +188,14 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
                 for (int kb = B.lo[2]; kb < B.hi[2]; kb += zchunk)
                     for (int j0 = B.lo[1]; j0 < B.hi[1]; j0 += th)
                         for (int i0 = B.lo[0]; i0 < B.hi[0]; i0 += tw) {
-                            WorkItem w = {(int)bi, q, i0, j0, kb, std::min(kb + zchunk, B.hi[2])};
+                            WorkItem w = {(int)bi, q, i0, j0, kb, std::min(kb + zchunk, B.hi[2]), 0, 0};
                             (nar ? narrow : wide).push_back(w);
                         }
         }
         s->n_items_wide = (int)wide.size(); s->n_items_narrow = (int)narrow.size();
+        s->h_items_wide = wide; s->h_items_narrow = narrow;
+        CK(cudaMalloc((void **)&s->flags_wide, std::max<size_t>(wide.size(), 1) * sizeof(unsigned)));
+        CK(cudaMalloc((void **)&s->flags_narrow, std::max<size_t>(narrow.size(), 1) * sizeof(unsigned)));
         CK(cudaMalloc((void **)&s->items_wide, std::max<size_t>(wide.size(), 1) * sizeof(WorkItem)));
         CK(cudaMalloc((void **)&s->items_narrow, std::max<size_t>(narrow.size(), 1) * sizeof(WorkItem)));
         if (!wide.empty()) CK(cudaMemcpy(s->items_wide, wide.data(), wide.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
@@ -199,7 +216,8 @@ extern "C" void sj_destroy(sj_sim *s) {
     if (!s) return;
     cudaStreamSynchronize(s->stream);
     for (int c = 0; c < 3; ++c) { cudaFree(s->E[c]); cudaFree(s->H[c]); cudaFree(s->mat[c]); cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
-    cudaFree(s->items_wide); cudaFree(s->items_narrow);
+    cudaFree(s->items_wide); cudaFree(s->items_narrow); cudaFree(s->flags_wide); cudaFree(s->flags_narrow); cudaFree(s->flags_int);
+    for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) cudaFree(s->il_pml[a][b].dev); }
     for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { cudaFree(s->PA[q][c]); cudaFree(s->PB[q][c]); }
     for (auto &B : s->boxes) for (int c = 0; c < 3; ++c) { cudaFree(B.D[c]); cudaFree(B.B[c]); cudaFree(B.UD[c]); cudaFree(B.UB[c]); }
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
@@ -218,8 +236,8 @@ static int upload_material_table(sj_sim *s) {
     std::vector<double> chi(SJ_MAX_MAT, 1.0), coef((size_t)SJ_MAX_MAT * SJ_MAX_POLES * 3, 0.0);
     std::vector<int> np(SJ_MAX_MAT, 0);
     int slots = 0;
-    for (size_t m = 0; m < s->mats.size(); ++m) {
-        const sj_material &M = s->mats[m];
+    for (size_t m = 0; m < s->mats_sorted.size(); ++m) {
+        const sj_material &M = s->mats_sorted[m];
         chi[m] = 1.0 / M.eps_inf;
         np[m] = M.n_poles;
         slots = std::max(slots, M.n_poles);
@@ -284,10 +302,91 @@ static int count_box(sj_sim *s, int i0, int i1, int j0, int j1, int k0, int k1, 
     return 0;
 }
 
+static void interior_geom(const sj_sim *s, int k_begin, int k_end, IntGeom &g, dim3 &grd) {
+    const int V = s->prec == SJ_F64 ? 2 : 4;
+    g.i_lo = s->lo[0]; g.i_hi = s->hi[0]; g.j_lo = s->lo[1]; g.j_hi = s->hi[1];
+    g.k_lo = std::max(s->lo[2], s->kz0); g.k_hi = std::min(s->hi[2], s->kz1);
+    g.zchunk = s->int_zchunk; g.flags = s->flags_int;
+    const int ni = std::max(g.i_hi - g.i_lo, 0), nj = std::max(g.j_hi - g.j_lo, 0);
+    const int tw = s->int_lx * V, th = (32 / s->int_lx) * 8;
+    const int kb = std::max(k_begin, g.k_lo), ke = std::min(k_end, g.k_hi);
+    g.c0 = 0; g.nzc = 0;
+    if (kb < ke) { g.c0 = (kb - g.k_lo) / g.zchunk; g.nzc = (ke - g.k_lo + g.zchunk - 1) / g.zchunk - g.c0; }
+    grd = dim3((ni + tw - 1) / tw, (nj + th - 1) / th, std::max(g.nzc, 0) * s->g.n_sets);
+}
+
 int sj_finish_materials(sj_sim *s) {
+    // sort the table: non-dispersive materials first, so "has poles" is a compare, not a load
+    const int nm = (int)s->mats.size();
+    std::vector<int> order;
+    for (int m = 0; m < nm; ++m) if (s->mats[m].n_poles == 0) order.push_back(m);
+    s->first_disp = (int)order.size();
+    for (int m = 0; m < nm; ++m) if (s->mats[m].n_poles != 0) order.push_back(m);
+    uint8_t lut[256];
+    for (int i = 0; i < 256; ++i) { lut[i] = 0; s->lut_inv[i] = (uint8_t)i; }
+    bool ident = true;
+    std::vector<sj_material> sorted(nm);
+    for (int nw = 0; nw < nm; ++nw) { sorted[nw] = s->mats[order[nw]]; lut[order[nw]] = (uint8_t)nw; s->lut_inv[nw] = (uint8_t)order[nw]; ident &= (order[nw] == nw); }
+    s->mats_sorted = sorted;
+    if (!ident) {
+        uint8_t *dl; CK(cudaMalloc((void **)&dl, 256)); CK(cudaMemcpy(dl, lut, 256, cudaMemcpyHostToDevice));
+        for (int c = 0; c < 3; ++c)
+            remap_bytes<<<(unsigned)((s->set_stride + 255) / 256), 256, 0, s->stream>>>(s->mat[c], s->set_stride, dl);
+        CK(cudaStreamSynchronize(s->stream));
+        cudaFree(dl);
+    }
     int rc = upload_material_table(s); if (rc) return rc;
     rc = count_box(s, 0, s->g.n[0] + 1, 0, s->g.n[1] + 1, s->kz0, s->kz1, &s->pole_points); if (rc) return rc;
     rc = count_box(s, s->lo[0], s->hi[0], s->lo[1], s->hi[1], s->lo[2], s->hi[2], &s->pole_points_int); if (rc) return rc;
+    // block-uniform material flags for the E kernels
+    {
+        const int V = s->prec == SJ_F64 ? 2 : 4;
+        IntGeom g; dim3 grd; interior_geom(s, s->kz0, s->kz1, g, grd);
+        cudaFree(s->flags_int); s->flags_int = NULL;
+        const size_t nfl = (size_t)grd.x * grd.y * std::max(g.nzc, 1);
+        CK(cudaMalloc((void **)&s->flags_int, std::max<size_t>(nfl, 1) * sizeof(unsigned)));
+        if (g.nzc > 0 && grd.x && grd.y) {
+            tile_flags_kernel<<<dim3(grd.x, grd.y, g.nzc), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], g, s->int_lx * V,
+                (32 / s->int_lx) * 8, s->pitch, s->plane, s->kz0, s->first_disp, s->flags_int);
+        }
+        if (s->n_items_wide)
+            item_flags_kernel<<<s->n_items_wide, 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->items_wide, 32 * V, 8,
+                s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, s->flags_wide);
+        if (s->n_items_narrow)
+            item_flags_kernel<<<s->n_items_narrow, 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->items_narrow, 8 * V, 32,
+                s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, s->flags_narrow);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s->stream));
+        // split the E-pass work into "uniform material" and "general" lists (block-uniform fast path)
+        auto upload = [&](ItemList &L, const std::vector<WorkItem> &v) -> int {
+            cudaFree(L.dev); L.dev = NULL; L.n = (int)v.size();
+            CK(cudaMalloc((void **)&L.dev, std::max<size_t>(v.size(), 1) * sizeof(WorkItem)));
+            if (!v.empty()) CK(cudaMemcpy(L.dev, v.data(), v.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+            return 0;
+        };
+        std::vector<WorkItem> lst[2];
+        std::vector<unsigned> fl(std::max<size_t>(nfl, 1));
+        if (nfl) CK(cudaMemcpy(fl.data(), s->flags_int, nfl * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        const int tw = s->int_lx * V, th = (32 / s->int_lx) * 8;
+        for (int q = 0; q < s->g.n_sets; ++q)
+            for (int kc = 0; kc < g.nzc; ++kc)
+                for (unsigned ty = 0; ty < grd.y; ++ty)
+                    for (unsigned tx = 0; tx < grd.x; ++tx) {
+                        const unsigned f = fl[((size_t)kc * grd.y + ty) * grd.x + tx];
+                        WorkItem w = {-1, q, g.i_lo + (int)tx * tw, g.j_lo + (int)ty * th, g.k_lo + kc * g.zchunk,
+                                      std::min(g.k_lo + (kc + 1) * g.zchunk, g.k_hi), (int)(f >> 8), 0};
+                        lst[f & 1u].push_back(w);
+                    }
+        for (int a = 0; a < 2; ++a) { rc = upload(s->il_int[a], lst[a]); if (rc) return rc; }
+        for (int wn = 0; wn < 2; ++wn) {
+            const std::vector<WorkItem> &src = wn == 0 ? s->h_items_wide : s->h_items_narrow;
+            std::vector<unsigned> f2(std::max<size_t>(src.size(), 1));
+            if (!src.empty()) CK(cudaMemcpy(f2.data(), wn == 0 ? s->flags_wide : s->flags_narrow, src.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+            std::vector<WorkItem> l2[2];
+            for (size_t i = 0; i < src.size(); ++i) { WorkItem w = src[i]; w.mat = (int)(f2[i] >> 8); l2[f2[i] & 1u].push_back(w); }
+            for (int a = 0; a < 2; ++a) { rc = upload(s->il_pml[wn][a], l2[a]); if (rc) return rc; }
+        }
+    }
     s->materials_set = true;
     return 0;
 }
@@ -331,6 +430,8 @@ extern "C" int sj_get_region_masks(sj_sim *s, int comp, uint8_t *out) {
     for (int k = s->kz0; k < s->kz1; ++k)
         CK(cudaMemcpy2D(out + (size_t)(k - s->kz0) * nx1 * ny1, nx1, src + (size_t)(k - s->kz0 + 1) * s->plane, s->pitch,
                         nx1, ny1, cudaMemcpyDeviceToHost));
+    if (!s->masks[comp])
+        for (size_t i = 0; i < (size_t)nx1 * ny1 * (s->kz1 - s->kz0); ++i) out[i] = s->lut_inv[out[i]];
     return SJ_OK;
 }
 
@@ -520,7 +621,7 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; p.siginv[c] = (const T *)s->siginvd[c]; }
     for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { p.PA[q][c] = (T *)s->PA[q][c]; p.PB[q][c] = (T *)s->PB[q][c]; }
     p.n_slots = s->n_slots;
-    p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef;
+    p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef; p.first_disp = s->first_disp;
     p.courant = (T)s->g.courant;
     p.n_src = (int)s->srcs.size();
     for (int q = 0; q < p.n_src; ++q) {
@@ -540,51 +641,40 @@ static void fill_box(const sj_sim::Box &B, PmlBox<T> &b) {
     for (int c = 0; c < 3; ++c) { b.D[c] = (T *)B.D[c]; b.B[c] = (T *)B.B[c]; b.UD[c] = (T *)B.UD[c]; b.UB[c] = (T *)B.UB[c]; }
 }
 
+template <typename T, int V, int LX>
+static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_begin, int k_end, cudaStream_t st) {
+    IntGeom g; dim3 grd; interior_geom(s, k_begin, k_end, g, grd);
+    if (g.nzc <= 0 || !grd.x || !grd.y) return;
+    if (which == 0) { h_interior<T, V, LX><<<grd, 256, 0, st>>>(p, g, k_begin, k_end); s->launches++; return; }
+    if (s->il_int[0].n) { e_interior<T, V, LX, false><<<s->il_int[0].n, 256, 0, st>>>(p, g, s->il_int[0].dev, k_begin, k_end); s->launches++; }
+    if (s->il_int[1].n) { e_interior<T, V, LX, true><<<s->il_int[1].n, 256, 0, st>>>(p, g, s->il_int[1].dev, k_begin, k_end); s->launches++; }
+}
+
+template <typename T, int V>
+static void launch_pml(sj_sim *s, const KParams<T> &p, int which, int k_begin, int k_end, cudaStream_t st) {
+    PmlBoxSet<T> bs;
+    memset(&bs, 0, sizeof bs);
+    for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi]);
+    if (which == 0) {
+        if (s->n_items_wide) { h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end); s->launches++; }
+        if (s->n_items_narrow) { h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end); s->launches++; }
+        return;
+    }
+    if (s->il_pml[0][0].n) { e_pml_tile<T, V, 32, false><<<s->il_pml[0][0].n, 256, 0, st>>>(p, bs, s->il_pml[0][0].dev, k_begin, k_end); s->launches++; }
+    if (s->il_pml[0][1].n) { e_pml_tile<T, V, 32, true><<<s->il_pml[0][1].n, 256, 0, st>>>(p, bs, s->il_pml[0][1].dev, k_begin, k_end); s->launches++; }
+    if (s->il_pml[1][0].n) { e_pml_tile<T, V, 8, false><<<s->il_pml[1][0].n, 256, 0, st>>>(p, bs, s->il_pml[1][0].dev, k_begin, k_end); s->launches++; }
+    if (s->il_pml[1][1].n) { e_pml_tile<T, V, 8, true><<<s->il_pml[1][1].n, 256, 0, st>>>(p, bs, s->il_pml[1][1].dev, k_begin, k_end); s->launches++; }
+}
+
 template <typename T, int V>
 static int launch_pass(sj_sim *s, int which, int k_begin, int k_end, cudaStream_t st) {
     KParams<T> p; fill_params(s, p);
     k_begin = std::max(k_begin, s->kz0); k_end = std::min(k_end, s->kz1);
     if (k_begin >= k_end) return 0;
-    // interior box
-    {
-        const int kl = std::max(k_begin, s->lo[2]), kh = std::min(k_end, s->hi[2]);
-        const int ni = s->hi[0] - s->lo[0], nj = s->hi[1] - s->lo[1];
-        if (kl < kh && ni > 0 && nj > 0) {
-            const int by = 8, zchunk = 16;
-            const int nzc = (kh - kl + zchunk - 1) / zchunk;
-            dim3 blk(32, by), grd((ni + 32 * V - 1) / (32 * V), (nj + by - 1) / by, nzc * s->g.n_sets);
-            if (which == 0) h_interior<T, V><<<grd, blk, 0, st>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
-            else e_interior<T, V><<<grd, blk, 0, st>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
-            s->launches++;
-        }
-    }
-    static const bool simple = getenv("SJ_PML_SIMPLE") != NULL;   // per-cell reference kernels (debug A/B)
-    if (simple) {
-        for (const auto &B : s->boxes) {
-            const int kl = std::max(k_begin, B.lo[2]), kh = std::min(k_end, B.hi[2]);
-            if (kl >= kh) continue;
-            PmlBox<T> b; fill_box(B, b);
-            const long long nt = (long long)B.bx * B.by * (kh - kl) * s->g.n_sets;
-            const int grd = (int)((nt + 255) / 256);
-            if (which == 0) h_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
-            else e_pml<T><<<grd, 256, 0, st>>>(p, b, kl, kh);
-            s->launches++;
-        }
-    } else {
-        PmlBoxSet<T> bs;
-        memset(&bs, 0, sizeof bs);
-        for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi]);
-        if (s->n_items_wide) {
-            if (which == 0) h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end);
-            else e_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end);
-            s->launches++;
-        }
-        if (s->n_items_narrow) {
-            if (which == 0) h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end);
-            else e_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end);
-            s->launches++;
-        }
-    }
+    if (s->int_lx == 32) launch_interior<T, V, 32>(s, p, which, k_begin, k_end, st);
+    else if (s->int_lx == 16) launch_interior<T, V, 16>(s, p, which, k_begin, k_end, st);
+    else launch_interior<T, V, 8>(s, p, which, k_begin, k_end, st);
+    launch_pml<T, V>(s, p, which, k_begin, k_end, st);
     CK(cudaGetLastError());
     return 0;
 }
@@ -672,35 +762,16 @@ static int profile_impl(sj_sim *s, int reps, double out[4]) {
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     int rc = ensure_drive(s, s->steps_done + 1); if (rc) return rc;
     KParams<T> p; fill_params(s, p);
-    const int by = 8, zchunk = 16;
-    const int kl = std::max(s->kz0, s->lo[2]), kh = std::min(s->kz1, s->hi[2]);
-    const int ni = s->hi[0] - s->lo[0], nj = s->hi[1] - s->lo[1];
     for (int fam = 0; fam < 4; ++fam) {
         out[fam] = 0.0;
         for (int rep = -2; rep < reps; ++rep) {          // two untimed warm-up launches
             if (rep == 0) CK(cudaEventRecord(e0, s->stream));
             if (fam < 2) {
-                if (kl < kh && ni > 0 && nj > 0) {
-                    const int nzc = (kh - kl + zchunk - 1) / zchunk;
-                    dim3 blk(32, by), grd((ni + 32 * V - 1) / (32 * V), (nj + by - 1) / by, nzc * s->g.n_sets);
-                    if (fam == 0) h_interior<T, V><<<grd, blk, 0, s->stream>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
-                    else e_interior<T, V><<<grd, blk, 0, s->stream>>>(p, s->lo[0], s->hi[0], s->lo[1], s->hi[1], kl, kh, zchunk, nzc);
-                    s->launches++;
-                }
+                if (s->int_lx == 32) launch_interior<T, V, 32>(s, p, fam, s->kz0, s->kz1, s->stream);
+                else if (s->int_lx == 16) launch_interior<T, V, 16>(s, p, fam, s->kz0, s->kz1, s->stream);
+                else launch_interior<T, V, 8>(s, p, fam, s->kz0, s->kz1, s->stream);
             } else {
-                PmlBoxSet<T> bs;
-                memset(&bs, 0, sizeof bs);
-                for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi]);
-                if (s->n_items_wide) {
-                    if (fam == 2) h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, s->stream>>>(p, bs, s->items_wide, s->kz0, s->kz1);
-                    else e_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, s->stream>>>(p, bs, s->items_wide, s->kz0, s->kz1);
-                    s->launches++;
-                }
-                if (s->n_items_narrow) {
-                    if (fam == 2) h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, s->stream>>>(p, bs, s->items_narrow, s->kz0, s->kz1);
-                    else e_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, s->stream>>>(p, bs, s->items_narrow, s->kz0, s->kz1);
-                    s->launches++;
-                }
+                launch_pml<T, V>(s, p, fam - 2, s->kz0, s->kz1, s->stream);
             }
         }
         CK(cudaEventRecord(e1, s->stream));

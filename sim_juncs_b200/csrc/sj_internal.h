@@ -38,6 +38,7 @@ struct KParams {
     int n_slots;
     const T *mt_chi;      // [SJ_MAX_MAT] 1/eps_inf
     const int *mt_np;     // [SJ_MAX_MAT] number of poles
+    int first_disp;       // material ids >= first_disp have poles (table is sorted that way)
     const T *mt_coef;     // [SJ_MAX_MAT][SJ_MAX_POLES][3] a1,a2,a3
     const T *sig[3];      // PML sigma*dt/2 per half-pixel index, length 2n+2
     const T *siginv[3];   // 1/(1+sig), meep's siginv table (kappa == 1)
@@ -46,6 +47,13 @@ struct KParams {
     SrcDev<T> src[SJ_MAX_SRC];
     const T *drive;       // [step][src][set][2] = {S (integrated dipole), dt*current}
     const long long *step;// device step counter
+};
+
+// interior box + its fixed z-chunk grid (chunk c covers [k_lo + c*zchunk, k_lo + (c+1)*zchunk))
+struct IntGeom {
+    int i_lo, i_hi, j_lo, j_hi, k_lo, k_hi;
+    int zchunk, nzc, c0;        // chunks launched: c0 .. c0+nzc-1
+    const unsigned *flags;      // [chunk][tile_y][tile_x] material flags (e_interior)
 };
 
 template <typename T>
@@ -62,7 +70,8 @@ template <typename T>
 struct PmlBoxSet { PmlBox<T> b[SJ_N_PML_BOX]; };
 
 // one thread block of a PML tile kernel: a (tile_w x tile_h) column of box `box`, planes [kb,ke)
-struct WorkItem { int box, set, i0, j0, kb, ke; };
+struct WorkItem { int box, set, i0, j0, kb, ke, mat, pad; };   // mat: uniform material id (fast-path lists)
+struct ItemList { WorkItem *dev; int n; };
 
 struct MonDev {
     int n_mon;
@@ -103,8 +112,15 @@ struct sj_sim {
     void *mt_chi, *mt_coef; int *mt_np;
     void *sigd[3], *siginvd[3];
     WorkItem *items_wide, *items_narrow; int n_items_wide, n_items_narrow;
+    unsigned *flags_wide, *flags_narrow, *flags_int;
+    std::vector<WorkItem> h_items_wide, h_items_narrow;
+    ItemList il_int[2], il_pml[2][2];   // E-pass lists: [uniform|general], PML: [wide|narrow][uniform|general]
+    int int_lx, int_zchunk;   // interior tiling: lanes along x per warp, planes per chunk
+    int first_disp;
+    uint8_t lut_inv[256];     // material id -> id as given by the caller
     bool materials_set;
-    std::vector<sj_material> mats;
+    std::vector<sj_material> mats;         // as given by the caller / rasterizer (id = caller id)
+    std::vector<sj_material> mats_sorted;  // device order: non-dispersive first
 
     struct Box { int lo[3], hi[3]; int bx, by, bz, bpitch; long long bplane, bset; void *D[3], *B[3], *UD[3], *UB[3]; };
     std::vector<Box> boxes;

@@ -4,19 +4,24 @@
 //   H-pass : B -= C curl E (M1) fused with H = mu^-1 B and the UPML auxiliaries (M2)
 //   E-pass : D += C curl H (M3) + source injection (M4) + Drude-Lorentz ADE (M5) +
 //            E = chi1inv (D - sum P) (M6), UPML auxiliaries fused
-// Interior cells (all PML sigmas zero) run the *_interior kernels: z-marching 2.5-D tiles,
-// 128-bit row loads, the k+-1 plane carried in registers, i+-1 neighbours by warp shuffle.  They
-// keep only E and H: E^{n+1} = E^n + chi1inv (dD - dP - dS), algebraically meep's
-// E = chi1inv (D - P - S) with D eliminated.  The PML shell (six boxes) runs the *_pml kernels,
-// which hold D/B (and U where two sigmas overlap) in compact per-box arrays and follow meep's
-// step_curl / step_update_EDHB formulas.
+// All kernels share one structure: a thread block owns an xy tile and marches along z over a chunk
+// of planes; every row access is a 128-bit load/store; the k-1 / k+1 plane is carried in registers;
+// the i-1 / i+1 neighbour comes from the adjacent lane by warp shuffle (one scalar load per tile
+// edge).  LX = lanes of a warp along x (32, 16 or 8; the warp covers 32/LX rows) so that narrow
+// regions still fill their warps.
+//   *_interior : cells where every PML sigma is zero.  Only E and H exist there:
+//                E^{n+1} = E^n + chi1inv (dD - dP - dS), algebraically meep's E = chi1inv (D - P - S).
+//                A per-(tile,chunk) flag selects a uniform-material fast path (no material bytes
+//                read, no ADE code) -- block-uniform, no divergence.
+//   *_pml_tile : the PML shell (six boxes), driven by a work list.  Box-local auxiliary arrays hold
+//                D / B (and U where two sigmas overlap); arithmetic follows meep's step_curl /
+//                step_update_EDHB with the sig / siginv tables.
 #pragma once
 #include "sj_internal.h"
 
 template <typename T, int V> struct VecOf;
 template <> struct VecOf<double, 2> { typedef double2 type; };
 template <> struct VecOf<float, 4> { typedef float4 type; };
-template <> struct VecOf<float, 2> { typedef float2 type; };
 
 template <typename T, int V>
 struct Vec {
@@ -42,32 +47,30 @@ struct Vec {
     }
 };
 
-// Source amplitude at a Yee point of component c: amp * wx * wy * wz, for set q the real drive
-// pair {dS, dt*J}.  Returns the D-side increment  -(A dS) - (A dtJ)  to add to dD.
-template <typename T>
-__device__ __forceinline__ T source_term(const KParams<T> &p, int c, int i, int j, int k, int set, long long step) {
-    T acc = T(0);
-    for (int s = 0; s < p.n_src; ++s) {
-        const SrcDev<T> &g = p.src[s];
-        if (g.comp != c) continue;
-        if (k < g.lo[2] || k > g.hi[2] || j < g.lo[1] || j > g.hi[1] || i < g.lo[0] || i > g.hi[0]) continue;
-        const T wgt = g.w[0][i - g.lo[0]] * g.w[1][j - g.lo[1]] * g.w[2][k - g.lo[2]];
-        const T *d0 = p.drive + ((step * p.n_src + s) * p.n_sets + set) * 2;
-        const T *d1 = d0 + (long long)p.n_src * p.n_sets * 2;
-        // integrated sources: S_{n+1} - S_n ; current sources: dt*J_n
-        acc -= wgt * ((d1[0] - d0[0]) + d0[1]);
-    }
-    return acc;
+template <int V>
+__device__ __forceinline__ void load_bytes(const uint8_t *p, unsigned char (&m)[V]) {
+    if (V == 2) { const uchar2 t = *reinterpret_cast<const uchar2 *>(p); m[0] = t.x; m[1] = t.y; }
+    else { const uchar4 t = *reinterpret_cast<const uchar4 *>(p); m[0] = t.x; m[1] = t.y; m[V > 2 ? 2 : 0] = t.z; m[V > 3 ? 3 : 0] = t.w; }
 }
-// Same, but split into the "S" part at step n, at n+1 and the current kick (PML kernels need W_old).
+
+// ---- sources ---------------------------------------------------------------------------------
+// bit s of the result: source s touches plane k (block-uniform test, a few scalar instructions)
 template <typename T>
-__device__ __forceinline__ void source_parts(const KParams<T> &p, int c, int i, int j, int k, int set, long long step,
-                                             T &S0, T &S1, T &J) {
+__device__ __forceinline__ unsigned src_plane_mask(const KParams<T> &p, int k) {
+    unsigned m = 0;
+    for (int s = 0; s < p.n_src; ++s)
+        if (k >= p.src[s].lo[2] && k <= p.src[s].hi[2]) m |= 1u << s;
+    return m;
+}
+// S_n, S_{n+1} (integrated dipole) and dt*J_n (current) weights at a Yee point of component c
+template <typename T>
+__device__ __forceinline__ void source_parts(const KParams<T> &p, unsigned smask, int c, int i, int j, int k, int set,
+                                             long long step, T &S0, T &S1, T &J) {
     S0 = S1 = J = T(0);
     for (int s = 0; s < p.n_src; ++s) {
+        if (!((smask >> s) & 1u)) continue;
         const SrcDev<T> &g = p.src[s];
-        if (g.comp != c) continue;
-        if (k < g.lo[2] || k > g.hi[2] || j < g.lo[1] || j > g.hi[1] || i < g.lo[0] || i > g.hi[0]) continue;
+        if (g.comp != c || j < g.lo[1] || j > g.hi[1] || i < g.lo[0] || i > g.hi[0]) continue;
         const T wgt = g.w[0][i - g.lo[0]] * g.w[1][j - g.lo[1]] * g.w[2][k - g.lo[2]];
         const T *d0 = p.drive + ((step * p.n_src + s) * p.n_sets + set) * 2;
         const T *d1 = d0 + (long long)p.n_src * p.n_sets * 2;
@@ -75,11 +78,10 @@ __device__ __forceinline__ void source_parts(const KParams<T> &p, int c, int i, 
     }
 }
 
-// ADE update of all poles of material m at linear index x (M5): returns sum(P_new - P_cur) and
-// optionally sum P_cur / sum P_new.  `drive` is E^n (W^n inside the PML).
+// ---- ADE (M5): all poles of material m at linear index x; `drive` is E^n (W^n inside the PML) ----
 template <typename T>
-__device__ __forceinline__ T ade_update(const KParams<T> &p, int c, int m, long long x, int parity, T drive,
-                                        T *sum_old, T *sum_new) {
+__device__ __forceinline__ T ade_update(const KParams<T> &p, int c, int m, long long x, int parity, T drive, T &sum_old,
+                                        T &sum_new) {
     const int np = p.mt_np[m];
     T dP = T(0), so = T(0), sn = T(0);
     for (int s = 0; s < np; ++s) {
@@ -91,47 +93,60 @@ __device__ __forceinline__ T ade_update(const KParams<T> &p, int c, int m, long 
         prv[x] = pn;  // becomes "current" after the parity flip
         dP += pn - pc; so += pc; sn += pn;
     }
-    if (sum_old) *sum_old = so;
-    if (sum_new) *sum_new = sn;
+    sum_old = so; sum_new = sn;
     return dP;
 }
 
+// One E component element of the interior (E-only) update.
+template <typename T, bool GEN>
+__device__ __forceinline__ void e_elem_interior(const KParams<T> &p, int c, T &e, T dD, int m, T chi_u, long long xg,
+                                                int parity) {
+    if (GEN) {
+        const T chi = p.mt_chi[m];
+        T dP = T(0);
+        if (m >= p.first_disp) { T so, sn; dP = ade_update(p, c, m, xg, parity, e, so, sn); }
+        e += chi * (dD - dP);
+    } else {
+        e += chi_u * dD;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
-// Interior H-pass.  Block = 32 lanes (x, V cells each) x blockDim.y rows; marches k over a chunk.
+// Interior H-pass
 // ------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(256) h_interior(KParams<T> p, int i_lo, int i_hi, int j_lo, int j_hi, int k_lo,
-                                                  int k_hi, int zchunk, int nzc) {
-    const int lane = threadIdx.x;
-    const int i0 = i_lo + (blockIdx.x * 32 + lane) * V;
-    const int j = j_lo + blockIdx.y * blockDim.y + threadIdx.y;
-    const int set = blockIdx.z / nzc;
-    const int kb = k_lo + (blockIdx.z % nzc) * zchunk;
-    const int ke = min(kb + zchunk, k_hi);
-    if (j >= j_hi) return;  // whole warp shares j: warp-uniform exit keeps shuffles legal
-    const bool ld = (i0 + V <= p.pitch);
-    const bool st = (i0 < i_hi);
+template <typename T, int V, int LX>
+__global__ void __launch_bounds__(256, 4) h_interior(KParams<T> p, IntGeom g, int k_begin, int k_end) {
+    constexpr int RW = 32 / LX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane % LX, ly = lane / LX;
+    const int i0 = g.i_lo + (blockIdx.x * LX + lx) * V;
+    const int j = g.j_lo + (blockIdx.y * 8 + warp) * RW + ly;
+    const int set = blockIdx.z / g.nzc;
+    const int kc = g.c0 + blockIdx.z % g.nzc;
+    const int kb = max(g.k_lo + kc * g.zchunk, k_begin);
+    const int ke = min(min(g.k_lo + (kc + 1) * g.zchunk, g.k_hi), k_end);
+    if (kb >= ke) return;
+    const bool ld = (j < g.j_hi) && (i0 + V <= p.pitch);
+    const bool st = (j < g.j_hi) && (i0 < g.i_hi);
     const T C = p.courant;
-    const long long so = (long long)set * p.set_stride;
-    const T *Ex = p.E[0] + so, *Ey = p.E[1] + so, *Ez = p.E[2] + so;
-    T *Hx = p.H[0] + so, *Hy = p.H[1] + so, *Hz = p.H[2] + so;
-    long long x = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    const long long x0 = (long long)set * p.set_stride + (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    const T *pEx = p.E[0] + x0, *pEy = p.E[1] + x0, *pEz = p.E[2] + x0;
+    T *pHx = p.H[0] + x0, *pHy = p.H[1] + x0, *pHz = p.H[2] + x0;
+    const long long plane = p.plane;
+    const int pitch = p.pitch;
+    const bool edge = st && (lx == LX - 1) && (i0 + V < pitch);
 
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz;
-    if (ld) { ex0.load(Ex + x); ey0.load(Ey + x); } else { ex0.zero(); ey0.zero(); }
-    for (int k = kb; k < ke; ++k, x += p.plane) {
+    if (ld) { ex0.load(pEx); ey0.load(pEy); } else { ex0.zero(); ey0.zero(); }
+    for (int k = kb; k < ke; ++k) {
         if (ld) {
-            ex1.load(Ex + x + p.plane); ey1.load(Ey + x + p.plane);
-            ez0.load(Ez + x); ezj.load(Ez + x + p.pitch); exj.load(Ex + x + p.pitch);
+            ex1.load(pEx + plane); ey1.load(pEy + plane);
+            ez0.load(pEz); ezj.load(pEz + pitch); exj.load(pEx + pitch);
         } else { ex1.zero(); ey1.zero(); ez0.zero(); ezj.zero(); exj.zero(); }
-        if (st) { hx.load(Hx + x); hy.load(Hy + x); hz.load(Hz + x); }
-        T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1);
-        T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1);
-        if (lane == 31 && st) {
-            const bool ok = (i0 + V < p.pitch);
-            ez_n = ok ? Ez[x + V] : T(0);
-            ey_n = ok ? Ey[x + V] : T(0);
-        }
+        if (st) { hx.load(pHx); hy.load(pHy); hz.load(pHz); }
+        T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
+        T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
+        if (edge) { ez_n = pEz[V]; ey_n = pEy[V]; }
         if (st) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -141,54 +156,49 @@ __global__ void __launch_bounds__(256) h_interior(KParams<T> p, int i_lo, int i_
                 hy.v[v] -= C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
                 hz.v[v] -= C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
             }
-            hx.store(Hx + x); hy.store(Hy + x); hz.store(Hz + x);
+            hx.store(pHx); hy.store(pHy); hz.store(pHz);
         }
         ex0 = ex1; ey0 = ey1;
+        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Interior E-pass.
+// Interior E-pass
 // ------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(256) e_interior(KParams<T> p, int i_lo, int i_hi, int j_lo, int j_hi, int k_lo,
-                                                  int k_hi, int zchunk, int nzc) {
-    const int lane = threadIdx.x;
-    const int i0 = i_lo + (blockIdx.x * 32 + lane) * V;
-    const int j = j_lo + blockIdx.y * blockDim.y + threadIdx.y;
-    const int set = blockIdx.z / nzc;
-    const int kb = k_lo + (blockIdx.z % nzc) * zchunk;
-    const int ke = min(kb + zchunk, k_hi);
-    if (j >= j_hi) return;
-    const bool ld = (i0 + V <= p.pitch);
-    const bool st = (i0 < i_hi);
+template <typename T, int V, int LX, bool GEN>
+__device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGeom &g, int i0, int j, int lx, int set, int kb,
+                                                int ke, T chi_u) {
+    const bool ld = (j < g.j_hi) && (i0 + V <= p.pitch);
+    const bool st = (j < g.j_hi) && (i0 < g.i_hi);
     const T C = p.courant;
     const long long step = *p.step;
     const int parity = (int)(step & 1);
-    const long long so = (long long)set * p.set_stride;
-    T *Ex = p.E[0] + so, *Ey = p.E[1] + so, *Ez = p.E[2] + so;
-    const T *Hx = p.H[0] + so, *Hy = p.H[1] + so, *Hz = p.H[2] + so;
-    long long x = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    const long long xl0 = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    long long xg = (long long)set * p.set_stride + xl0;
+    T *pEx = p.E[0] + xg, *pEy = p.E[1] + xg, *pEz = p.E[2] + xg;
+    const T *pHx = p.H[0] + xg, *pHy = p.H[1] + xg, *pHz = p.H[2] + xg;
+    const uint8_t *pm0 = p.mat[0] + xl0, *pm1 = p.mat[1] + xl0, *pm2 = p.mat[2] + xl0;
+    const long long plane = p.plane;
+    const int pitch = p.pitch;
+    const bool edge = st && (lx == 0) && (i0 > 0);
 
     Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez;
-    if (ld) { hxm.load(Hx + x - p.plane); hym.load(Hy + x - p.plane); } else { hxm.zero(); hym.zero(); }
-    for (int k = kb; k < ke; ++k, x += p.plane) {
+    if (ld) { hxm.load(pHx - plane); hym.load(pHy - plane); } else { hxm.zero(); hym.zero(); }
+    for (int k = kb; k < ke; ++k) {
         if (ld) {
-            hx0.load(Hx + x); hy0.load(Hy + x); hz0.load(Hz + x);
-            hzj.load(Hz + x - p.pitch); hxj.load(Hx + x - p.pitch);
+            hx0.load(pHx); hy0.load(pHy); hz0.load(pHz);
+            hzj.load(pHz - pitch); hxj.load(pHx - pitch);
         } else { hx0.zero(); hy0.zero(); hz0.zero(); hzj.zero(); hxj.zero(); }
         unsigned char mx[V], my[V], mz[V];
         if (st) {
-            ex.load(Ex + x); ey.load(Ey + x); ez.load(Ez + x);
-#pragma unroll
-            for (int v = 0; v < V; ++v) { mx[v] = p.mat[0][x + v]; my[v] = p.mat[1][x + v]; mz[v] = p.mat[2][x + v]; }
+            ex.load(pEx); ey.load(pEy); ez.load(pEz);
+            if (GEN) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
         }
-        T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1);
-        T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1);
-        if (lane == 0 && st) {
-            hz_p = (i0 > 0) ? Hz[x - 1] : T(0);
-            hy_p = (i0 > 0) ? Hy[x - 1] : T(0);
-        }
+        T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
+        T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
+        if (edge) { hz_p = pHz[-1]; hy_p = pHy[-1]; }
+        const unsigned smask = src_plane_mask(p, k);
         if (st) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -197,194 +207,104 @@ __global__ void __launch_bounds__(256) e_interior(KParams<T> p, int i_lo, int i_
                 T dDx = -(C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]));
                 T dDy = -(C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi));
                 T dDz = -(C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]));
-                const int i = i0 + v;
-                if (p.n_src) {
-                    dDx += source_term(p, 0, i, j, k, set, step);
-                    dDy += source_term(p, 1, i, j, k, set, step);
-                    dDz += source_term(p, 2, i, j, k, set, step);
+                if (smask) {
+                    T S0, S1, J;
+                    source_parts(p, smask, 0, i0 + v, j, k, set, step, S0, S1, J); dDx -= (S1 - S0) + J;
+                    source_parts(p, smask, 1, i0 + v, j, k, set, step, S0, S1, J); dDy -= (S1 - S0) + J;
+                    source_parts(p, smask, 2, i0 + v, j, k, set, step, S0, S1, J); dDz -= (S1 - S0) + J;
                 }
-                const long long xv = so + x + v;
-                {
-                    const int m = mx[v];
-                    T dP = T(0);
-                    if (p.mt_np[m]) dP = ade_update(p, 0, m, xv, parity, ex.v[v], (T *)0, (T *)0);
-                    ex.v[v] += p.mt_chi[m] * (dDx - dP);
-                }
-                {
-                    const int m = my[v];
-                    T dP = T(0);
-                    if (p.mt_np[m]) dP = ade_update(p, 1, m, xv, parity, ey.v[v], (T *)0, (T *)0);
-                    ey.v[v] += p.mt_chi[m] * (dDy - dP);
-                }
-                {
-                    const int m = mz[v];
-                    T dP = T(0);
-                    if (p.mt_np[m]) dP = ade_update(p, 2, m, xv, parity, ez.v[v], (T *)0, (T *)0);
-                    ez.v[v] += p.mt_chi[m] * (dDz - dP);
-                }
+                e_elem_interior<T, GEN>(p, 0, ex.v[v], dDx, GEN ? mx[v] : 0, chi_u, xg + v, parity);
+                e_elem_interior<T, GEN>(p, 1, ey.v[v], dDy, GEN ? my[v] : 0, chi_u, xg + v, parity);
+                e_elem_interior<T, GEN>(p, 2, ez.v[v], dDz, GEN ? mz[v] : 0, chi_u, xg + v, parity);
             }
-            ex.store(Ex + x); ey.store(Ey + x); ez.store(Ez + x);
+            ex.store(pEx); ey.store(pEy); ez.store(pEz);
         }
         hxm = hx0; hym = hy0;
+        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
+        pm0 += plane; pm1 += plane; pm2 += plane; xg += plane;
     }
 }
 
+template <typename T, int V, int LX, bool GEN>
+__global__ void __launch_bounds__(256, GEN ? 2 : 3) e_interior(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
+                                                                 int k_begin, int k_end) {
+    const WorkItem it = items[blockIdx.x];
+    constexpr int RW = 32 / LX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane % LX, ly = lane / LX;
+    const int i0 = it.i0 + lx * V;
+    const int j = it.j0 + warp * RW + ly;
+    const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
+    if (kb >= ke) return;
+    e_interior_body<T, V, LX, GEN>(p, g, i0, j, lx, it.set, kb, ke, GEN ? T(0) : p.mt_chi[it.mat]);
+}
+
+// flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
+// from the first one anywhere in the tile or has poles
+__global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, IntGeom g, int tile_w, int tile_h,
+                                  int pitch, long long plane, int kz0, int first_disp, unsigned *flags) {
+    const int kc = blockIdx.z;
+    const int kb = g.k_lo + kc * g.zchunk, ke = min(kb + g.zchunk, g.k_hi);
+    const int i_lo = g.i_lo + blockIdx.x * tile_w, j_lo = g.j_lo + blockIdx.y * tile_h;
+    const int i_hi = min(i_lo + tile_w, g.i_hi), j_hi = min(j_lo + tile_h, g.j_hi);
+    __shared__ int s_gen;
+    if (threadIdx.x == 0) s_gen = 0;
+    __syncthreads();
+    const int nx = max(i_hi - i_lo, 0), ny = max(j_hi - j_lo, 0), nz = max(ke - kb, 0);
+    const int ref = (nx && ny && nz) ? m0[(long long)(kb - kz0 + 1) * plane + (long long)j_lo * pitch + i_lo] : 0;
+    int gen = (ref >= first_disp);
+    for (int t = threadIdx.x; t < nx * ny * nz && !gen; t += blockDim.x) {
+        const int i = i_lo + t % nx, j = j_lo + (t / nx) % ny, k = kb + t / (nx * ny);
+        const long long x = (long long)(k - kz0 + 1) * plane + (long long)j * pitch + i;
+        if (m0[x] != ref || m1[x] != ref || m2[x] != ref) gen = 1;
+    }
+    if (gen) s_gen = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flags[((long long)kc * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s_gen ? 1u : ((unsigned)ref << 8);
+}
+
 // ------------------------------------------------------------------------------------------
-// PML shell kernels: one thread per cell of a box, general meep formulas.
+// PML shell, tiled
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ T pml_db(T fold, T curl, T sk, T su, T *U, long long xb, T &fnew_out) {
-    // returns new f; meep step_curl general branch with kappa = 1
-    T fnew;
+__device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu, T *U) {
     if (su != T(0) && sk != T(0)) {
-        const T uold = U[xb];
-        const T unew = ((T(1) - sk) * uold - curl) / (T(1) + sk);
-        U[xb] = unew;
-        fnew = ((T(1) - su) * fold + (unew - uold)) / (T(1) + su);
-    } else if (su != T(0)) {
-        fnew = ((T(1) - su) * fold - curl) / (T(1) + su);
-    } else {
-        fnew = ((T(1) - sk) * fold - curl) / (T(1) + sk);
-    }
-    fnew_out = fnew;
-    return fnew;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) h_pml(KParams<T> p, PmlBox<T> b, int k_lo, int k_hi) {
-    const long long ncell = (long long)b.bx * b.by * (k_hi - k_lo);
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ncell * p.n_sets) return;
-    const int set = (int)(t / ncell);
-    t -= (long long)set * ncell;
-    const int li = (int)(t % b.bx);
-    const int lj = (int)((t / b.bx) % b.by);
-    const int lk = (int)(t / ((long long)b.bx * b.by));
-    const int i = b.lo[0] + li, j = b.lo[1] + lj, k = k_lo + lk;
-    const int idx[3] = {i, j, k};
-    const long long so = (long long)set * p.set_stride;
-    const long long x = so + (long long)(k - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i;
-    const long long xb = (long long)set * b.bset + (long long)(k - b.lo[2]) * b.bplane + (long long)lj * b.bpitch + li;
-    const long long str[3] = {1, p.pitch, p.plane};
-    const T C = p.courant;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int d1 = (c + 1) % 3, d2 = (c + 2) % 3;
-        // owned + non-metal range of H component c
-        if (idx[c] < 1 || idx[c] > p.n[c] - 1 || idx[d1] > p.n[d1] - 1 || idx[d2] > p.n[d2] - 1) continue;
-        const T *g1 = p.E[d2], *g2 = p.E[d1];
-        const T curl = C * (((g1[x + str[d1]] - g1[x]) + g2[x]) - g2[x + str[d2]]);
-        const T sk = p.sig[d1][2 * idx[d1] + 1], su = p.sig[d2][2 * idx[d2] + 1], sw = p.sig[c][2 * idx[c]];
-        const T bold = b.B[c][xb];
-        T bnew;
-        pml_db(bold, curl, sk, su, b.UB[c], xb, bnew);
-        b.B[c][xb] = bnew;
-        T *H = p.H[c];
-        if (sw != T(0)) H[x] += (T(1) + sw) * bnew - (T(1) - sw) * bold;
-        else H[x] = bnew;
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) e_pml(KParams<T> p, PmlBox<T> b, int k_lo, int k_hi) {
-    const long long ncell = (long long)b.bx * b.by * (k_hi - k_lo);
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ncell * p.n_sets) return;
-    const int set = (int)(t / ncell);
-    t -= (long long)set * ncell;
-    const int li = (int)(t % b.bx);
-    const int lj = (int)((t / b.bx) % b.by);
-    const int lk = (int)(t / ((long long)b.bx * b.by));
-    const int i = b.lo[0] + li, j = b.lo[1] + lj, k = k_lo + lk;
-    const int idx[3] = {i, j, k};
-    const long long so = (long long)set * p.set_stride;
-    const long long xl = (long long)(k - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i;
-    const long long x = so + xl;
-    const long long xb = (long long)set * b.bset + (long long)(k - b.lo[2]) * b.bplane + (long long)lj * b.bpitch + li;
-    const long long str[3] = {1, p.pitch, p.plane};
-    const T C = p.courant;
-    const long long step = *p.step;
-    const int parity = (int)(step & 1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int d1 = (c + 1) % 3, d2 = (c + 2) % 3;
-        if (idx[c] > p.n[c] - 1 || idx[d1] < 1 || idx[d1] > p.n[d1] - 1 || idx[d2] < 1 || idx[d2] > p.n[d2] - 1) continue;
-        const T *g1 = p.H[d2], *g2 = p.H[d1];
-        const T curl = C * (((g1[x - str[d1]] - g1[x]) + g2[x]) - g2[x - str[d2]]);
-        const T sk = p.sig[d1][2 * idx[d1]], su = p.sig[d2][2 * idx[d2]], sw = p.sig[c][2 * idx[c] + 1];
-        const T dold = b.D[c][xb];
-        T dnew;
-        pml_db(dold, curl, sk, su, b.UD[c], xb, dnew);
-        T S0 = T(0), S1 = T(0), J = T(0);
-        if (p.n_src) source_parts(p, c, i, j, k, set, step, S0, S1, J);
-        dnew -= J;
-        b.D[c][xb] = dnew;
-        const int m = p.mat[c][xl];
-        const T chi = p.mt_chi[m];
-        T pold = T(0), pnew = T(0);
-        T wold = chi * (dold - S0);
-        if (p.mt_np[m]) {
-            // W^n = chi (D^n - sum P^n - S^n) needs sum P^n before the poles advance
-            T so_ = T(0);
-            const int np = p.mt_np[m];
-            for (int s = 0; s < np; ++s) so_ += (parity ? p.PB[s][c] : p.PA[s][c])[x];
-            wold = chi * ((dold - so_) - S0);
-            ade_update(p, c, m, x, parity, wold, &pold, &pnew);
-        }
-        const T wnew = chi * ((dnew - pnew) - S1);
-        T *E = p.E[c];
-        if (sw != T(0)) E[x] += (T(1) + sw) * wnew - (T(1) - sw) * wold;
-        else E[x] = wnew;
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// PML shell, tiled: same z-marching / 128-bit / shuffle structure as the interior kernels, plus
-// the box-local auxiliary arrays (D or B always, U where two sigmas overlap) and meep's
-// step_curl / step_update_EDHB arithmetic with the sig / siginv tables.  LX = lanes of a warp
-// along x (32 for the wide z- and y-boxes, 8 for the narrow x-boxes: 4 rows per warp).
-// ------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu, T *U, long long xb) {
-    if (su != T(0) && sk != T(0)) {
-        const T uo = U[xb];
+        const T uo = *U;
         const T un = ((T(1) - sk) * uo - curl) * ik;
-        U[xb] = un;
+        *U = un;
         return ((T(1) - su) * fold + (un - uo)) * iu;
     }
     if (su != T(0)) return ((T(1) - su) * fold - curl) * iu;
     return ((T(1) - sk) * fold - curl) * ik;
 }
 
-template <typename T>
+template <typename T, bool GEN>
 __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, int c, T &e, T &d, T curl, T sk, T ik, T su, T iu, T sw,
-                                           T *U, long long xb, long long x, long long xl, int i, int j, int k, int set,
-                                           long long step, int parity) {
+                                           T *U, int m, T chi_u, long long xg, T S0, T S1, T J, int parity) {
     const T dold = d;
-    T dnew = pml_step_db(dold, curl, sk, ik, su, iu, U, xb);
-    T S0 = T(0), S1 = T(0), J = T(0);
-    if (p.n_src) source_parts(p, c, i, j, k, set, step, S0, S1, J);
+    T dnew = pml_step_db(dold, curl, sk, ik, su, iu, U);
     dnew -= J;
     d = dnew;
-    const int m = p.mat[c][xl];
-    const T chi = p.mt_chi[m];
-    T pold = T(0), pnew = T(0);
-    T wold = chi * (dold - S0);
-    const int np = p.mt_np[m];
-    if (np) {
-        T so_ = T(0);
-        for (int s = 0; s < np; ++s) so_ += (parity ? p.PB[s][c] : p.PA[s][c])[x];
-        wold = chi * ((dold - so_) - S0);
-        ade_update(p, c, m, x, parity, wold, &pold, &pnew);
+    T chi = chi_u, pold = T(0), pnew = T(0);
+    if (GEN) {
+        chi = p.mt_chi[m];
+        if (m >= p.first_disp) {
+            // W^n = chi (D^n - sum P^n - S^n) drives the poles, so sum P^n is needed first
+            const int np = p.mt_np[m];
+            for (int s = 0; s < np; ++s) pold += (parity ? p.PB[s][c] : p.PA[s][c])[xg];
+            const T wdrive = chi * ((dold - pold) - S0);
+            T so;
+            ade_update(p, c, m, xg, parity, wdrive, so, pnew);
+        }
     }
+    const T wold = chi * ((dold - pold) - S0);
     const T wnew = chi * ((dnew - pnew) - S1);
     e = (sw != T(0)) ? e + (T(1) + sw) * wnew - (T(1) - sw) * wold : wnew;
 }
 
 template <typename T, int V, int LX>
-__global__ void __launch_bounds__(256) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
-                                                  int k_lo, int k_hi) {
+__global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+                                                     int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
     const PmlBox<T> &b = bs.b[it.box];
     constexpr int RW = 32 / LX;
@@ -397,42 +317,44 @@ __global__ void __launch_bounds__(256) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs,
     const bool act = (j < b.hi[1]) && (i0 < b.hi[0]);
     const bool rowp = act && (j + 1 <= p.n[1]);
     const T C = p.courant;
-    const int set = it.set;
-    const long long so = (long long)set * p.set_stride;
-    const T *Ex = p.E[0] + so, *Ey = p.E[1] + so, *Ez = p.E[2] + so;
-    T *Hx = p.H[0] + so, *Hy = p.H[1] + so, *Hz = p.H[2] + so;
-    long long x = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
-    long long xb = (long long)set * b.bset + (long long)(kb - b.lo[2]) * b.bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
+    const long long plane = p.plane, bplane = b.bplane;
+    const int pitch = p.pitch;
+    const long long x0 = (long long)it.set * p.set_stride + (long long)(kb - p.kz0 + 1) * plane + (long long)j * pitch + i0;
+    const long long xb0 = (long long)it.set * b.bset + (long long)(kb - b.lo[2]) * bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
+    const T *pEx = p.E[0] + x0, *pEy = p.E[1] + x0, *pEz = p.E[2] + x0;
+    T *pHx = p.H[0] + x0, *pHy = p.H[1] + x0, *pHz = p.H[2] + x0;
+    T *pBx = b.B[0] + xb0, *pBy = b.B[1] + xb0, *pBz = b.B[2] + xb0;
+    T *pUx = b.UB[0] + xb0, *pUy = b.UB[1] + xb0, *pUz = b.UB[2] + xb0;
+    const bool last = (lx == LX - 1 || i0 + V >= b.hi[0]);
+    const bool edge = act && last && (i0 + V < pitch);
     // per-thread PML coefficients along x (per element) and y
-    T sxi[V], ixi[V], sxh[V], ixh[V];
-    T syi = T(0), iyi = T(1), syh = T(0), iyh = T(1);
+    T sxi[V], sxh[V], ixh[V];
+    T syi = T(0), syh = T(0), iyh = T(1);
     if (act) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const int h = 2 * (i0 + v);
-            sxi[v] = p.sig[0][h]; ixi[v] = p.siginv[0][h]; sxh[v] = p.sig[0][h + 1]; ixh[v] = p.siginv[0][h + 1];
+            sxi[v] = p.sig[0][h]; sxh[v] = p.sig[0][h + 1]; ixh[v] = p.siginv[0][h + 1];
         }
-        syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1];
+        syi = p.sig[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1];
     }
+    const bool jok = (j <= p.n[1] - 1);
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz;
-    if (act) { ex0.load(Ex + x); ey0.load(Ey + x); } else { ex0.zero(); ey0.zero(); }
-    for (int k = kb; k < ke; ++k, x += p.plane, xb += b.bplane) {
+    if (act) { ex0.load(pEx); ey0.load(pEy); } else { ex0.zero(); ey0.zero(); }
+    for (int k = kb; k < ke; ++k) {
         if (act) {
-            ex1.load(Ex + x + p.plane); ey1.load(Ey + x + p.plane); ez0.load(Ez + x);
-            hx.load(Hx + x); hy.load(Hy + x); hz.load(Hz + x);
-            bx.load(b.B[0] + xb); by.load(b.B[1] + xb); bz.load(b.B[2] + xb);
+            ex1.load(pEx + plane); ey1.load(pEy + plane); ez0.load(pEz);
+            hx.load(pHx); hy.load(pHy); hz.load(pHz);
+            bx.load(pBx); by.load(pBy); bz.load(pBz);
         } else { ex1.zero(); ey1.zero(); ez0.zero(); }
-        if (rowp) { ezj.load(Ez + x + p.pitch); exj.load(Ex + x + p.pitch); } else { ezj.zero(); exj.zero(); }
+        if (rowp) { ezj.load(pEz + pitch); exj.load(pEx + pitch); } else { ezj.zero(); exj.zero(); }
         T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
         T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
-        if (act && (lx == LX - 1 || i0 + V >= b.hi[0])) {
-            const bool ok = (i0 + V < p.pitch);
-            ez_n = ok ? Ez[x + V] : T(0);
-            ey_n = ok ? Ey[x + V] : T(0);
-        }
+        if (edge) { ez_n = pEz[V]; ey_n = pEy[V]; }
+        else if (last) { ez_n = T(0); ey_n = T(0); }
         if (act) {
             const T szi = p.sig[2][2 * k], szh = p.sig[2][2 * k + 1], izh = p.siginv[2][2 * k + 1];
-            const bool kok = (k <= p.n[2] - 1), jok = (j <= p.n[1] - 1);
+            const bool kok = (k <= p.n[2] - 1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int i = i0 + v;
@@ -442,38 +364,37 @@ __global__ void __launch_bounds__(256) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs,
                 if (i >= 1 && iok && jok && kok) {       // Hx: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((ezj.v[v] - ez0.v[v]) + ey0.v[v]) - ey1.v[v]);
                     const T bo = bx.v[v];
-                    const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, b.UB[0], xb + v);
+                    const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, pUx + v);
                     bx.v[v] = bn;
                     hx.v[v] = (sxi[v] != T(0)) ? hx.v[v] + (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo : bn;
                 }
                 if (j >= 1 && jok && iok && kok) {       // Hy: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
                     const T bo = by.v[v];
-                    const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], b.UB[1], xb + v);
+                    const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], pUy + v);
                     by.v[v] = bn;
                     hy.v[v] = (syi != T(0)) ? hy.v[v] + (T(1) + syi) * bn - (T(1) - syi) * bo : bn;
                 }
                 if (k >= 1 && kok && iok && jok) {       // Hz: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
                     const T bo = bz.v[v];
-                    const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, b.UB[2], xb + v);
+                    const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, pUz + v);
                     bz.v[v] = bn;
                     hz.v[v] = (szi != T(0)) ? hz.v[v] + (T(1) + szi) * bn - (T(1) - szi) * bo : bn;
                 }
             }
-            hx.store(Hx + x); hy.store(Hy + x); hz.store(Hz + x);
-            bx.store(b.B[0] + xb); by.store(b.B[1] + xb); bz.store(b.B[2] + xb);
+            hx.store(pHx); hy.store(pHy); hz.store(pHz);
+            bx.store(pBx); by.store(pBy); bz.store(pBz);
         }
         ex0 = ex1; ey0 = ey1;
+        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
+        pBx += bplane; pBy += bplane; pBz += bplane; pUx += bplane; pUy += bplane; pUz += bplane;
     }
-    (void)iyi; (void)ixi;
 }
 
-template <typename T, int V, int LX>
-__global__ void __launch_bounds__(256) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
-                                                  int k_lo, int k_hi) {
-    const WorkItem it = items[blockIdx.x];
-    const PmlBox<T> &b = bs.b[it.box];
+template <typename T, int V, int LX, bool GEN>
+__device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> &b, const WorkItem &it, int k_lo, int k_hi,
+                                           T chi_u) {
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane % LX, ly = lane / LX;
@@ -487,11 +408,18 @@ __global__ void __launch_bounds__(256) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs,
     const int set = it.set;
     const long long step = *p.step;
     const int parity = (int)(step & 1);
-    const long long so = (long long)set * p.set_stride;
-    T *Ex = p.E[0] + so, *Ey = p.E[1] + so, *Ez = p.E[2] + so;
-    const T *Hx = p.H[0] + so, *Hy = p.H[1] + so, *Hz = p.H[2] + so;
-    long long x = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
-    long long xb = (long long)set * b.bset + (long long)(kb - b.lo[2]) * b.bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
+    const long long plane = p.plane, bplane = b.bplane;
+    const int pitch = p.pitch;
+    const long long xl0 = (long long)(kb - p.kz0 + 1) * plane + (long long)j * pitch + i0;
+    long long xg = (long long)set * p.set_stride + xl0;
+    const long long xb0 = (long long)set * b.bset + (long long)(kb - b.lo[2]) * bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
+    T *pEx = p.E[0] + xg, *pEy = p.E[1] + xg, *pEz = p.E[2] + xg;
+    const T *pHx = p.H[0] + xg, *pHy = p.H[1] + xg, *pHz = p.H[2] + xg;
+    T *pDx = b.D[0] + xb0, *pDy = b.D[1] + xb0, *pDz = b.D[2] + xb0;
+    T *pUx = b.UD[0] + xb0, *pUy = b.UD[1] + xb0, *pUz = b.UD[2] + xb0;
+    const uint8_t *pm0 = p.mat[0] + xl0, *pm1 = p.mat[1] + xl0, *pm2 = p.mat[2] + xl0;
+    const bool first = (lx == 0 || i0 == b.lo[0]);
+    const bool edge = act && first && (i0 > 0);
     T sxi[V], ixi[V], sxh[V];
     T syi = T(0), iyi = T(1), syh = T(0);
     if (act) {
@@ -502,49 +430,86 @@ __global__ void __launch_bounds__(256) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs,
         }
         syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1];
     }
+    const bool jin = (j >= 1 && j <= p.n[1] - 1);
     Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez, dx, dy, dz;
-    if (act) { hxm.load(Hx + x - p.plane); hym.load(Hy + x - p.plane); } else { hxm.zero(); hym.zero(); }
-    for (int k = kb; k < ke; ++k, x += p.plane, xb += b.bplane) {
+    if (act) { hxm.load(pHx - plane); hym.load(pHy - plane); } else { hxm.zero(); hym.zero(); }
+    for (int k = kb; k < ke; ++k) {
+        unsigned char mx[V], my[V], mz[V];
         if (act) {
-            hx0.load(Hx + x); hy0.load(Hy + x); hz0.load(Hz + x);
-            ex.load(Ex + x); ey.load(Ey + x); ez.load(Ez + x);
-            dx.load(b.D[0] + xb); dy.load(b.D[1] + xb); dz.load(b.D[2] + xb);
+            hx0.load(pHx); hy0.load(pHy); hz0.load(pHz);
+            ex.load(pEx); ey.load(pEy); ez.load(pEz);
+            dx.load(pDx); dy.load(pDy); dz.load(pDz);
+            if (GEN) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
         } else { hx0.zero(); hy0.zero(); hz0.zero(); }
-        if (rowm) { hzj.load(Hz + x - p.pitch); hxj.load(Hx + x - p.pitch); } else { hzj.zero(); hxj.zero(); }
+        if (rowm) { hzj.load(pHz - pitch); hxj.load(pHx - pitch); } else { hzj.zero(); hxj.zero(); }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
-        if (act && (lx == 0 || i0 == b.lo[0])) {
-            hz_p = (i0 > 0) ? Hz[x - 1] : T(0);
-            hy_p = (i0 > 0) ? Hy[x - 1] : T(0);
-        }
+        if (edge) { hz_p = pHz[-1]; hy_p = pHy[-1]; }
+        else if (first) { hz_p = T(0); hy_p = T(0); }
+        const unsigned smask = src_plane_mask(p, k);
         if (act) {
             const T szi = p.sig[2][2 * k], izi = p.siginv[2][2 * k], szh = p.sig[2][2 * k + 1];
-            const bool kin = (k >= 1 && k <= p.n[2] - 1), jin = (j >= 1 && j <= p.n[1] - 1);
+            const bool kin = (k >= 1 && k <= p.n[2] - 1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int i = i0 + v;
                 const T hzi = (v > 0) ? hz0.v[v > 0 ? v - 1 : 0] : hz_p;
                 const T hyi = (v > 0) ? hy0.v[v > 0 ? v - 1 : 0] : hy_p;
                 const bool iin = (i >= 1 && i <= p.n[0] - 1);
-                const long long xg = so + x + v, xl = x + v;
+                T S0 = T(0), S1 = T(0), J = T(0);
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
-                    pml_e_elem(p, 0, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], b.UD[0], xb + v, xg, xl, i, j, k, set, step, parity);
+                    if (smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
+                    pml_e_elem<T, GEN>(p, 0, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pUx + v, GEN ? mx[v] : 0, chi_u, xg + v, S0, S1, J, parity);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
-                    pml_e_elem(p, 1, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, b.UD[1], xb + v, xg, xl, i, j, k, set, step, parity);
+                    if (smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
+                    pml_e_elem<T, GEN>(p, 1, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, pUy + v, GEN ? my[v] : 0, chi_u, xg + v, S0, S1, J, parity);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
-                    pml_e_elem(p, 2, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, b.UD[2], xb + v, xg, xl, i, j, k, set, step, parity);
+                    if (smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
+                    pml_e_elem<T, GEN>(p, 2, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, pUz + v, GEN ? mz[v] : 0, chi_u, xg + v, S0, S1, J, parity);
                 }
             }
-            ex.store(Ex + x); ey.store(Ey + x); ez.store(Ez + x);
-            dx.store(b.D[0] + xb); dy.store(b.D[1] + xb); dz.store(b.D[2] + xb);
+            ex.store(pEx); ey.store(pEy); ez.store(pEz);
+            dx.store(pDx); dy.store(pDy); dz.store(pDz);
         }
         hxm = hx0; hym = hy0;
+        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
+        pDx += bplane; pDy += bplane; pDz += bplane; pUx += bplane; pUy += bplane; pUz += bplane;
+        pm0 += plane; pm1 += plane; pm2 += plane; xg += plane;
     }
+}
+
+template <typename T, int V, int LX, bool GEN>
+__global__ void __launch_bounds__(256, 2) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+                                                     int k_lo, int k_hi) {
+    const WorkItem it = items[blockIdx.x];
+    e_pml_body<T, V, LX, GEN>(p, bs.b[it.box], it, k_lo, k_hi, GEN ? T(0) : p.mt_chi[it.mat]);
+}
+
+// material flags of the PML work items (one block per item)
+__global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, const WorkItem *items, int tile_w,
+                                  int tile_h, int n0, int n1, int pitch, long long plane, int kz0, int first_disp,
+                                  unsigned *flags) {
+    const WorkItem it = items[blockIdx.x];
+    const int i_hi = min(it.i0 + tile_w, n0 + 1), j_hi = min(it.j0 + tile_h, n1 + 1);
+    __shared__ int s_gen;
+    if (threadIdx.x == 0) s_gen = 0;
+    __syncthreads();
+    const int nx = max(i_hi - it.i0, 0), ny = max(j_hi - it.j0, 0), nz = max(it.ke - it.kb, 0);
+    const int ref = (nx && ny && nz) ? m0[(long long)(it.kb - kz0 + 1) * plane + (long long)it.j0 * pitch + it.i0] : 0;
+    int gen = (ref >= first_disp);
+    for (int t = threadIdx.x; t < nx * ny * nz && !gen; t += blockDim.x) {
+        const int i = it.i0 + t % nx, j = it.j0 + (t / nx) % ny, k = it.kb + t / (nx * ny);
+        const long long x = (long long)(k - kz0 + 1) * plane + (long long)j * pitch + i;
+        if (m0[x] != ref || m1[x] != ref || m2[x] != ref) gen = 1;
+    }
+    if (gen) s_gen = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flags[blockIdx.x] = s_gen ? 1u : ((unsigned)ref << 8);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -572,3 +537,9 @@ __global__ void sample_monitors(KParams<T> p, MonDev m, long long base_step, int
 }
 
 __global__ void tick_kernel(long long *step) { *step += 1; }
+
+// remap material bytes through a 256-entry LUT (non-dispersive materials first)
+__global__ void remap_bytes(uint8_t *a, long long n, const uint8_t *lut) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] = lut[a[t]];
+}
