@@ -106,7 +106,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->flags_wide = s->flags_narrow = s->flags_int = NULL;
     for (int a = 0; a < 2; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; for (int b = 0; b < 2; ++b) { s->il_pml[a][b].dev = NULL; s->il_pml[a][b].n = 0; } } s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
     for (int i = 0; i < 256; ++i) s->lut_inv[i] = (uint8_t)i;
-    for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) s->PA[q][c] = s->PB[q][c] = NULL;
+    s->Pall = NULL;
+    for (int q = 0; q < SJ_MAX_POLES; ++q) s->np_thr[q] = 1 << 30;
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) s->srcw[q][c] = NULL;
     *out = s;
 
@@ -218,7 +219,7 @@ extern "C" void sj_destroy(sj_sim *s) {
     for (int c = 0; c < 3; ++c) { cudaFree(s->E[c]); cudaFree(s->H[c]); cudaFree(s->mat[c]); cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
     cudaFree(s->items_wide); cudaFree(s->items_narrow); cudaFree(s->flags_wide); cudaFree(s->flags_narrow); cudaFree(s->flags_int);
     for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) cudaFree(s->il_pml[a][b].dev); }
-    for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { cudaFree(s->PA[q][c]); cudaFree(s->PB[q][c]); }
+    cudaFree(s->Pall);
     for (auto &B : s->boxes) for (int c = 0; c < 3; ++c) { cudaFree(B.D[c]); cudaFree(B.B[c]); cudaFree(B.UD[c]); cudaFree(B.UB[c]); }
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
     cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
@@ -262,13 +263,16 @@ static int upload_material_table(sj_sim *s) {
     CK(cudaMalloc((void **)&s->mt_np, SJ_MAX_MAT * sizeof(int)));
     CK(cudaMemcpy(s->mt_np, np.data(), SJ_MAX_MAT * sizeof(int), cudaMemcpyHostToDevice));
     // polarisation slots (dense over the slab; loads are skipped where the material has no pole)
-    const size_t bytes = (size_t)s->set_stride * s->g.n_sets * s->esz;
-    for (int q = s->n_slots; q < slots; ++q)
-        for (int c = 0; c < 3; ++c) {
-            rc = alloc_zero(s, &s->PA[q][c], bytes); if (rc) return rc;
-            rc = alloc_zero(s, &s->PB[q][c], bytes); if (rc) return rc;
-        }
-    s->n_slots = std::max(s->n_slots, slots);
+    if (slots != s->n_slots || !s->Pall) {
+        cudaFree(s->Pall); s->Pall = NULL;
+        const size_t bytes = (size_t)2 * std::max(slots, 1) * 3 * s->set_stride * s->g.n_sets * s->esz;
+        rc = alloc_zero(s, &s->Pall, bytes); if (rc) return rc;
+    }
+    for (int q = 0; q < SJ_MAX_POLES; ++q) {
+        s->np_thr[q] = 1 << 30;
+        for (int m = (int)s->mats_sorted.size() - 1; m >= 0; --m) if (s->mats_sorted[m].n_poles > q) s->np_thr[q] = m;
+    }
+    s->n_slots = slots;
     return 0;
 }
 
@@ -319,9 +323,10 @@ int sj_finish_materials(sj_sim *s) {
     // sort the table: non-dispersive materials first, so "has poles" is a compare, not a load
     const int nm = (int)s->mats.size();
     std::vector<int> order;
-    for (int m = 0; m < nm; ++m) if (s->mats[m].n_poles == 0) order.push_back(m);
-    s->first_disp = (int)order.size();
-    for (int m = 0; m < nm; ++m) if (s->mats[m].n_poles != 0) order.push_back(m);
+    for (int np = 0; np <= SJ_MAX_POLES; ++np) {
+        if (np == 1) s->first_disp = (int)order.size();
+        for (int m = 0; m < nm; ++m) if (s->mats[m].n_poles == np) order.push_back(m);
+    }
     uint8_t lut[256];
     for (int i = 0; i < 256; ++i) { lut[i] = 0; s->lut_inv[i] = (uint8_t)i; }
     bool ident = true;
@@ -619,8 +624,8 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     p.pitch = s->pitch; p.rows = s->rows; p.plane = s->plane; p.set_stride = s->set_stride;
     p.kz0 = s->kz0; p.nzl = s->nzl; p.n_sets = s->g.n_sets;
     for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; p.siginv[c] = (const T *)s->siginvd[c]; }
-    for (int q = 0; q < SJ_MAX_POLES; ++q) for (int c = 0; c < 3; ++c) { p.PA[q][c] = (T *)s->PA[q][c]; p.PB[q][c] = (T *)s->PB[q][c]; }
-    p.n_slots = s->n_slots;
+    p.Pall = (T *)s->Pall; p.p_comp_stride = s->set_stride * s->g.n_sets; p.n_slots = std::max(s->n_slots, 1);
+    for (int q = 0; q < SJ_MAX_POLES; ++q) p.np_thr[q] = s->np_thr[q];
     p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef; p.first_disp = s->first_disp;
     p.courant = (T)s->g.courant;
     p.n_src = (int)s->srcs.size();
@@ -646,8 +651,24 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
     IntGeom g; dim3 grd; interior_geom(s, k_begin, k_end, g, grd);
     if (g.nzc <= 0 || !grd.x || !grd.y) return;
     if (which == 0) { h_interior<T, V, LX><<<grd, 256, 0, st>>>(p, g, k_begin, k_end); s->launches++; return; }
-    if (s->il_int[0].n) { e_interior<T, V, LX, false><<<s->il_int[0].n, 256, 0, st>>>(p, g, s->il_int[0].dev, k_begin, k_end); s->launches++; }
-    if (s->il_int[1].n) { e_interior<T, V, LX, true><<<s->il_int[1].n, 256, 0, st>>>(p, g, s->il_int[1].dev, k_begin, k_end); s->launches++; }
+    if (s->il_int[0].n) { e_interior<T, V, LX, 0><<<s->il_int[0].n, 256, 0, st>>>(p, g, s->il_int[0].dev, k_begin, k_end); s->launches++; }
+    if (s->il_int[1].n) {
+        const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;
+        if (s->n_slots <= 1) e_interior<T, V, LX, 1><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
+        else if (s->n_slots == 2) e_interior<T, V, LX, 2><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
+        else e_interior<T, V, LX, 4><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
+        s->launches++;
+    }
+}
+
+template <typename T, int V, int LX>
+static void launch_e_pml_gen(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, const ItemList &L, int k_begin, int k_end,
+                             cudaStream_t st) {
+    if (!L.n) return;
+    if (s->n_slots <= 1) e_pml_tile<T, V, LX, 1><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
+    else if (s->n_slots == 2) e_pml_tile<T, V, LX, 2><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
+    else e_pml_tile<T, V, LX, 4><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
+    s->launches++;
 }
 
 template <typename T, int V>
@@ -660,10 +681,10 @@ static void launch_pml(sj_sim *s, const KParams<T> &p, int which, int k_begin, i
         if (s->n_items_narrow) { h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end); s->launches++; }
         return;
     }
-    if (s->il_pml[0][0].n) { e_pml_tile<T, V, 32, false><<<s->il_pml[0][0].n, 256, 0, st>>>(p, bs, s->il_pml[0][0].dev, k_begin, k_end); s->launches++; }
-    if (s->il_pml[0][1].n) { e_pml_tile<T, V, 32, true><<<s->il_pml[0][1].n, 256, 0, st>>>(p, bs, s->il_pml[0][1].dev, k_begin, k_end); s->launches++; }
-    if (s->il_pml[1][0].n) { e_pml_tile<T, V, 8, false><<<s->il_pml[1][0].n, 256, 0, st>>>(p, bs, s->il_pml[1][0].dev, k_begin, k_end); s->launches++; }
-    if (s->il_pml[1][1].n) { e_pml_tile<T, V, 8, true><<<s->il_pml[1][1].n, 256, 0, st>>>(p, bs, s->il_pml[1][1].dev, k_begin, k_end); s->launches++; }
+    if (s->il_pml[0][0].n) { e_pml_tile<T, V, 32, 0><<<s->il_pml[0][0].n, 256, 0, st>>>(p, bs, s->il_pml[0][0].dev, k_begin, k_end); s->launches++; }
+    launch_e_pml_gen<T, V, 32>(s, p, bs, s->il_pml[0][1], k_begin, k_end, st);
+    if (s->il_pml[1][0].n) { e_pml_tile<T, V, 8, 0><<<s->il_pml[1][0].n, 256, 0, st>>>(p, bs, s->il_pml[1][0].dev, k_begin, k_end); s->launches++; }
+    launch_e_pml_gen<T, V, 8>(s, p, bs, s->il_pml[1][1], k_begin, k_end, st);
 }
 
 template <typename T, int V>

@@ -33,9 +33,10 @@ struct KParams {
     T *E[3];
     T *H[3];
     const uint8_t *mat[3];
-    T *PA[SJ_MAX_POLES][3];
-    T *PB[SJ_MAX_POLES][3];
+    T *Pall;              // polarisation: [parity][slot][comp][set][...] in one allocation
+    long long p_comp_stride;
     int n_slots;
+    int np_thr[SJ_MAX_POLES]; // material ids >= np_thr[s] have more than s poles (table sorted by pole count)
     const T *mt_chi;      // [SJ_MAX_MAT] 1/eps_inf
     const int *mt_np;     // [SJ_MAX_MAT] number of poles
     int first_disp;       // material ids >= first_disp have poles (table is sorted that way)
@@ -107,8 +108,9 @@ struct sj_sim {
     void *E[3], *H[3];        // device, [set][local plane][row][pitch]
     uint8_t *mat[3];
     uint8_t *masks[3];        // region masks from the rasterizer (same layout)
-    void *PA[SJ_MAX_POLES][3], *PB[SJ_MAX_POLES][3];
+    void *Pall;
     int n_slots;
+    int np_thr[SJ_MAX_POLES];
     void *mt_chi, *mt_coef; int *mt_np;
     void *sigd[3], *siginvd[3];
     WorkItem *items_wide, *items_narrow; int n_items_wide, n_items_narrow;

@@ -78,38 +78,67 @@ __device__ __forceinline__ void source_parts(const KParams<T> &p, unsigned smask
     }
 }
 
-// ---- ADE (M5): all poles of material m at linear index x; `drive` is E^n (W^n inside the PML) ----
+// ---- ADE (M5) ----------------------------------------------------------------------------------
+// Polarisation arrays live in one allocation [parity][slot][comp][set][plane][row][x]; the material
+// table is sorted by pole count, so the pole count of id m is a sum of compares (no table load) and
+// the P loads of a plane can be issued at the top of the iteration together with the field loads.
 template <typename T>
-__device__ __forceinline__ T ade_update(const KParams<T> &p, int c, int m, long long x, int parity, T drive, T &sum_old,
-                                        T &sum_new) {
-    const int np = p.mt_np[m];
-    T dP = T(0), so = T(0), sn = T(0);
-    for (int s = 0; s < np; ++s) {
-        T *cur = parity ? p.PB[s][c] : p.PA[s][c];
-        T *prv = parity ? p.PA[s][c] : p.PB[s][c];
-        const T *cf = p.mt_coef + ((long long)m * SJ_MAX_POLES + s) * 3;
-        const T pc = cur[x], pp = prv[x];
-        const T pn = cf[0] * pc + cf[1] * pp + cf[2] * drive;
-        prv[x] = pn;  // becomes "current" after the parity flip
-        dP += pn - pc; so += pc; sn += pn;
-    }
-    sum_old = so; sum_new = sn;
-    return dP;
+__device__ __forceinline__ int pole_count(const KParams<T> &p, int m) {
+    return (m >= p.np_thr[0]) + (m >= p.np_thr[1]) + (m >= p.np_thr[2]) + (m >= p.np_thr[3]);
+}
+template <typename T>
+__device__ __forceinline__ T *pol_ptr(const KParams<T> &p, int par, int s, int c) {
+    return p.Pall + ((long long)(par * p.n_slots + s) * 3 + c) * p.p_comp_stride;
 }
 
-// One E component element of the interior (E-only) update.
-template <typename T, bool GEN>
-__device__ __forceinline__ void e_elem_interior(const KParams<T> &p, int c, T &e, T dD, int m, T chi_u, long long xg,
-                                                int parity) {
-    if (GEN) {
-        const T chi = p.mt_chi[m];
-        T dP = T(0);
-        if (m >= p.first_disp) { T so, sn; dP = ade_update(p, c, m, xg, parity, e, so, sn); }
-        e += chi * (dD - dP);
-    } else {
-        e += chi_u * dD;
+template <typename T, int V, int NS>
+struct PolState {
+    Vec<T, V> cur[3][NS > 0 ? NS : 1], prv[3][NS > 0 ? NS : 1];
+    bool need[3][NS > 0 ? NS : 1];
+    // issue every polarisation load of this vector (all components, all slots that any element uses)
+    __device__ __forceinline__ void load(const KParams<T> &p, int parity, long long xg, const unsigned char (&mx)[V],
+                                         const unsigned char (&my)[V], const unsigned char (&mz)[V]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int npmax = 0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) npmax = max(npmax, pole_count(p, c == 0 ? mx[v] : c == 1 ? my[v] : mz[v]));
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                need[c][s] = (npmax > s);
+                if (need[c][s]) { cur[c][s].load(pol_ptr(p, parity, s, c) + xg); prv[c][s].load(pol_ptr(p, parity ^ 1, s, c) + xg); }
+                else { cur[c][s].zero(); prv[c][s].zero(); }
+            }
+        }
     }
-}
+    // advance the poles of element v of component c; returns sum(P_new - P_cur), also sum P_new
+    __device__ __forceinline__ T advance(const KParams<T> &p, int c, int v, int m, T drive, T &sum_new) {
+        T dP = T(0), sn = T(0);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const T *cf = p.mt_coef + ((long long)m * SJ_MAX_POLES + s) * 3;   // zero rows beyond the pole count
+            const T pc = cur[c][s].v[v];
+            const T pn = cf[0] * pc + cf[1] * prv[c][s].v[v] + cf[2] * drive;
+            prv[c][s].v[v] = pn;      // written to the "previous" array, which becomes current after the flip
+            dP += pn - pc; sn += pn;
+        }
+        sum_new = sn;
+        return dP;
+    }
+    __device__ __forceinline__ T sum_cur(int c, int v) const {
+        T so = T(0);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) so += cur[c][s].v[v];
+        return so;
+    }
+    __device__ __forceinline__ void store(const KParams<T> &p, int parity, long long xg) const {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (need[c][s]) prv[c][s].store(pol_ptr(p, parity ^ 1, s, c) + xg);
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // Interior H-pass
@@ -166,9 +195,12 @@ __global__ void __launch_bounds__(256, 4) h_interior(KParams<T> p, IntGeom g, in
 // ------------------------------------------------------------------------------------------
 // Interior E-pass
 // ------------------------------------------------------------------------------------------
-template <typename T, int V, int LX, bool GEN>
+// NS = 0: uniform non-dispersive material (chi_u), no material bytes read; NS > 0: general path for
+// materials with up to NS poles (every polarisation load is issued with the field loads).
+template <typename T, int V, int LX, int NS>
 __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGeom &g, int i0, int j, int lx, int set, int kb,
                                                 int ke, T chi_u) {
+    constexpr bool GEN = NS > 0;
     const bool ld = (j < g.j_hi) && (i0 + V <= p.pitch);
     const bool st = (j < g.j_hi) && (i0 < g.i_hi);
     const T C = p.courant;
@@ -184,16 +216,25 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
     const bool edge = st && (lx == 0) && (i0 > 0);
 
     Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez;
+    unsigned char mx[V], my[V], mz[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
+    PolState<T, V, NS> pol;
     if (ld) { hxm.load(pHx - plane); hym.load(pHy - plane); } else { hxm.zero(); hym.zero(); }
+    if (GEN && st) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
     for (int k = kb; k < ke; ++k) {
         if (ld) {
             hx0.load(pHx); hy0.load(pHy); hz0.load(pHz);
             hzj.load(pHz - pitch); hxj.load(pHx - pitch);
         } else { hx0.zero(); hy0.zero(); hz0.zero(); hzj.zero(); hxj.zero(); }
-        unsigned char mx[V], my[V], mz[V];
+        unsigned char nx_[V], ny_[V], nz_[V];
         if (st) {
             ex.load(pEx); ey.load(pEy); ez.load(pEz);
-            if (GEN) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
+            if (GEN) {
+                pol.load(p, parity, xg, mx, my, mz);
+                // material bytes of the next plane (a halo plane always exists)
+                load_bytes<V>(pm0 + plane, nx_); load_bytes<V>(pm1 + plane, ny_); load_bytes<V>(pm2 + plane, nz_);
+            }
         }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
@@ -213,11 +254,21 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
                     source_parts(p, smask, 1, i0 + v, j, k, set, step, S0, S1, J); dDy -= (S1 - S0) + J;
                     source_parts(p, smask, 2, i0 + v, j, k, set, step, S0, S1, J); dDz -= (S1 - S0) + J;
                 }
-                e_elem_interior<T, GEN>(p, 0, ex.v[v], dDx, GEN ? mx[v] : 0, chi_u, xg + v, parity);
-                e_elem_interior<T, GEN>(p, 1, ey.v[v], dDy, GEN ? my[v] : 0, chi_u, xg + v, parity);
-                e_elem_interior<T, GEN>(p, 2, ez.v[v], dDz, GEN ? mz[v] : 0, chi_u, xg + v, parity);
+                if (GEN) {
+                    T sn;
+                    ex.v[v] += p.mt_chi[mx[v]] * (dDx - pol.advance(p, 0, v, mx[v], ex.v[v], sn));
+                    ey.v[v] += p.mt_chi[my[v]] * (dDy - pol.advance(p, 1, v, my[v], ey.v[v], sn));
+                    ez.v[v] += p.mt_chi[mz[v]] * (dDz - pol.advance(p, 2, v, mz[v], ez.v[v], sn));
+                } else {
+                    ex.v[v] += chi_u * dDx; ey.v[v] += chi_u * dDy; ez.v[v] += chi_u * dDz;
+                }
             }
             ex.store(pEx); ey.store(pEy); ez.store(pEz);
+            if (GEN) {
+                pol.store(p, parity, xg);
+#pragma unroll
+                for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; }
+            }
         }
         hxm = hx0; hym = hy0;
         pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
@@ -225,9 +276,9 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
     }
 }
 
-template <typename T, int V, int LX, bool GEN>
-__global__ void __launch_bounds__(256, GEN ? 2 : 3) e_interior(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
-                                                                 int k_begin, int k_end) {
+template <typename T, int V, int LX, int NS>
+__global__ void __launch_bounds__(256, NS == 0 ? 3 : 1) e_interior(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
+                                                                   int k_begin, int k_end) {
     const WorkItem it = items[blockIdx.x];
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -236,7 +287,7 @@ __global__ void __launch_bounds__(256, GEN ? 2 : 3) e_interior(KParams<T> p, Int
     const int j = it.j0 + warp * RW + ly;
     const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
     if (kb >= ke) return;
-    e_interior_body<T, V, LX, GEN>(p, g, i0, j, lx, it.set, kb, ke, GEN ? T(0) : p.mt_chi[it.mat]);
+    e_interior_body<T, V, LX, NS>(p, g, i0, j, lx, it.set, kb, ke, NS > 0 ? T(0) : p.mt_chi[it.mat]);
 }
 
 // flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
@@ -278,24 +329,20 @@ __device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu,
     return ((T(1) - sk) * fold - curl) * ik;
 }
 
-template <typename T, bool GEN>
-__device__ __forceinline__ void pml_e_elem(const KParams<T> &p, int c, T &e, T &d, T curl, T sk, T ik, T su, T iu, T sw,
-                                           T *U, int m, T chi_u, long long xg, T S0, T S1, T J, int parity) {
+template <typename T, int V, int NS>
+__device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, NS> &pol, int c, int v, T &e, T &d, T curl, T sk,
+                                           T ik, T su, T iu, T sw, T *U, int m, T chi_u, T S0, T S1, T J) {
     const T dold = d;
     T dnew = pml_step_db(dold, curl, sk, ik, su, iu, U);
     dnew -= J;
     d = dnew;
     T chi = chi_u, pold = T(0), pnew = T(0);
-    if (GEN) {
+    if (NS > 0) {
         chi = p.mt_chi[m];
-        if (m >= p.first_disp) {
-            // W^n = chi (D^n - sum P^n - S^n) drives the poles, so sum P^n is needed first
-            const int np = p.mt_np[m];
-            for (int s = 0; s < np; ++s) pold += (parity ? p.PB[s][c] : p.PA[s][c])[xg];
-            const T wdrive = chi * ((dold - pold) - S0);
-            T so;
-            ade_update(p, c, m, xg, parity, wdrive, so, pnew);
-        }
+        // W^n = chi (D^n - sum P^n - S^n) drives the poles (meep update_pols runs on W)
+        pold = pol.sum_cur(c, v);
+        const T wdrive = chi * ((dold - pold) - S0);
+        pol.advance(p, c, v, m, wdrive, pnew);
     }
     const T wold = chi * ((dold - pold) - S0);
     const T wnew = chi * ((dnew - pnew) - S1);
@@ -392,9 +439,10 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
     }
 }
 
-template <typename T, int V, int LX, bool GEN>
+template <typename T, int V, int LX, int NS>
 __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> &b, const WorkItem &it, int k_lo, int k_hi,
                                            T chi_u) {
+    constexpr bool GEN = NS > 0;
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane % LX, ly = lane / LX;
@@ -432,14 +480,22 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     }
     const bool jin = (j >= 1 && j <= p.n[1] - 1);
     Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez, dx, dy, dz;
+    unsigned char mx[V], my[V], mz[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
+    PolState<T, V, NS> pol;
     if (act) { hxm.load(pHx - plane); hym.load(pHy - plane); } else { hxm.zero(); hym.zero(); }
+    if (GEN && act) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
     for (int k = kb; k < ke; ++k) {
-        unsigned char mx[V], my[V], mz[V];
+        unsigned char nx_[V], ny_[V], nz_[V];
         if (act) {
             hx0.load(pHx); hy0.load(pHy); hz0.load(pHz);
             ex.load(pEx); ey.load(pEy); ez.load(pEz);
             dx.load(pDx); dy.load(pDy); dz.load(pDz);
-            if (GEN) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
+            if (GEN) {
+                pol.load(p, parity, xg, mx, my, mz);
+                load_bytes<V>(pm0 + plane, nx_); load_bytes<V>(pm1 + plane, ny_); load_bytes<V>(pm2 + plane, nz_);
+            }
         } else { hx0.zero(); hy0.zero(); hz0.zero(); }
         if (rowm) { hzj.load(pHz - pitch); hxj.load(pHx - pitch); } else { hzj.zero(); hxj.zero(); }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
@@ -460,21 +516,26 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
                     if (smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, GEN>(p, 0, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pUx + v, GEN ? mx[v] : 0, chi_u, xg + v, S0, S1, J, parity);
+                    pml_e_elem<T, V, NS>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pUx + v, mx[v], chi_u, S0, S1, J);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
                     if (smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, GEN>(p, 1, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, pUy + v, GEN ? my[v] : 0, chi_u, xg + v, S0, S1, J, parity);
+                    pml_e_elem<T, V, NS>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, pUy + v, my[v], chi_u, S0, S1, J);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
                     if (smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, GEN>(p, 2, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, pUz + v, GEN ? mz[v] : 0, chi_u, xg + v, S0, S1, J, parity);
+                    pml_e_elem<T, V, NS>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, pUz + v, mz[v], chi_u, S0, S1, J);
                 }
             }
             ex.store(pEx); ey.store(pEy); ez.store(pEz);
             dx.store(pDx); dy.store(pDy); dz.store(pDz);
+            if (GEN) {
+                pol.store(p, parity, xg);
+#pragma unroll
+                for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; }
+            }
         }
         hxm = hx0; hym = hy0;
         pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
@@ -483,11 +544,11 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     }
 }
 
-template <typename T, int V, int LX, bool GEN>
-__global__ void __launch_bounds__(256, 2) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
-                                                     int k_lo, int k_hi) {
+template <typename T, int V, int LX, int NS>
+__global__ void __launch_bounds__(256, NS == 0 ? 2 : 1) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+                                                                   int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
-    e_pml_body<T, V, LX, GEN>(p, bs.b[it.box], it, k_lo, k_hi, GEN ? T(0) : p.mt_chi[it.mat]);
+    e_pml_body<T, V, LX, NS>(p, bs.b[it.box], it, k_lo, k_hi, NS > 0 ? T(0) : p.mt_chi[it.mat]);
 }
 
 // material flags of the PML work items (one block per item)

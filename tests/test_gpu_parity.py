@@ -252,7 +252,7 @@ def test_quadrature_sets_are_phase_shifted_copies(scene_json):
     sc.sources[0].phase += np.pi / 2
     b = BoundGeom(st, sc, n_sets=1)
     for bg in (a, b):
-        bg.sim.run(700, 20)
+        bg.sim.run(1600, 20)
     ma, mb = a.sim.monitors(), b.sim.monitors()
     assert np.abs(ma[:, :, 1]).max() > 1e-6
     assert rel_l2(mb[:, :, 0], ma[:, :, 1]) < 1e-12
