@@ -101,6 +101,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->n_mon = 0; s->mon_idx = NULL; s->mon_w = NULL; s->series = NULL; s->series_cap = 0; s->n_samples = 0;
     s->steps_done = 0; s->launches = 0; s->pole_points = 0; s->pml_cells = 0;
     s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
+    s->F = NULL;
     for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = s->siginvd[c] = NULL; }
     s->items_wide = s->items_narrow = NULL; s->n_items_wide = s->n_items_narrow = 0;
     s->flags_wide = s->flags_narrow = s->flags_int = NULL;
@@ -138,10 +139,14 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
         if (getenv("SJ_ZCHUNK")) s->int_zchunk = atoi(getenv("SJ_ZCHUNK"));
     }
     const size_t fbytes = (size_t)s->set_stride * g->n_sets * s->esz;
-    for (int c = 0; c < 3; ++c) {
-        int rc = alloc_zero(s, &s->E[c], fbytes); if (rc) return rc;
-        rc = alloc_zero(s, &s->H[c], fbytes); if (rc) return rc;
-        rc = alloc_zero(s, (void **)&s->mat[c], (size_t)s->set_stride); if (rc) return rc;
+    {
+        int rc = alloc_zero(s, &s->F, 6 * fbytes); if (rc) return rc;
+        uint8_t *mall; rc = alloc_zero(s, (void **)&mall, 3 * (size_t)s->set_stride); if (rc) return rc;
+        for (int c = 0; c < 3; ++c) {
+            s->E[c] = (char *)s->F + (size_t)c * fbytes;
+            s->H[c] = (char *)s->F + (size_t)(3 + c) * fbytes;
+            s->mat[c] = mall + (size_t)c * s->set_stride;
+        }
     }
     // PML shell boxes (global index boxes [lo,hi), k clipped to the owned slab)
     {
@@ -166,11 +171,12 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
             B.bplane = (long long)B.bpitch * B.by;
             B.bset = B.bplane * B.bz;
             const size_t bytes = (size_t)B.bset * g->n_sets * s->esz;
-            for (int c = 0; c < 3; ++c) {
-                int rc = alloc_zero(s, &B.D[c], bytes); if (rc) return rc;
-                rc = alloc_zero(s, &B.B[c], bytes); if (rc) return rc;
-                rc = alloc_zero(s, &B.UD[c], bytes); if (rc) return rc;
-                rc = alloc_zero(s, &B.UB[c], bytes); if (rc) return rc;
+            {
+                int rc = alloc_zero(s, &B.base, 12 * bytes); if (rc) return rc;
+                for (int c = 0; c < 3; ++c) {
+                    B.D[c] = (char *)B.base + (size_t)c * bytes; B.B[c] = (char *)B.base + (size_t)(3 + c) * bytes;
+                    B.UD[c] = (char *)B.base + (size_t)(6 + c) * bytes; B.UB[c] = (char *)B.base + (size_t)(9 + c) * bytes;
+                }
             }
             s->pml_cells += (double)B.bx * B.by * B.bz;
             s->boxes.push_back(B);
@@ -216,11 +222,12 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
 extern "C" void sj_destroy(sj_sim *s) {
     if (!s) return;
     cudaStreamSynchronize(s->stream);
-    for (int c = 0; c < 3; ++c) { cudaFree(s->E[c]); cudaFree(s->H[c]); cudaFree(s->mat[c]); cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
+    cudaFree(s->F); cudaFree(s->mat[0]);
+    for (int c = 0; c < 3; ++c) { cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
     cudaFree(s->items_wide); cudaFree(s->items_narrow); cudaFree(s->flags_wide); cudaFree(s->flags_narrow); cudaFree(s->flags_int);
     for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) cudaFree(s->il_pml[a][b].dev); }
     cudaFree(s->Pall);
-    for (auto &B : s->boxes) for (int c = 0; c < 3; ++c) { cudaFree(B.D[c]); cudaFree(B.B[c]); cudaFree(B.UD[c]); cudaFree(B.UB[c]); }
+    for (auto &B : s->boxes) cudaFree(B.base);
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
     cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
     cudaFree(s->mon_idx); cudaFree(s->mon_w); cudaFree(s->series); cudaFree(s->step_dev); cudaFree(s->flags);
@@ -241,7 +248,7 @@ static int upload_material_table(sj_sim *s) {
         const sj_material &M = s->mats_sorted[m];
         chi[m] = 1.0 / M.eps_inf;
         np[m] = M.n_poles;
-        slots = std::max(slots, M.n_poles);
+        if (s->present[m]) slots = std::max(slots, M.n_poles);   // only materials that occur in the slab
         for (int q = 0; q < M.n_poles; ++q) {
             const sj_pole &P = M.poles[q];
             const double omega2pi = 2 * M_PI * P.omega0, g2pi = P.gamma * 2 * M_PI;
@@ -288,6 +295,15 @@ __global__ void count_pole_points(const uint8_t *mat, const int *np, long long p
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+__global__ void present_kernel(const uint8_t *a, long long n, unsigned *hist) {
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) sh[a[t]] = 1;
+    __syncthreads();
+    if (sh[threadIdx.x]) hist[threadIdx.x] = 1;
 }
 
 static int count_box(sj_sim *s, int i0, int i1, int j0, int j1, int k0, int k1, double *res) {
@@ -339,6 +355,17 @@ int sj_finish_materials(sj_sim *s) {
             remap_bytes<<<(unsigned)((s->set_stride + 255) / 256), 256, 0, s->stream>>>(s->mat[c], s->set_stride, dl);
         CK(cudaStreamSynchronize(s->stream));
         cudaFree(dl);
+    }
+    // which material ids occur at all (the rasterizer's table has 2^regions entries, most unused)
+    {
+        unsigned *dh; CK(cudaMalloc((void **)&dh, 256 * sizeof(unsigned))); CK(cudaMemset(dh, 0, 256 * sizeof(unsigned)));
+        for (int c = 0; c < 3; ++c)
+            present_kernel<<<296, 256, 0, s->stream>>>(s->mat[c] + s->plane, s->plane * (s->nzl - 2), dh);
+        unsigned hh[256];
+        CK(cudaMemcpyAsync(hh, dh, sizeof hh, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        cudaFree(dh);
+        for (int i = 0; i < 256; ++i) s->present[i] = hh[i] != 0;
     }
     int rc = upload_material_table(s); if (rc) return rc;
     rc = count_box(s, 0, s->g.n[0] + 1, 0, s->g.n[1] + 1, s->kz0, s->kz1, &s->pole_points); if (rc) return rc;
@@ -623,6 +650,7 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     for (int d = 0; d < 3; ++d) p.n[d] = s->g.n[d];
     p.pitch = s->pitch; p.rows = s->rows; p.plane = s->plane; p.set_stride = s->set_stride;
     p.kz0 = s->kz0; p.nzl = s->nzl; p.n_sets = s->g.n_sets;
+    p.F = (T *)s->F; p.fcs = s->set_stride * s->g.n_sets;
     for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; p.siginv[c] = (const T *)s->siginvd[c]; }
     p.Pall = (T *)s->Pall; p.p_comp_stride = s->set_stride * s->g.n_sets; p.n_slots = std::max(s->n_slots, 1);
     for (int q = 0; q < SJ_MAX_POLES; ++q) p.np_thr[q] = s->np_thr[q];
@@ -640,7 +668,8 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
 }
 
 template <typename T>
-static void fill_box(const sj_sim::Box &B, PmlBox<T> &b) {
+static void fill_box(const sj_sim::Box &B, PmlBox<T> &b, int n_sets) {
+    b.bcs = B.bset * n_sets;
     for (int d = 0; d < 3; ++d) { b.lo[d] = B.lo[d]; b.hi[d] = B.hi[d]; }
     b.bx = B.bx; b.by = B.by; b.bpitch = B.bpitch; b.bplane = B.bplane; b.bset = B.bset;
     for (int c = 0; c < 3; ++c) { b.D[c] = (T *)B.D[c]; b.B[c] = (T *)B.B[c]; b.UD[c] = (T *)B.UD[c]; b.UB[c] = (T *)B.UB[c]; }
@@ -656,6 +685,7 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
         const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;
         if (s->n_slots <= 1) e_interior<T, V, LX, 1><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
         else if (s->n_slots == 2) e_interior<T, V, LX, 2><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
+        else if (s->n_slots == 3) e_interior<T, V, LX, 3><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
         else e_interior<T, V, LX, 4><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
         s->launches++;
     }
@@ -667,6 +697,7 @@ static void launch_e_pml_gen(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> 
     if (!L.n) return;
     if (s->n_slots <= 1) e_pml_tile<T, V, LX, 1><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
     else if (s->n_slots == 2) e_pml_tile<T, V, LX, 2><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
+    else if (s->n_slots == 3) e_pml_tile<T, V, LX, 3><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
     else e_pml_tile<T, V, LX, 4><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
     s->launches++;
 }
@@ -675,7 +706,7 @@ template <typename T, int V>
 static void launch_pml(sj_sim *s, const KParams<T> &p, int which, int k_begin, int k_end, cudaStream_t st) {
     PmlBoxSet<T> bs;
     memset(&bs, 0, sizeof bs);
-    for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi]);
+    for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi], s->g.n_sets);
     if (which == 0) {
         if (s->n_items_wide) { h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end); s->launches++; }
         if (s->n_items_narrow) { h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end); s->launches++; }

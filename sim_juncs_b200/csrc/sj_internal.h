@@ -30,6 +30,8 @@ struct KParams {
     int kz0;              // global k of local plane 1 (local plane 0 is the lower halo)
     int nzl;              // local planes including both halos
     int n_sets;
+    T *F;                 // all six components in one allocation: E[c] = F + c*fcs, H[c] = F + (3+c)*fcs
+    long long fcs;        // component stride = set_stride * n_sets
     T *E[3];
     T *H[3];
     const uint8_t *mat[3];
@@ -64,6 +66,7 @@ struct PmlBox {
     int bpitch;           // row pitch of aux arrays
     long long bplane;     // bpitch * by
     long long bset;       // elements per set
+    long long bcs;        // component stride of the box arrays (= bset * n_sets); X[c] = X[0] + c*bcs
     T *D[3], *B[3], *UD[3], *UB[3];
 };
 
@@ -105,6 +108,7 @@ struct sj_sim {
     int lo[3], hi[3];         // interior box [lo,hi) in global indices (x aligned)
     std::vector<double> sig[3];
 
+    void *F;                  // one allocation holding E[0..2], H[0..2]
     void *E[3], *H[3];        // device, [set][local plane][row][pitch]
     uint8_t *mat[3];
     uint8_t *masks[3];        // region masks from the rasterizer (same layout)
@@ -119,12 +123,13 @@ struct sj_sim {
     ItemList il_int[2], il_pml[2][2];   // E-pass lists: [uniform|general], PML: [wide|narrow][uniform|general]
     int int_lx, int_zchunk;   // interior tiling: lanes along x per warp, planes per chunk
     int first_disp;
+    bool present[256];        // material id (sorted order) occurs in the slab
     uint8_t lut_inv[256];     // material id -> id as given by the caller
     bool materials_set;
     std::vector<sj_material> mats;         // as given by the caller / rasterizer (id = caller id)
     std::vector<sj_material> mats_sorted;  // device order: non-dispersive first
 
-    struct Box { int lo[3], hi[3]; int bx, by, bz, bpitch; long long bplane, bset; void *D[3], *B[3], *UD[3], *UB[3]; };
+    struct Box { int lo[3], hi[3]; int bx, by, bz, bpitch; long long bplane, bset; void *base; void *D[3], *B[3], *UD[3], *UB[3]; };
     std::vector<Box> boxes;
 
     std::vector<HostSource> srcs;

@@ -86,9 +86,10 @@ template <typename T>
 __device__ __forceinline__ int pole_count(const KParams<T> &p, int m) {
     return (m >= p.np_thr[0]) + (m >= p.np_thr[1]) + (m >= p.np_thr[2]) + (m >= p.np_thr[3]);
 }
+// base of the parity-`par` half; (slot s, component c) sits at + (3 s + c) * p_comp_stride
 template <typename T>
-__device__ __forceinline__ T *pol_ptr(const KParams<T> &p, int par, int s, int c) {
-    return p.Pall + ((long long)(par * p.n_slots + s) * 3 + c) * p.p_comp_stride;
+__device__ __forceinline__ T *pol_base(const KParams<T> &p, int par) {
+    return p.Pall + (long long)par * p.n_slots * 3 * p.p_comp_stride;
 }
 
 template <typename T, int V, int NS>
@@ -98,6 +99,8 @@ struct PolState {
     // issue every polarisation load of this vector (all components, all slots that any element uses)
     __device__ __forceinline__ void load(const KParams<T> &p, int parity, long long xg, const unsigned char (&mx)[V],
                                          const unsigned char (&my)[V], const unsigned char (&mz)[V]) {
+        const T *bc = pol_base(p, parity) + xg, *bp = pol_base(p, parity ^ 1) + xg;
+        const long long cs = p.p_comp_stride;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             int npmax = 0;
@@ -106,7 +109,7 @@ struct PolState {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 need[c][s] = (npmax > s);
-                if (need[c][s]) { cur[c][s].load(pol_ptr(p, parity, s, c) + xg); prv[c][s].load(pol_ptr(p, parity ^ 1, s, c) + xg); }
+                if (need[c][s]) { cur[c][s].load(bc + (3 * s + c) * cs); prv[c][s].load(bp + (3 * s + c) * cs); }
                 else { cur[c][s].zero(); prv[c][s].zero(); }
             }
         }
@@ -132,11 +135,13 @@ struct PolState {
         return so;
     }
     __device__ __forceinline__ void store(const KParams<T> &p, int parity, long long xg) const {
+        T *bp = pol_base(p, parity ^ 1) + xg;
+        const long long cs = p.p_comp_stride;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int s = 0; s < NS; ++s)
-                if (need[c][s]) prv[c][s].store(pol_ptr(p, parity ^ 1, s, c) + xg);
+                if (need[c][s]) prv[c][s].store(bp + (3 * s + c) * cs);
     }
 };
 
@@ -159,23 +164,24 @@ __global__ void __launch_bounds__(256, 4) h_interior(KParams<T> p, IntGeom g, in
     const bool st = (j < g.j_hi) && (i0 < g.i_hi);
     const T C = p.courant;
     const long long x0 = (long long)set * p.set_stride + (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
-    const T *pEx = p.E[0] + x0, *pEy = p.E[1] + x0, *pEz = p.E[2] + x0;
-    T *pHx = p.H[0] + x0, *pHy = p.H[1] + x0, *pHz = p.H[2] + x0;
+    const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
+    const T *pE = p.F + x0;
+    T *pH = p.F + 3 * fcs + x0;
     const long long plane = p.plane;
     const int pitch = p.pitch;
     const bool edge = st && (lx == LX - 1) && (i0 + V < pitch);
 
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz;
-    if (ld) { ex0.load(pEx); ey0.load(pEy); } else { ex0.zero(); ey0.zero(); }
+    if (ld) { ex0.load(pE); ey0.load((pE + fcs)); } else { ex0.zero(); ey0.zero(); }
     for (int k = kb; k < ke; ++k) {
         if (ld) {
-            ex1.load(pEx + plane); ey1.load(pEy + plane);
-            ez0.load(pEz); ezj.load(pEz + pitch); exj.load(pEx + pitch);
+            ex1.load(pE + plane); ey1.load((pE + fcs) + plane);
+            ez0.load((pE + fcs2)); ezj.load((pE + fcs2) + pitch); exj.load(pE + pitch);
         } else { ex1.zero(); ey1.zero(); ez0.zero(); ezj.zero(); exj.zero(); }
-        if (st) { hx.load(pHx); hy.load(pHy); hz.load(pHz); }
+        if (st) { hx.load(pH); hy.load((pH + fcs)); hz.load((pH + fcs2)); }
         T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
         T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
-        if (edge) { ez_n = pEz[V]; ey_n = pEy[V]; }
+        if (edge) { ez_n = (pE + fcs2)[V]; ey_n = (pE + fcs)[V]; }
         if (st) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -185,10 +191,10 @@ __global__ void __launch_bounds__(256, 4) h_interior(KParams<T> p, IntGeom g, in
                 hy.v[v] -= C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
                 hz.v[v] -= C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
             }
-            hx.store(pHx); hy.store(pHy); hz.store(pHz);
+            hx.store(pH); hy.store((pH + fcs)); hz.store((pH + fcs2));
         }
         ex0 = ex1; ey0 = ey1;
-        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
+        pE += plane; pH += plane;
     }
 }
 
@@ -208,9 +214,11 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
     const int parity = (int)(step & 1);
     const long long xl0 = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
     long long xg = (long long)set * p.set_stride + xl0;
-    T *pEx = p.E[0] + xg, *pEy = p.E[1] + xg, *pEz = p.E[2] + xg;
-    const T *pHx = p.H[0] + xg, *pHy = p.H[1] + xg, *pHz = p.H[2] + xg;
-    const uint8_t *pm0 = p.mat[0] + xl0, *pm1 = p.mat[1] + xl0, *pm2 = p.mat[2] + xl0;
+    const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
+    T *pE = p.F + xg;
+    const T *pH = p.F + 3 * fcs + xg;
+    const long long mcs = p.set_stride, mcs2 = 2 * p.set_stride;
+    const uint8_t *pm = p.mat[0] + xl0;
     const long long plane = p.plane;
     const int pitch = p.pitch;
     const bool edge = st && (lx == 0) && (i0 > 0);
@@ -220,25 +228,25 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
 #pragma unroll
     for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
     PolState<T, V, NS> pol;
-    if (ld) { hxm.load(pHx - plane); hym.load(pHy - plane); } else { hxm.zero(); hym.zero(); }
-    if (GEN && st) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
+    if (ld) { hxm.load(pH - plane); hym.load((pH + fcs) - plane); } else { hxm.zero(); hym.zero(); }
+    if (GEN && st) { load_bytes<V>(pm, mx); load_bytes<V>((pm + mcs), my); load_bytes<V>((pm + mcs2), mz); }
     for (int k = kb; k < ke; ++k) {
         if (ld) {
-            hx0.load(pHx); hy0.load(pHy); hz0.load(pHz);
-            hzj.load(pHz - pitch); hxj.load(pHx - pitch);
+            hx0.load(pH); hy0.load((pH + fcs)); hz0.load((pH + fcs2));
+            hzj.load((pH + fcs2) - pitch); hxj.load(pH - pitch);
         } else { hx0.zero(); hy0.zero(); hz0.zero(); hzj.zero(); hxj.zero(); }
         unsigned char nx_[V], ny_[V], nz_[V];
         if (st) {
-            ex.load(pEx); ey.load(pEy); ez.load(pEz);
+            ex.load(pE); ey.load((pE + fcs)); ez.load((pE + fcs2));
             if (GEN) {
                 pol.load(p, parity, xg, mx, my, mz);
                 // material bytes of the next plane (a halo plane always exists)
-                load_bytes<V>(pm0 + plane, nx_); load_bytes<V>(pm1 + plane, ny_); load_bytes<V>(pm2 + plane, nz_);
+                load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
             }
         }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
-        if (edge) { hz_p = pHz[-1]; hy_p = pHy[-1]; }
+        if (edge) { hz_p = (pH + fcs2)[-1]; hy_p = (pH + fcs)[-1]; }
         const unsigned smask = src_plane_mask(p, k);
         if (st) {
 #pragma unroll
@@ -263,7 +271,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
                     ex.v[v] += chi_u * dDx; ey.v[v] += chi_u * dDy; ez.v[v] += chi_u * dDz;
                 }
             }
-            ex.store(pEx); ey.store(pEy); ez.store(pEz);
+            ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
             if (GEN) {
                 pol.store(p, parity, xg);
 #pragma unroll
@@ -271,8 +279,8 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
             }
         }
         hxm = hx0; hym = hy0;
-        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
-        pm0 += plane; pm1 += plane; pm2 += plane; xg += plane;
+        pE += plane; pH += plane;
+        pm += plane; xg += plane;
     }
 }
 
@@ -368,10 +376,12 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
     const int pitch = p.pitch;
     const long long x0 = (long long)it.set * p.set_stride + (long long)(kb - p.kz0 + 1) * plane + (long long)j * pitch + i0;
     const long long xb0 = (long long)it.set * b.bset + (long long)(kb - b.lo[2]) * bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
-    const T *pEx = p.E[0] + x0, *pEy = p.E[1] + x0, *pEz = p.E[2] + x0;
-    T *pHx = p.H[0] + x0, *pHy = p.H[1] + x0, *pHz = p.H[2] + x0;
-    T *pBx = b.B[0] + xb0, *pBy = b.B[1] + xb0, *pBz = b.B[2] + xb0;
-    T *pUx = b.UB[0] + xb0, *pUy = b.UB[1] + xb0, *pUz = b.UB[2] + xb0;
+    const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
+    const T *pE = p.F + x0;
+    T *pH = p.F + 3 * fcs + x0;
+    const long long bcs = b.bcs, bcs2 = 2 * b.bcs;
+    T *pB = b.B[0] + xb0;
+    T *pU = b.UB[0] + xb0;
     const bool last = (lx == LX - 1 || i0 + V >= b.hi[0]);
     const bool edge = act && last && (i0 + V < pitch);
     // per-thread PML coefficients along x (per element) and y
@@ -387,17 +397,17 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
     }
     const bool jok = (j <= p.n[1] - 1);
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz;
-    if (act) { ex0.load(pEx); ey0.load(pEy); } else { ex0.zero(); ey0.zero(); }
+    if (act) { ex0.load(pE); ey0.load((pE + fcs)); } else { ex0.zero(); ey0.zero(); }
     for (int k = kb; k < ke; ++k) {
         if (act) {
-            ex1.load(pEx + plane); ey1.load(pEy + plane); ez0.load(pEz);
-            hx.load(pHx); hy.load(pHy); hz.load(pHz);
-            bx.load(pBx); by.load(pBy); bz.load(pBz);
+            ex1.load(pE + plane); ey1.load((pE + fcs) + plane); ez0.load((pE + fcs2));
+            hx.load(pH); hy.load((pH + fcs)); hz.load((pH + fcs2));
+            bx.load(pB); by.load((pB + bcs)); bz.load((pB + bcs2));
         } else { ex1.zero(); ey1.zero(); ez0.zero(); }
-        if (rowp) { ezj.load(pEz + pitch); exj.load(pEx + pitch); } else { ezj.zero(); exj.zero(); }
+        if (rowp) { ezj.load((pE + fcs2) + pitch); exj.load(pE + pitch); } else { ezj.zero(); exj.zero(); }
         T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
         T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
-        if (edge) { ez_n = pEz[V]; ey_n = pEy[V]; }
+        if (edge) { ez_n = (pE + fcs2)[V]; ey_n = (pE + fcs)[V]; }
         else if (last) { ez_n = T(0); ey_n = T(0); }
         if (act) {
             const T szi = p.sig[2][2 * k], szh = p.sig[2][2 * k + 1], izh = p.siginv[2][2 * k + 1];
@@ -411,31 +421,31 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
                 if (i >= 1 && iok && jok && kok) {       // Hx: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((ezj.v[v] - ez0.v[v]) + ey0.v[v]) - ey1.v[v]);
                     const T bo = bx.v[v];
-                    const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, pUx + v);
+                    const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, pU + v);
                     bx.v[v] = bn;
                     hx.v[v] = (sxi[v] != T(0)) ? hx.v[v] + (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo : bn;
                 }
                 if (j >= 1 && jok && iok && kok) {       // Hy: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
                     const T bo = by.v[v];
-                    const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], pUy + v);
+                    const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], (pU + bcs) + v);
                     by.v[v] = bn;
                     hy.v[v] = (syi != T(0)) ? hy.v[v] + (T(1) + syi) * bn - (T(1) - syi) * bo : bn;
                 }
                 if (k >= 1 && kok && iok && jok) {       // Hz: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
                     const T bo = bz.v[v];
-                    const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, pUz + v);
+                    const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, (pU + bcs2) + v);
                     bz.v[v] = bn;
                     hz.v[v] = (szi != T(0)) ? hz.v[v] + (T(1) + szi) * bn - (T(1) - szi) * bo : bn;
                 }
             }
-            hx.store(pHx); hy.store(pHy); hz.store(pHz);
-            bx.store(pBx); by.store(pBy); bz.store(pBz);
+            hx.store(pH); hy.store((pH + fcs)); hz.store((pH + fcs2));
+            bx.store(pB); by.store((pB + bcs)); bz.store((pB + bcs2));
         }
         ex0 = ex1; ey0 = ey1;
-        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
-        pBx += bplane; pBy += bplane; pBz += bplane; pUx += bplane; pUy += bplane; pUz += bplane;
+        pE += plane; pH += plane;
+        pB += bplane; pU += bplane;
     }
 }
 
@@ -461,11 +471,14 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     const long long xl0 = (long long)(kb - p.kz0 + 1) * plane + (long long)j * pitch + i0;
     long long xg = (long long)set * p.set_stride + xl0;
     const long long xb0 = (long long)set * b.bset + (long long)(kb - b.lo[2]) * bplane + (long long)(j - b.lo[1]) * b.bpitch + (i0 - b.lo[0]);
-    T *pEx = p.E[0] + xg, *pEy = p.E[1] + xg, *pEz = p.E[2] + xg;
-    const T *pHx = p.H[0] + xg, *pHy = p.H[1] + xg, *pHz = p.H[2] + xg;
-    T *pDx = b.D[0] + xb0, *pDy = b.D[1] + xb0, *pDz = b.D[2] + xb0;
-    T *pUx = b.UD[0] + xb0, *pUy = b.UD[1] + xb0, *pUz = b.UD[2] + xb0;
-    const uint8_t *pm0 = p.mat[0] + xl0, *pm1 = p.mat[1] + xl0, *pm2 = p.mat[2] + xl0;
+    const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
+    T *pE = p.F + xg;
+    const T *pH = p.F + 3 * fcs + xg;
+    const long long bcs = b.bcs, bcs2 = 2 * b.bcs;
+    T *pD = b.D[0] + xb0;
+    T *pU = b.UD[0] + xb0;
+    const long long mcs = p.set_stride, mcs2 = 2 * p.set_stride;
+    const uint8_t *pm = p.mat[0] + xl0;
     const bool first = (lx == 0 || i0 == b.lo[0]);
     const bool edge = act && first && (i0 > 0);
     T sxi[V], ixi[V], sxh[V];
@@ -484,23 +497,23 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
 #pragma unroll
     for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
     PolState<T, V, NS> pol;
-    if (act) { hxm.load(pHx - plane); hym.load(pHy - plane); } else { hxm.zero(); hym.zero(); }
-    if (GEN && act) { load_bytes<V>(pm0, mx); load_bytes<V>(pm1, my); load_bytes<V>(pm2, mz); }
+    if (act) { hxm.load(pH - plane); hym.load((pH + fcs) - plane); } else { hxm.zero(); hym.zero(); }
+    if (GEN && act) { load_bytes<V>(pm, mx); load_bytes<V>((pm + mcs), my); load_bytes<V>((pm + mcs2), mz); }
     for (int k = kb; k < ke; ++k) {
         unsigned char nx_[V], ny_[V], nz_[V];
         if (act) {
-            hx0.load(pHx); hy0.load(pHy); hz0.load(pHz);
-            ex.load(pEx); ey.load(pEy); ez.load(pEz);
-            dx.load(pDx); dy.load(pDy); dz.load(pDz);
+            hx0.load(pH); hy0.load((pH + fcs)); hz0.load((pH + fcs2));
+            ex.load(pE); ey.load((pE + fcs)); ez.load((pE + fcs2));
+            dx.load(pD); dy.load((pD + bcs)); dz.load((pD + bcs2));
             if (GEN) {
                 pol.load(p, parity, xg, mx, my, mz);
-                load_bytes<V>(pm0 + plane, nx_); load_bytes<V>(pm1 + plane, ny_); load_bytes<V>(pm2 + plane, nz_);
+                load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
             }
         } else { hx0.zero(); hy0.zero(); hz0.zero(); }
-        if (rowm) { hzj.load(pHz - pitch); hxj.load(pHx - pitch); } else { hzj.zero(); hxj.zero(); }
+        if (rowm) { hzj.load((pH + fcs2) - pitch); hxj.load(pH - pitch); } else { hzj.zero(); hxj.zero(); }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
-        if (edge) { hz_p = pHz[-1]; hy_p = pHy[-1]; }
+        if (edge) { hz_p = (pH + fcs2)[-1]; hy_p = (pH + fcs)[-1]; }
         else if (first) { hz_p = T(0); hy_p = T(0); }
         const unsigned smask = src_plane_mask(p, k);
         if (act) {
@@ -516,21 +529,21 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
                     if (smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, V, NS>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pUx + v, mx[v], chi_u, S0, S1, J);
+                    pml_e_elem<T, V, NS>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pU + v, mx[v], chi_u, S0, S1, J);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
                     if (smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, V, NS>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, pUy + v, my[v], chi_u, S0, S1, J);
+                    pml_e_elem<T, V, NS>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, (pU + bcs) + v, my[v], chi_u, S0, S1, J);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
                     if (smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, V, NS>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, pUz + v, mz[v], chi_u, S0, S1, J);
+                    pml_e_elem<T, V, NS>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, (pU + bcs2) + v, mz[v], chi_u, S0, S1, J);
                 }
             }
-            ex.store(pEx); ey.store(pEy); ez.store(pEz);
-            dx.store(pDx); dy.store(pDy); dz.store(pDz);
+            ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
+            dx.store(pD); dy.store((pD + bcs)); dz.store((pD + bcs2));
             if (GEN) {
                 pol.store(p, parity, xg);
 #pragma unroll
@@ -538,9 +551,9 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             }
         }
         hxm = hx0; hym = hy0;
-        pEx += plane; pEy += plane; pEz += plane; pHx += plane; pHy += plane; pHz += plane;
-        pDx += bplane; pDy += bplane; pDz += bplane; pUx += bplane; pUy += bplane; pUz += bplane;
-        pm0 += plane; pm1 += plane; pm2 += plane; xg += plane;
+        pE += plane; pH += plane;
+        pD += bplane; pU += bplane;
+        pm += plane; xg += plane;
     }
 }
 
