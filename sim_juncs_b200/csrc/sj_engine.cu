@@ -103,9 +103,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
     s->F = NULL;
     for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = s->siginvd[c] = NULL; }
-    s->items_wide = s->items_narrow = NULL; s->n_items_wide = s->n_items_narrow = 0;
-    s->flags_wide = s->flags_narrow = s->flags_int = NULL;
-    for (int a = 0; a < 2; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; for (int b = 0; b < 2; ++b) { s->il_pml[a][b].dev = NULL; s->il_pml[a][b].n = 0; } } s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
+    s->flags_int = NULL; s->mt_eps = NULL; s->pml_lx = 32;
+    for (int a = 0; a < 2; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; for (int b = 0; b < 2; ++b) { s->il_h[a][b].dev = NULL; s->il_h[a][b].n = 0; for (int c = 0; c < 2; ++c) { s->il_pml[a][b][c].dev = NULL; s->il_pml[a][b][c].n = 0; } } } s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
     for (int i = 0; i < 256; ++i) s->lut_inv[i] = (uint8_t)i;
     s->Pall = NULL;
     for (int q = 0; q < SJ_MAX_POLES; ++q) s->np_thr[q] = 1 << 30;
@@ -182,31 +181,51 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
             s->boxes.push_back(B);
         }
     }
-    // work lists of the tiled PML kernels: one entry per thread block
+    // work lists of the tiled PML kernels: one entry per thread block.  Every box is cut into
+    // rectangles: the part with a single non-zero sigma ("face", kind = normal direction) and the
+    // frame around it where sigmas overlap (kind 0, general kernel).
     {
         const int V = s->prec == SJ_F64 ? 2 : 4;
-        std::vector<WorkItem> wide, narrow;
+        s->pml_lx = std::max(s->int_lx, 16);
         const int zchunk = 16;
+        const int L[3] = {s->lo[0], s->lo[1], s->lo[2]}, Hh[3] = {s->hi[0], s->hi[1], s->hi[2]};
+        const int N1x = n[0] + 1, N1y = n[1] + 1;
         for (size_t bi = 0; bi < s->boxes.size(); ++bi) {
             const sj_sim::Box &B = s->boxes[bi];
-            const bool nar = (B.bx <= 8 * V);
-            const int tw = (nar ? 8 : 32) * V, th = (nar ? 4 : 1) * 8;
-            for (int q = 0; q < g->n_sets; ++q)
-                for (int kb = B.lo[2]; kb < B.hi[2]; kb += zchunk)
-                    for (int j0 = B.lo[1]; j0 < B.hi[1]; j0 += th)
-                        for (int i0 = B.lo[0]; i0 < B.hi[0]; i0 += tw) {
-                            WorkItem w = {(int)bi, q, i0, j0, kb, std::min(kb + zchunk, B.hi[2]), 0, 0};
-                            (nar ? narrow : wide).push_back(w);
-                        }
+            struct Rect { int i0, i1, j0, j1, kind; };
+            std::vector<Rect> rects;
+            const bool zbox = (B.lo[0] == 0 && B.hi[0] == N1x && B.lo[1] == 0 && B.hi[1] == N1y);
+            const bool ybox = !zbox && (B.lo[0] == 0 && B.hi[0] == N1x);
+            if (zbox) {
+                rects.push_back({L[0], Hh[0], L[1], Hh[1], 3});
+                rects.push_back({0, N1x, 0, L[1], 0}); rects.push_back({0, N1x, Hh[1], N1y, 0});
+                rects.push_back({0, L[0], L[1], Hh[1], 0}); rects.push_back({Hh[0], N1x, L[1], Hh[1], 0});
+            } else if (ybox) {
+                rects.push_back({L[0], Hh[0], B.lo[1], B.hi[1], 2});
+                rects.push_back({0, L[0], B.lo[1], B.hi[1], 0}); rects.push_back({Hh[0], N1x, B.lo[1], B.hi[1], 0});
+            } else {
+                rects.push_back({B.lo[0], B.hi[0], B.lo[1], B.hi[1], 1});
+            }
+            for (const Rect &R : rects) {
+                if (R.i1 <= R.i0 || R.j1 <= R.j0) continue;
+                const bool nar = (R.i1 - R.i0 <= 8 * V);
+                const int tw = (nar ? 8 : s->pml_lx) * V, th = (32 / (nar ? 8 : s->pml_lx)) * 8;
+                for (int q = 0; q < g->n_sets; ++q)
+                    for (int kb = B.lo[2]; kb < B.hi[2]; kb += zchunk)
+                        for (int j0 = R.j0; j0 < R.j1; j0 += th)
+                            for (int i0 = R.i0; i0 < R.i1; i0 += tw) {
+                                WorkItem w = {(int)bi, q, i0, j0, kb, std::min(kb + zchunk, B.hi[2]), 0, R.kind, R.i1, R.j1};
+                                s->h_items[R.kind ? 1 : 0][nar ? 1 : 0].push_back(w);
+                            }
+            }
         }
-        s->n_items_wide = (int)wide.size(); s->n_items_narrow = (int)narrow.size();
-        s->h_items_wide = wide; s->h_items_narrow = narrow;
-        CK(cudaMalloc((void **)&s->flags_wide, std::max<size_t>(wide.size(), 1) * sizeof(unsigned)));
-        CK(cudaMalloc((void **)&s->flags_narrow, std::max<size_t>(narrow.size(), 1) * sizeof(unsigned)));
-        CK(cudaMalloc((void **)&s->items_wide, std::max<size_t>(wide.size(), 1) * sizeof(WorkItem)));
-        CK(cudaMalloc((void **)&s->items_narrow, std::max<size_t>(narrow.size(), 1) * sizeof(WorkItem)));
-        if (!wide.empty()) CK(cudaMemcpy(s->items_wide, wide.data(), wide.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-        if (!narrow.empty()) CK(cudaMemcpy(s->items_narrow, narrow.data(), narrow.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+        for (int f = 0; f < 2; ++f)
+            for (int w = 0; w < 2; ++w) {
+                const std::vector<WorkItem> &v = s->h_items[f][w];
+                s->il_h[f][w].n = (int)v.size();
+                CK(cudaMalloc((void **)&s->il_h[f][w].dev, std::max<size_t>(v.size(), 1) * sizeof(WorkItem)));
+                if (!v.empty()) CK(cudaMemcpy(s->il_h[f][w].dev, v.data(), v.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+            }
     }
     // default material table: vacuum
     {
@@ -224,8 +243,8 @@ extern "C" void sj_destroy(sj_sim *s) {
     cudaStreamSynchronize(s->stream);
     cudaFree(s->F); cudaFree(s->mat[0]);
     for (int c = 0; c < 3; ++c) { cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
-    cudaFree(s->items_wide); cudaFree(s->items_narrow); cudaFree(s->flags_wide); cudaFree(s->flags_narrow); cudaFree(s->flags_int);
-    for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) cudaFree(s->il_pml[a][b].dev); }
+    cudaFree(s->flags_int); cudaFree(s->mt_eps);
+    for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) { cudaFree(s->il_h[a][b].dev); for (int c = 0; c < 2; ++c) cudaFree(s->il_pml[a][b][c].dev); } }
     cudaFree(s->Pall);
     for (auto &B : s->boxes) cudaFree(B.base);
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
@@ -261,8 +280,11 @@ static int upload_material_table(sj_sim *s) {
             cf[2] = gamma1inv * omega0dtsqr * P.sigma;
         }
     }
-    cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np);
-    s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
+    cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->mt_eps);
+    s->mt_chi = s->mt_coef = s->mt_eps = NULL; s->mt_np = NULL;
+    std::vector<double> epsv(SJ_MAX_MAT, 1.0);
+    for (size_t m = 0; m < s->mats_sorted.size(); ++m) epsv[m] = s->mats_sorted[m].eps_inf;
+    { int rc0 = s->prec == SJ_F64 ? upload_vec<double>(s, epsv, &s->mt_eps) : upload_vec<float>(s, epsv, &s->mt_eps); if (rc0) return rc0; }
     int rc;
     if (s->prec == SJ_F64) { rc = upload_vec<double>(s, chi, &s->mt_chi); if (rc) return rc; rc = upload_vec<double>(s, coef, &s->mt_coef); }
     else { rc = upload_vec<float>(s, chi, &s->mt_chi); if (rc) return rc; rc = upload_vec<float>(s, coef, &s->mt_coef); }
@@ -381,12 +403,6 @@ int sj_finish_materials(sj_sim *s) {
             tile_flags_kernel<<<dim3(grd.x, grd.y, g.nzc), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], g, s->int_lx * V,
                 (32 / s->int_lx) * 8, s->pitch, s->plane, s->kz0, s->first_disp, s->flags_int);
         }
-        if (s->n_items_wide)
-            item_flags_kernel<<<s->n_items_wide, 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->items_wide, 32 * V, 8,
-                s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, s->flags_wide);
-        if (s->n_items_narrow)
-            item_flags_kernel<<<s->n_items_narrow, 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->items_narrow, 8 * V, 32,
-                s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, s->flags_narrow);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(s->stream));
         // split the E-pass work into "uniform material" and "general" lists (block-uniform fast path)
@@ -410,14 +426,23 @@ int sj_finish_materials(sj_sim *s) {
                         lst[f & 1u].push_back(w);
                     }
         for (int a = 0; a < 2; ++a) { rc = upload(s->il_int[a], lst[a]); if (rc) return rc; }
-        for (int wn = 0; wn < 2; ++wn) {
-            const std::vector<WorkItem> &src = wn == 0 ? s->h_items_wide : s->h_items_narrow;
-            std::vector<unsigned> f2(std::max<size_t>(src.size(), 1));
-            if (!src.empty()) CK(cudaMemcpy(f2.data(), wn == 0 ? s->flags_wide : s->flags_narrow, src.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
-            std::vector<WorkItem> l2[2];
-            for (size_t i = 0; i < src.size(); ++i) { WorkItem w = src[i]; w.mat = (int)(f2[i] >> 8); l2[f2[i] & 1u].push_back(w); }
-            for (int a = 0; a < 2; ++a) { rc = upload(s->il_pml[wn][a], l2[a]); if (rc) return rc; }
-        }
+        for (int f = 0; f < 2; ++f)
+            for (int wn = 0; wn < 2; ++wn) {
+                const std::vector<WorkItem> &src = s->h_items[f][wn];
+                std::vector<unsigned> f2(std::max<size_t>(src.size(), 1), 0u);
+                if (!src.empty()) {
+                    unsigned *df; CK(cudaMalloc((void **)&df, src.size() * sizeof(unsigned)));
+                    const int lxw = wn ? 8 : s->pml_lx;
+                    item_flags_kernel<<<(unsigned)src.size(), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->il_h[f][wn].dev,
+                        lxw * V, (32 / lxw) * 8, s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df);
+                    CK(cudaMemcpyAsync(f2.data(), df, src.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+                    CK(cudaStreamSynchronize(s->stream));
+                    cudaFree(df);
+                }
+                std::vector<WorkItem> l2[2];
+                for (size_t i = 0; i < src.size(); ++i) { WorkItem w = src[i]; w.mat = (int)(f2[i] >> 8); l2[f2[i] & 1u].push_back(w); }
+                for (int a2 = 0; a2 < 2; ++a2) { rc = upload(s->il_pml[f][wn][a2], l2[a2]); if (rc) return rc; }
+            }
     }
     s->materials_set = true;
     return 0;
@@ -654,7 +679,7 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; p.siginv[c] = (const T *)s->siginvd[c]; }
     p.Pall = (T *)s->Pall; p.p_comp_stride = s->set_stride * s->g.n_sets; p.n_slots = std::max(s->n_slots, 1);
     for (int q = 0; q < SJ_MAX_POLES; ++q) p.np_thr[q] = s->np_thr[q];
-    p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef; p.first_disp = s->first_disp;
+    p.mt_eps = (const T *)s->mt_eps; p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef; p.first_disp = s->first_disp;
     p.courant = (T)s->g.courant;
     p.n_src = (int)s->srcs.size();
     for (int q = 0; q < p.n_src; ++q) {
@@ -685,21 +710,33 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
         const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;
         if (s->n_slots <= 1) e_interior<T, V, LX, 1><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
         else if (s->n_slots == 2) e_interior<T, V, LX, 2><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
-        else if (s->n_slots == 3) e_interior<T, V, LX, 3><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
         else e_interior<T, V, LX, 4><<<n, 256, 0, st>>>(p, g, d, k_begin, k_end);
         s->launches++;
     }
 }
 
+template <typename T, int V, int LX, bool FACE>
+static void launch_e_pml(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, const ItemList (&L)[2], int k_begin, int k_end,
+                         cudaStream_t st) {
+    if (L[0].n) { e_pml_tile<T, V, LX, 0, FACE><<<L[0].n, 256, 0, st>>>(p, bs, L[0].dev, k_begin, k_end); s->launches++; }
+    if (L[1].n) {
+        if (s->n_slots <= 1) e_pml_tile<T, V, LX, 1, FACE><<<L[1].n, 256, 0, st>>>(p, bs, L[1].dev, k_begin, k_end);
+        else if (s->n_slots == 2) e_pml_tile<T, V, LX, 2, FACE><<<L[1].n, 256, 0, st>>>(p, bs, L[1].dev, k_begin, k_end);
+        else e_pml_tile<T, V, LX, 4, FACE><<<L[1].n, 256, 0, st>>>(p, bs, L[1].dev, k_begin, k_end);
+        s->launches++;
+    }
+}
+
 template <typename T, int V, int LX>
-static void launch_e_pml_gen(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, const ItemList &L, int k_begin, int k_end,
-                             cudaStream_t st) {
-    if (!L.n) return;
-    if (s->n_slots <= 1) e_pml_tile<T, V, LX, 1><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
-    else if (s->n_slots == 2) e_pml_tile<T, V, LX, 2><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
-    else if (s->n_slots == 3) e_pml_tile<T, V, LX, 3><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
-    else e_pml_tile<T, V, LX, 4><<<L.n, 256, 0, st>>>(p, bs, L.dev, k_begin, k_end);
-    s->launches++;
+static void launch_pml_lx(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, int which, int wn, int k_begin, int k_end,
+                          cudaStream_t st) {
+    if (which == 0) {
+        if (s->il_h[0][wn].n) { h_pml_tile<T, V, LX, false><<<s->il_h[0][wn].n, 256, 0, st>>>(p, bs, s->il_h[0][wn].dev, k_begin, k_end); s->launches++; }
+        if (s->il_h[1][wn].n) { h_pml_tile<T, V, LX, true><<<s->il_h[1][wn].n, 256, 0, st>>>(p, bs, s->il_h[1][wn].dev, k_begin, k_end); s->launches++; }
+        return;
+    }
+    launch_e_pml<T, V, LX, false>(s, p, bs, s->il_pml[0][wn], k_begin, k_end, st);
+    launch_e_pml<T, V, LX, true>(s, p, bs, s->il_pml[1][wn], k_begin, k_end, st);
 }
 
 template <typename T, int V>
@@ -707,15 +744,9 @@ static void launch_pml(sj_sim *s, const KParams<T> &p, int which, int k_begin, i
     PmlBoxSet<T> bs;
     memset(&bs, 0, sizeof bs);
     for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi], s->g.n_sets);
-    if (which == 0) {
-        if (s->n_items_wide) { h_pml_tile<T, V, 32><<<s->n_items_wide, 256, 0, st>>>(p, bs, s->items_wide, k_begin, k_end); s->launches++; }
-        if (s->n_items_narrow) { h_pml_tile<T, V, 8><<<s->n_items_narrow, 256, 0, st>>>(p, bs, s->items_narrow, k_begin, k_end); s->launches++; }
-        return;
-    }
-    if (s->il_pml[0][0].n) { e_pml_tile<T, V, 32, 0><<<s->il_pml[0][0].n, 256, 0, st>>>(p, bs, s->il_pml[0][0].dev, k_begin, k_end); s->launches++; }
-    launch_e_pml_gen<T, V, 32>(s, p, bs, s->il_pml[0][1], k_begin, k_end, st);
-    if (s->il_pml[1][0].n) { e_pml_tile<T, V, 8, 0><<<s->il_pml[1][0].n, 256, 0, st>>>(p, bs, s->il_pml[1][0].dev, k_begin, k_end); s->launches++; }
-    launch_e_pml_gen<T, V, 8>(s, p, bs, s->il_pml[1][1], k_begin, k_end, st);
+    if (s->pml_lx == 32) launch_pml_lx<T, V, 32>(s, p, bs, which, 0, k_begin, k_end, st);
+    else launch_pml_lx<T, V, 16>(s, p, bs, which, 0, k_begin, k_end, st);
+    launch_pml_lx<T, V, 8>(s, p, bs, which, 1, k_begin, k_end, st);
 }
 
 template <typename T, int V>

@@ -40,6 +40,7 @@ struct KParams {
     int n_slots;
     int np_thr[SJ_MAX_POLES]; // material ids >= np_thr[s] have more than s poles (table sorted by pole count)
     const T *mt_chi;      // [SJ_MAX_MAT] 1/eps_inf
+    const T *mt_eps;      // [SJ_MAX_MAT] eps_inf
     const int *mt_np;     // [SJ_MAX_MAT] number of poles
     int first_disp;       // material ids >= first_disp have poles (table is sorted that way)
     const T *mt_coef;     // [SJ_MAX_MAT][SJ_MAX_POLES][3] a1,a2,a3
@@ -74,7 +75,9 @@ template <typename T>
 struct PmlBoxSet { PmlBox<T> b[SJ_N_PML_BOX]; };
 
 // one thread block of a PML tile kernel: a (tile_w x tile_h) column of box `box`, planes [kb,ke)
-struct WorkItem { int box, set, i0, j0, kb, ke, mat, pad; };   // mat: uniform material id (fast-path lists)
+// box: PML box (-1 interior); [i0,i_hi) x [j0,j_hi): the tile clipped to its rectangle; mat: uniform material id
+// (fast-path lists); kind: 0 general PML cell, 1/2/3 face tile with normal x/y/z
+struct WorkItem { int box, set, i0, j0, kb, ke, mat, kind, i_hi, j_hi; };
 struct ItemList { WorkItem *dev; int n; };
 
 struct MonDev {
@@ -115,12 +118,13 @@ struct sj_sim {
     void *Pall;
     int n_slots;
     int np_thr[SJ_MAX_POLES];
-    void *mt_chi, *mt_coef; int *mt_np;
+    void *mt_chi, *mt_eps, *mt_coef; int *mt_np;
     void *sigd[3], *siginvd[3];
-    WorkItem *items_wide, *items_narrow; int n_items_wide, n_items_narrow;
-    unsigned *flags_wide, *flags_narrow, *flags_int;
-    std::vector<WorkItem> h_items_wide, h_items_narrow;
-    ItemList il_int[2], il_pml[2][2];   // E-pass lists: [uniform|general], PML: [wide|narrow][uniform|general]
+    unsigned *flags_int;
+    std::vector<WorkItem> h_items[2][2];   // PML tiles: [general|face][wide|narrow]
+    ItemList il_h[2][2];                   // H-pass PML lists, same indexing
+    ItemList il_int[2], il_pml[2][2][2];   // E-pass lists: interior [uniform|general]; PML [general|face][wide|narrow][uniform|general]
+    int pml_lx;                            // lanes along x of the wide PML tiles
     int int_lx, int_zchunk;   // interior tiling: lanes along x per warp, planes per chunk
     int first_disp;
     bool present[256];        // material id (sorted order) occurs in the slab

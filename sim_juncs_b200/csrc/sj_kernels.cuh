@@ -323,7 +323,10 @@ __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const ui
 }
 
 // ------------------------------------------------------------------------------------------
-// PML shell, tiled
+// PML shell, tiled.  PD = 0: general cell (any combination of sigmas; D/B for all components, U
+// where two sigmas overlap).  PD = 1,2,3: "face" tile whose cells have a single non-zero sigma,
+// along x,y,z: no U; the tangential components need no auxiliary array at all (H doubles as B;
+// D is reconstructed as eps E + sum P + S), only the normal component keeps its D / B.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu, T *U) {
@@ -337,31 +340,35 @@ __device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu,
     return ((T(1) - sk) * fold - curl) * ik;
 }
 
-template <typename T, int V, int NS>
+// MODE 0: general; 1: tangential component of a face (sigma sf/isf, no D array); 2: normal
+// component of a face (sigma sw on W, D stored, no sigma on D).
+template <typename T, int V, int NS, int MODE>
 __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, NS> &pol, int c, int v, T &e, T &d, T curl, T sk,
-                                           T ik, T su, T iu, T sw, T *U, int m, T chi_u, T S0, T S1, T J) {
+                                           T ik, T su, T iu, T sw, T *U, int m, T chi_u, T eps_u, T S0, T S1, T J) {
+    const T chi = NS > 0 ? p.mt_chi[m] : chi_u;
+    const T pold = NS > 0 ? pol.sum_cur(c, v) : T(0);
+    T pnew = T(0);
+    if (MODE == 1) {
+        const T eps = NS > 0 ? p.mt_eps[m] : eps_u;
+        const T dold = (eps * e + pold) + S0;
+        const T dnew = ((T(1) - sk) * dold - curl) * ik - J;
+        if (NS > 0) pol.advance(p, c, v, m, e, pnew);          // W == E here
+        e = chi * ((dnew - pnew) - S1);
+        return;
+    }
     const T dold = d;
-    T dnew = pml_step_db(dold, curl, sk, ik, su, iu, U);
+    T dnew = (MODE == 2) ? dold - curl : pml_step_db(dold, curl, sk, ik, su, iu, U);
     dnew -= J;
     d = dnew;
-    T chi = chi_u, pold = T(0), pnew = T(0);
-    if (NS > 0) {
-        chi = p.mt_chi[m];
-        // W^n = chi (D^n - sum P^n - S^n) drives the poles (meep update_pols runs on W)
-        pold = pol.sum_cur(c, v);
-        const T wdrive = chi * ((dold - pold) - S0);
-        pol.advance(p, c, v, m, wdrive, pnew);
-    }
+    // W^n = chi (D^n - sum P^n - S^n) drives the poles (meep update_pols runs on W)
     const T wold = chi * ((dold - pold) - S0);
+    if (NS > 0) pol.advance(p, c, v, m, wold, pnew);
     const T wnew = chi * ((dnew - pnew) - S1);
-    e = (sw != T(0)) ? e + (T(1) + sw) * wnew - (T(1) - sw) * wold : wnew;
+    e = (MODE == 2 || sw != T(0)) ? e + (T(1) + sw) * wnew - (T(1) - sw) * wold : wnew;
 }
 
-template <typename T, int V, int LX>
-__global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
-                                                     int k_lo, int k_hi) {
-    const WorkItem it = items[blockIdx.x];
-    const PmlBox<T> &b = bs.b[it.box];
+template <typename T, int V, int LX, int PD>
+__device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> &b, const WorkItem &it, int k_lo, int k_hi) {
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane % LX, ly = lane / LX;
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
     const int j = it.j0 + warp * RW + ly;
     const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
     if (kb >= ke) return;
-    const bool act = (j < b.hi[1]) && (i0 < b.hi[0]);
+    const bool act = (j < it.j_hi) && (i0 < it.i_hi);
     const bool rowp = act && (j + 1 <= p.n[1]);
     const T C = p.courant;
     const long long plane = p.plane, bplane = b.bplane;
@@ -382,27 +389,34 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
     const long long bcs = b.bcs, bcs2 = 2 * b.bcs;
     T *pB = b.B[0] + xb0;
     T *pU = b.UB[0] + xb0;
-    const bool last = (lx == LX - 1 || i0 + V >= b.hi[0]);
+    const bool last = (lx == LX - 1 || i0 + V >= it.i_hi);
     const bool edge = act && last && (i0 + V < pitch);
     // per-thread PML coefficients along x (per element) and y
     T sxi[V], sxh[V], ixh[V];
     T syi = T(0), syh = T(0), iyh = T(1);
-    if (act) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const int h = 2 * (i0 + v);
-            sxi[v] = p.sig[0][h]; sxh[v] = p.sig[0][h + 1]; ixh[v] = p.siginv[0][h + 1];
+    for (int v = 0; v < V; ++v) { sxi[v] = T(0); sxh[v] = T(0); ixh[v] = T(1); }
+    if (act) {
+        if (PD == 0 || PD == 1) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int h = 2 * (i0 + v);
+                sxi[v] = p.sig[0][h]; sxh[v] = p.sig[0][h + 1]; ixh[v] = p.siginv[0][h + 1];
+            }
         }
-        syi = p.sig[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1];
+        if (PD == 0 || PD == 2) { syi = p.sig[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1]; }
     }
     const bool jok = (j <= p.n[1] - 1);
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz;
+    bx.zero(); by.zero(); bz.zero();
     if (act) { ex0.load(pE); ey0.load((pE + fcs)); } else { ex0.zero(); ey0.zero(); }
     for (int k = kb; k < ke; ++k) {
         if (act) {
             ex1.load(pE + plane); ey1.load((pE + fcs) + plane); ez0.load((pE + fcs2));
             hx.load(pH); hy.load((pH + fcs)); hz.load((pH + fcs2));
-            bx.load(pB); by.load((pB + bcs)); bz.load((pB + bcs2));
+            if (PD == 0 || PD == 1) bx.load(pB);
+            if (PD == 0 || PD == 2) by.load((pB + bcs));
+            if (PD == 0 || PD == 3) bz.load((pB + bcs2));
         } else { ex1.zero(); ey1.zero(); ez0.zero(); }
         if (rowp) { ezj.load((pE + fcs2) + pitch); exj.load(pE + pitch); } else { ezj.zero(); exj.zero(); }
         T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
@@ -410,7 +424,8 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
         if (edge) { ez_n = (pE + fcs2)[V]; ey_n = (pE + fcs)[V]; }
         else if (last) { ez_n = T(0); ey_n = T(0); }
         if (act) {
-            const T szi = p.sig[2][2 * k], szh = p.sig[2][2 * k + 1], izh = p.siginv[2][2 * k + 1];
+            T szi = T(0), szh = T(0), izh = T(1);
+            if (PD == 0 || PD == 3) { szi = p.sig[2][2 * k]; szh = p.sig[2][2 * k + 1]; izh = p.siginv[2][2 * k + 1]; }
             const bool kok = (k <= p.n[2] - 1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -418,30 +433,52 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
                 const T ezi = (v < V - 1) ? ez0.v[v + 1 < V ? v + 1 : v] : ez_n;
                 const T eyi = (v < V - 1) ? ey0.v[v + 1 < V ? v + 1 : v] : ey_n;
                 const bool iok = (i <= p.n[0] - 1);
+                // the face sigma at the half-pixel position (tangential components)
+                const T sf = PD == 1 ? sxh[v] : PD == 2 ? syh : szh, isf = PD == 1 ? ixh[v] : PD == 2 ? iyh : izh;
                 if (i >= 1 && iok && jok && kok) {       // Hx: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((ezj.v[v] - ez0.v[v]) + ey0.v[v]) - ey1.v[v]);
-                    const T bo = bx.v[v];
-                    const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, pU + v);
-                    bx.v[v] = bn;
-                    hx.v[v] = (sxi[v] != T(0)) ? hx.v[v] + (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo : bn;
+                    if (PD == 0) {
+                        const T bo = bx.v[v];
+                        const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, pU + v);
+                        bx.v[v] = bn;
+                        hx.v[v] = (sxi[v] != T(0)) ? hx.v[v] + (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo : bn;
+                    } else if (PD == 1) {
+                        const T bo = bx.v[v], bn = bo - curl;
+                        bx.v[v] = bn;
+                        hx.v[v] += (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo;
+                    } else hx.v[v] = ((T(1) - sf) * hx.v[v] - curl) * isf;
                 }
                 if (j >= 1 && jok && iok && kok) {       // Hy: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
-                    const T bo = by.v[v];
-                    const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], (pU + bcs) + v);
-                    by.v[v] = bn;
-                    hy.v[v] = (syi != T(0)) ? hy.v[v] + (T(1) + syi) * bn - (T(1) - syi) * bo : bn;
+                    if (PD == 0) {
+                        const T bo = by.v[v];
+                        const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], (pU + bcs) + v);
+                        by.v[v] = bn;
+                        hy.v[v] = (syi != T(0)) ? hy.v[v] + (T(1) + syi) * bn - (T(1) - syi) * bo : bn;
+                    } else if (PD == 2) {
+                        const T bo = by.v[v], bn = bo - curl;
+                        by.v[v] = bn;
+                        hy.v[v] += (T(1) + syi) * bn - (T(1) - syi) * bo;
+                    } else hy.v[v] = ((T(1) - sf) * hy.v[v] - curl) * isf;
                 }
                 if (k >= 1 && kok && iok && jok) {       // Hz: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
-                    const T bo = bz.v[v];
-                    const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, (pU + bcs2) + v);
-                    bz.v[v] = bn;
-                    hz.v[v] = (szi != T(0)) ? hz.v[v] + (T(1) + szi) * bn - (T(1) - szi) * bo : bn;
+                    if (PD == 0) {
+                        const T bo = bz.v[v];
+                        const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, (pU + bcs2) + v);
+                        bz.v[v] = bn;
+                        hz.v[v] = (szi != T(0)) ? hz.v[v] + (T(1) + szi) * bn - (T(1) - szi) * bo : bn;
+                    } else if (PD == 3) {
+                        const T bo = bz.v[v], bn = bo - curl;
+                        bz.v[v] = bn;
+                        hz.v[v] += (T(1) + szi) * bn - (T(1) - szi) * bo;
+                    } else hz.v[v] = ((T(1) - sf) * hz.v[v] - curl) * isf;
                 }
             }
             hx.store(pH); hy.store((pH + fcs)); hz.store((pH + fcs2));
-            bx.store(pB); by.store((pB + bcs)); bz.store((pB + bcs2));
+            if (PD == 0 || PD == 1) bx.store(pB);
+            if (PD == 0 || PD == 2) by.store((pB + bcs));
+            if (PD == 0 || PD == 3) bz.store((pB + bcs2));
         }
         ex0 = ex1; ey0 = ey1;
         pE += plane; pH += plane;
@@ -449,9 +486,21 @@ __global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> 
     }
 }
 
-template <typename T, int V, int LX, int NS>
+// FACE = false: general tiles (PD 0); FACE = true: face tiles, normal direction taken from the item
+template <typename T, int V, int LX, bool FACE>
+__global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+                                                     int k_lo, int k_hi) {
+    const WorkItem it = items[blockIdx.x];
+    const PmlBox<T> &b = bs.b[it.box];
+    if (!FACE) h_pml_body<T, V, LX, 0>(p, b, it, k_lo, k_hi);
+    else if (it.kind == 1) h_pml_body<T, V, LX, 1>(p, b, it, k_lo, k_hi);
+    else if (it.kind == 2) h_pml_body<T, V, LX, 2>(p, b, it, k_lo, k_hi);
+    else h_pml_body<T, V, LX, 3>(p, b, it, k_lo, k_hi);
+}
+
+template <typename T, int V, int LX, int NS, int PD>
 __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> &b, const WorkItem &it, int k_lo, int k_hi,
-                                           T chi_u) {
+                                           T chi_u, T eps_u) {
     constexpr bool GEN = NS > 0;
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -460,7 +509,7 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     const int j = it.j0 + warp * RW + ly;
     const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
     if (kb >= ke) return;
-    const bool act = (j < b.hi[1]) && (i0 < b.hi[0]);
+    const bool act = (j < it.j_hi) && (i0 < it.i_hi);
     const bool rowm = act && (j >= 1);
     const T C = p.courant;
     const int set = it.set;
@@ -479,20 +528,25 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     T *pU = b.UD[0] + xb0;
     const long long mcs = p.set_stride, mcs2 = 2 * p.set_stride;
     const uint8_t *pm = p.mat[0] + xl0;
-    const bool first = (lx == 0 || i0 == b.lo[0]);
+    const bool first = (lx == 0 || i0 == it.i0);
     const bool edge = act && first && (i0 > 0);
     T sxi[V], ixi[V], sxh[V];
     T syi = T(0), iyi = T(1), syh = T(0);
-    if (act) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const int h = 2 * (i0 + v);
-            sxi[v] = p.sig[0][h]; ixi[v] = p.siginv[0][h]; sxh[v] = p.sig[0][h + 1];
+    for (int v = 0; v < V; ++v) { sxi[v] = T(0); ixi[v] = T(1); sxh[v] = T(0); }
+    if (act) {
+        if (PD == 0 || PD == 1) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int h = 2 * (i0 + v);
+                sxi[v] = p.sig[0][h]; ixi[v] = p.siginv[0][h]; sxh[v] = p.sig[0][h + 1];
+            }
         }
-        syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1];
+        if (PD == 0 || PD == 2) { syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1]; }
     }
     const bool jin = (j >= 1 && j <= p.n[1] - 1);
     Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez, dx, dy, dz;
+    dx.zero(); dy.zero(); dz.zero();
     unsigned char mx[V], my[V], mz[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
@@ -504,7 +558,9 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
         if (act) {
             hx0.load(pH); hy0.load((pH + fcs)); hz0.load((pH + fcs2));
             ex.load(pE); ey.load((pE + fcs)); ez.load((pE + fcs2));
-            dx.load(pD); dy.load((pD + bcs)); dz.load((pD + bcs2));
+            if (PD == 0 || PD == 1) dx.load(pD);
+            if (PD == 0 || PD == 2) dy.load((pD + bcs));
+            if (PD == 0 || PD == 3) dz.load((pD + bcs2));
             if (GEN) {
                 pol.load(p, parity, xg, mx, my, mz);
                 load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
@@ -517,7 +573,8 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
         else if (first) { hz_p = T(0); hy_p = T(0); }
         const unsigned smask = src_plane_mask(p, k);
         if (act) {
-            const T szi = p.sig[2][2 * k], izi = p.siginv[2][2 * k], szh = p.sig[2][2 * k + 1];
+            T szi = T(0), izi = T(1), szh = T(0);
+            if (PD == 0 || PD == 3) { szi = p.sig[2][2 * k]; izi = p.siginv[2][2 * k]; szh = p.sig[2][2 * k + 1]; }
             const bool kin = (k >= 1 && k <= p.n[2] - 1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -525,25 +582,35 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
                 const T hzi = (v > 0) ? hz0.v[v > 0 ? v - 1 : 0] : hz_p;
                 const T hyi = (v > 0) ? hy0.v[v > 0 ? v - 1 : 0] : hy_p;
                 const bool iin = (i >= 1 && i <= p.n[0] - 1);
+                // the face sigma at the integer position (tangential components)
+                const T sf = PD == 1 ? sxi[v] : PD == 2 ? syi : szi, isf = PD == 1 ? ixi[v] : PD == 2 ? iyi : izi;
                 T S0 = T(0), S1 = T(0), J = T(0);
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
                     if (smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, V, NS>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pU + v, mx[v], chi_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pU + v, mx[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 1) pml_e_elem<T, V, NS, 2>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], pU, mx[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), pU, mx[v], chi_u, eps_u, S0, S1, J);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
                     if (smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, V, NS>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, (pU + bcs) + v, my[v], chi_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, (pU + bcs) + v, my[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 2) pml_e_elem<T, V, NS, 2>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, pU, my[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), pU, my[v], chi_u, eps_u, S0, S1, J);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
                     if (smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
-                    pml_e_elem<T, V, NS>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, (pU + bcs2) + v, mz[v], chi_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, (pU + bcs2) + v, mz[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 3) pml_e_elem<T, V, NS, 2>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, pU, mz[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), pU, mz[v], chi_u, eps_u, S0, S1, J);
                 }
             }
             ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
-            dx.store(pD); dy.store((pD + bcs)); dz.store((pD + bcs2));
+            if (PD == 0 || PD == 1) dx.store(pD);
+            if (PD == 0 || PD == 2) dy.store((pD + bcs));
+            if (PD == 0 || PD == 3) dz.store((pD + bcs2));
             if (GEN) {
                 pol.store(p, parity, xg);
 #pragma unroll
@@ -557,11 +624,16 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     }
 }
 
-template <typename T, int V, int LX, int NS>
+template <typename T, int V, int LX, int NS, bool FACE>
 __global__ void __launch_bounds__(256, NS == 0 ? 2 : 1) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
                                                                    int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
-    e_pml_body<T, V, LX, NS>(p, bs.b[it.box], it, k_lo, k_hi, NS > 0 ? T(0) : p.mt_chi[it.mat]);
+    const PmlBox<T> &b = bs.b[it.box];
+    const T chi_u = NS > 0 ? T(0) : p.mt_chi[it.mat], eps_u = NS > 0 ? T(0) : p.mt_eps[it.mat];
+    if (!FACE) e_pml_body<T, V, LX, NS, 0>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else e_pml_body<T, V, LX, NS, 3>(p, b, it, k_lo, k_hi, chi_u, eps_u);
 }
 
 // material flags of the PML work items (one block per item)
@@ -569,7 +641,7 @@ __global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, const ui
                                   int tile_h, int n0, int n1, int pitch, long long plane, int kz0, int first_disp,
                                   unsigned *flags) {
     const WorkItem it = items[blockIdx.x];
-    const int i_hi = min(it.i0 + tile_w, n0 + 1), j_hi = min(it.j0 + tile_h, n1 + 1);
+    const int i_hi = min(min(it.i0 + tile_w, it.i_hi), n0 + 1), j_hi = min(min(it.j0 + tile_h, it.j_hi), n1 + 1);
     __shared__ int s_gen;
     if (threadIdx.x == 0) s_gen = 0;
     __syncthreads();
