@@ -232,9 +232,8 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ N > 1: z-slabs, weak scaling
     st_tall_n2 = n * world                     # box world x taller in z
-    planes = st_tall_n2 + 1
-    per = (planes + world - 1) // world
-    kz = (rank * per, min(planes, (rank + 1) * per))
+    from sim_juncs_b200.parallel import slab_range
+    kz = slab_range(st_tall_n2 + 1, rank, world)
     from sim_juncs_b200.scene import LIGHT_SPEED, Scene
     sc = Scene.load(scene_path)
     sim = Sim((n, n, st_tall_n2), st.resolution, pml=st.pml_thickness, precision=prec, n_sets=n_sets, kz=kz, device=local)
@@ -253,36 +252,12 @@ def run_ours(args):
     sim.add_gaussian_source(info.component, p1, p2, info.amplitude, 1 / (info.wavelen * st.um_scale), info.width * cba,
                             info.phase, info.start_time * cba, info.end_time * cba, True)
     sim.add_monitors(np.array(sc.monitor_locs), comp=0)
+    from sim_juncs_b200.parallel import SlabRunner
     stream = torch.cuda.current_stream(dev)
-    sptr = stream.cuda_stream
-
-    def plane_t(comp, q, k):
-        ptr, nb = sim.plane_ptr(comp, q, k)
-        return cuda_tensor_from_ptr(torch, ptr, nb, dev)
-    up, down = rank + 1, rank - 1
-    ops_h, ops_e = [], []
-    for q in range(n_sets):
-        for c in (3, 4):       # after the H-pass: top owned Hx,Hy plane goes up, lower halo comes from below
-            if up < world:
-                ops_h.append(dist.P2POp(dist.isend, plane_t(c, q, kz[1] - 1), up))
-            if down >= 0:
-                ops_h.append(dist.P2POp(dist.irecv, plane_t(c, q, kz[0] - 1), down))
-        for c in (0, 1):       # after the E-pass: bottom owned Ex,Ey plane goes down, upper halo comes from above
-            if down >= 0:
-                ops_e.append(dist.P2POp(dist.isend, plane_t(c, q, kz[0]), down))
-            if up < world:
-                ops_e.append(dist.P2POp(dist.irecv, plane_t(c, q, kz[1]), up))
+    runner = SlabRunner(sim, kz, n_sets, dev, save_span=SAVE_SPAN)
 
     def step(i):
-        if i % SAVE_SPAN == 0:
-            sim.sample(sptr)
-        sim.h_pass(kz[0], kz[1], sptr)
-        for r in dist.batch_isend_irecv(ops_h):
-            r.wait()
-        sim.e_pass(kz[0], kz[1], sptr)
-        for r in dist.batch_isend_irecv(ops_e):
-            r.wait()
-        sim.tick(sptr)
+        runner.step()
 
     for i in range(args.warmup):
         step(i)
@@ -314,6 +289,7 @@ def run_ours(args):
                 "clocks": sampler.summary(), "gpu_launches": launches,
                 "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 2 * n_sets * 2 * esz, "d2h_bytes_per_step": 0,
                         "note": "multi-GPU arm reports the device-timed loop only"},
+                "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step(),
                 "roofline": None, "cpu_baseline": None}
         print(json.dumps(line))
     dist.destroy_process_group()
