@@ -190,7 +190,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     {
         const int V = s->prec == SJ_F64 ? 2 : 4;
         s->pml_lx = std::max(s->int_lx, 16);
-        const int zchunk = 16;
+        const int zc_face = getenv("SJ_ZC_FACE") ? atoi(getenv("SJ_ZC_FACE")) : 8, zc_gen = getenv("SJ_ZC_GEN") ? atoi(getenv("SJ_ZC_GEN")) : 4;
         const int L[3] = {s->lo[0], s->lo[1], s->lo[2]}, Hh[3] = {s->hi[0], s->hi[1], s->hi[2]};
         const int N1x = n[0] + 1, N1y = n[1] + 1;
         for (size_t bi = 0; bi < s->boxes.size(); ++bi) {
@@ -213,6 +213,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
                 if (R.i1 <= R.i0 || R.j1 <= R.j0) continue;
                 const bool nar = (R.i1 - R.i0 <= 8 * V);
                 const int tw = (nar ? 8 : s->pml_lx) * V, th = (32 / (nar ? 8 : s->pml_lx)) * 8;
+                const int zchunk = R.kind ? zc_face : zc_gen;   // short marches: these lists are small, keep every SM busy
                 for (int q = 0; q < g->n_sets; ++q)
                     for (int kb = B.lo[2]; kb < B.hi[2]; kb += zchunk)
                         for (int j0 = R.j0; j0 < R.j1; j0 += th)

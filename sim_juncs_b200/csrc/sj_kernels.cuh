@@ -329,11 +329,11 @@ __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const ui
 // D is reconstructed as eps E + sum P + S), only the normal component keeps its D / B.
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu, T *U) {
+__device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu, T &U) {
     if (su != T(0) && sk != T(0)) {
-        const T uo = *U;
+        const T uo = U;
         const T un = ((T(1) - sk) * uo - curl) * ik;
-        *U = un;
+        U = un;
         return ((T(1) - su) * fold + (un - uo)) * iu;
     }
     if (su != T(0)) return ((T(1) - su) * fold - curl) * iu;
@@ -344,7 +344,7 @@ __device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu,
 // component of a face (sigma sw on W, D stored, no sigma on D).
 template <typename T, int V, int NS, int MODE>
 __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, NS> &pol, int c, int v, T &e, T &d, T curl, T sk,
-                                           T ik, T su, T iu, T sw, T *U, int m, T chi_u, T eps_u, T S0, T S1, T J) {
+                                           T ik, T su, T iu, T sw, T &U, int m, T chi_u, T eps_u, T S0, T S1, T J) {
     const T chi = NS > 0 ? p.mt_chi[m] : chi_u;
     const T pold = NS > 0 ? pol.sum_cur(c, v) : T(0);
     T pnew = T(0);
@@ -407,8 +407,8 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
         if (PD == 0 || PD == 2) { syi = p.sig[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1]; }
     }
     const bool jok = (j <= p.n[1] - 1);
-    Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz;
-    bx.zero(); by.zero(); bz.zero();
+    Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz, ux, uy, uz;
+    bx.zero(); by.zero(); bz.zero(); ux.zero(); uy.zero(); uz.zero();
     if (act) { ex0.load(pE); ey0.load((pE + fcs)); } else { ex0.zero(); ey0.zero(); }
     for (int k = kb; k < ke; ++k) {
         if (act) {
@@ -417,6 +417,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0 || PD == 1) bx.load(pB);
             if (PD == 0 || PD == 2) by.load((pB + bcs));
             if (PD == 0 || PD == 3) bz.load((pB + bcs2));
+            if (PD == 0) { ux.load(pU); uy.load((pU + bcs)); uz.load((pU + bcs2)); }
         } else { ex1.zero(); ey1.zero(); ez0.zero(); }
         if (rowp) { ezj.load((pE + fcs2) + pitch); exj.load(pE + pitch); } else { ezj.zero(); exj.zero(); }
         T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
@@ -439,7 +440,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
                     const T curl = C * (((ezj.v[v] - ez0.v[v]) + ey0.v[v]) - ey1.v[v]);
                     if (PD == 0) {
                         const T bo = bx.v[v];
-                        const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, pU + v);
+                        const T bn = pml_step_db(bo, curl, syh, iyh, szh, izh, ux.v[v]);
                         bx.v[v] = bn;
                         hx.v[v] = (sxi[v] != T(0)) ? hx.v[v] + (T(1) + sxi[v]) * bn - (T(1) - sxi[v]) * bo : bn;
                     } else if (PD == 1) {
@@ -452,7 +453,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
                     const T curl = C * (((ex1.v[v] - ex0.v[v]) + ez0.v[v]) - ezi);
                     if (PD == 0) {
                         const T bo = by.v[v];
-                        const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], (pU + bcs) + v);
+                        const T bn = pml_step_db(bo, curl, szh, izh, sxh[v], ixh[v], uy.v[v]);
                         by.v[v] = bn;
                         hy.v[v] = (syi != T(0)) ? hy.v[v] + (T(1) + syi) * bn - (T(1) - syi) * bo : bn;
                     } else if (PD == 2) {
@@ -465,7 +466,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
                     const T curl = C * (((eyi - ey0.v[v]) + ex0.v[v]) - exj.v[v]);
                     if (PD == 0) {
                         const T bo = bz.v[v];
-                        const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, (pU + bcs2) + v);
+                        const T bn = pml_step_db(bo, curl, sxh[v], ixh[v], syh, iyh, uz.v[v]);
                         bz.v[v] = bn;
                         hz.v[v] = (szi != T(0)) ? hz.v[v] + (T(1) + szi) * bn - (T(1) - szi) * bo : bn;
                     } else if (PD == 3) {
@@ -479,6 +480,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0 || PD == 1) bx.store(pB);
             if (PD == 0 || PD == 2) by.store((pB + bcs));
             if (PD == 0 || PD == 3) bz.store((pB + bcs2));
+            if (PD == 0) { ux.store(pU); uy.store((pU + bcs)); uz.store((pU + bcs2)); }
         }
         ex0 = ex1; ey0 = ey1;
         pE += plane; pH += plane;
@@ -545,8 +547,8 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
         if (PD == 0 || PD == 2) { syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1]; }
     }
     const bool jin = (j >= 1 && j <= p.n[1] - 1);
-    Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez, dx, dy, dz;
-    dx.zero(); dy.zero(); dz.zero();
+    Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez, dx, dy, dz, ux, uy, uz;
+    dx.zero(); dy.zero(); dz.zero(); ux.zero(); uy.zero(); uz.zero();
     unsigned char mx[V], my[V], mz[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
@@ -561,6 +563,7 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0 || PD == 1) dx.load(pD);
             if (PD == 0 || PD == 2) dy.load((pD + bcs));
             if (PD == 0 || PD == 3) dz.load((pD + bcs2));
+            if (PD == 0) { ux.load(pU); uy.load((pU + bcs)); uz.load((pU + bcs2)); }
             if (GEN) {
                 pol.load(p, parity, xg, mx, my, mz);
                 load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
@@ -588,29 +591,30 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
                     if (smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], pU + v, mx[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 1) pml_e_elem<T, V, NS, 2>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], pU, mx[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), pU, mx[v], chi_u, eps_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 1) pml_e_elem<T, V, NS, 2>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
                     if (smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, (pU + bcs) + v, my[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 2) pml_e_elem<T, V, NS, 2>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, pU, my[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), pU, my[v], chi_u, eps_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 2) pml_e_elem<T, V, NS, 2>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
                     if (smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, (pU + bcs2) + v, mz[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 3) pml_e_elem<T, V, NS, 2>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, pU, mz[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), pU, mz[v], chi_u, eps_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 3) pml_e_elem<T, V, NS, 2>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
                 }
             }
             ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
             if (PD == 0 || PD == 1) dx.store(pD);
             if (PD == 0 || PD == 2) dy.store((pD + bcs));
             if (PD == 0 || PD == 3) dz.store((pD + bcs2));
+            if (PD == 0) { ux.store(pU); uy.store((pU + bcs)); uz.store((pU + bcs2)); }
             if (GEN) {
                 pol.store(p, parity, xg);
 #pragma unroll
