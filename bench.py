@@ -165,6 +165,12 @@ def run_ours(args):
         l1 = sim.launches()
         ms = sim.run_timed(args.steps, SAVE_SPAN)
         launches = sim.launches() - l1
+        extended = False
+        if len(sampler.samples) < 4:          # timed region shorter than a few nvidia-smi polls: keep the same load running
+            extended = True
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                sim.run(50, SAVE_SPAN)
         sampler.stop_flag = True
         value = cells * n_sets * args.steps / (ms * 1e-3)
         bytes_step = sim.bytes_per_step()
@@ -178,8 +184,12 @@ def run_ours(args):
         dom = "e_interior" if prof["e_interior"] >= prof["h_interior"] else "h_interior"
         alg = alg_e if dom == "e_interior" else alg_h
         achieved = alg / (prof[dom] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if prec == "f64" and os.path.exists(tp):
+            traffic = json.load(open(tp))["traffic_bytes_per_pass"].get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": None, "kernel_ms": prof,
+                    "peak_source": peak_src, "traffic": traffic, "kernel_ms": prof,
                     "algorithmic_bytes_per_launch": alg,
                     "step": {"algorithmic_bytes": bytes_step, "achieved_gbs": bytes_step / (ms * 1e-3 / args.steps) / 1e9,
                              "frac": bytes_step / (ms * 1e-3 / args.steps) / 1e9 / peak}}
@@ -226,7 +236,8 @@ def run_ours(args):
                 "config": {"workload": "junctions/Au_graphene_box 181^3 cells x 2 field sets (complex), res 10 -> 181/18",
                            "scene": "scenes/Au_graphene_box/junc.geom (re-authored, see DESIGN.md)", "save_span": SAVE_SPAN,
                            "l2": "working set %.0f MB per step >> 126 MB L2 (no flush needed)" % (bytes_step / 1e6)},
-                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": dict(sampler.summary(), extended_sampling=extended), "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
         return
 
@@ -275,6 +286,17 @@ def run_ours(args):
     dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0 and len(sampler.samples) < 4:
+        t_end = time.time() + 1.5
+        flag = torch.ones(1, device=dev)
+    else:
+        t_end = 0.0
+        flag = torch.zeros(1, device=dev)
+    dist.broadcast(flag, 0)
+    if flag.item() > 0:                       # keep the same load running while nvidia-smi samples
+        for i in range(300):
+            step(args.warmup + args.steps + i)
+        torch.cuda.synchronize()
     sampler.stop_flag = True
     launches = sim.launches() - l1
     ms = float(ms.item())
