@@ -730,7 +730,18 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
     if (s->il_int[0].n) { e_interior<T, V, LX, 0><<<s->il_int[0].n, 256, 0, fan_stream(s)>>>(p, g, s->il_int[0].dev, k_begin, k_end); s->launches++; }
     if (s->il_int[1].n) {
         const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;
-        if (s->n_slots <= 1) e_interior<T, V, LX, 1><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
+        static const bool stg = getenv("SJ_NO_STAGE") == NULL;
+        if (stg && s->n_slots <= 2) {
+            // cp.async-staged variant: 2 stages x (8 + 6 NS) slots x 256 threads x 16 B of dynamic shared memory
+            static bool attr_done[2][3] = {{false, false, false}, {false, false, false}};
+            const int ns = std::max(s->n_slots, 1);
+            const size_t smem = (size_t)2 * (8 + 6 * ns) * 256 * 16;
+            auto k1 = e_interior_stg<T, V, LX, 1>; auto k2 = e_interior_stg<T, V, LX, 2>;
+            if (ns == 1) { cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k1<<<n, 256, smem, fan_stream(s)>>>(p, g, d, k_begin, k_end); }
+            else { cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k2<<<n, 256, smem, fan_stream(s)>>>(p, g, d, k_begin, k_end); }
+            (void)attr_done;
+        }
+        else if (s->n_slots <= 1) e_interior<T, V, LX, 1><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
         else if (s->n_slots == 2) e_interior<T, V, LX, 2><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
         else e_interior<T, V, LX, 4><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
         s->launches++;

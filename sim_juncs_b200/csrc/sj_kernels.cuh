@@ -298,6 +298,181 @@ __global__ void __launch_bounds__(256, NS == 0 ? 3 : 1) e_interior(KParams<T> p,
     e_interior_body<T, V, LX, NS>(p, g, i0, j, lx, it.set, kb, ke, NS > 0 ? T(0) : p.mt_chi[it.mat]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Staged variant of the general interior E-pass: every vector of plane k+1 is fetched with
+// cp.async (LDGSTS, 16 B per thread, L2 -> shared, no registers held) while plane k is computed.
+// Each thread only ever reads the shared-memory slots it filled itself, so the pipeline needs
+// cp.async.wait_group but no block barrier.  Slots: [stage][slot][thread] of 16 bytes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <typename T, int V, int NSLOT>
+struct Stager {
+    uint4 *base;   // &smem[threadIdx.x]
+    __device__ __forceinline__ uint4 *addr(int st, int slot) const { return base + (st * NSLOT + slot) * 256; }
+    __device__ __forceinline__ void issue(int st, int slot, const T *g, bool pred) const {
+        if (pred) cp_async16(addr(st, slot), g);
+        else *addr(st, slot) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __device__ __forceinline__ void get(int st, int slot, Vec<T, V> &v) const {
+        const uint4 t = *addr(st, slot);
+        const T *q = reinterpret_cast<const T *>(&t);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v.v[i] = q[i];
+    }
+};
+
+template <typename T, int V, int LX, int NS>
+__global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
+                                                         int k_begin, int k_end) {
+    constexpr int NSLOT = 8 + 6 * NS;
+    extern __shared__ uint4 sj_smem[];
+    const WorkItem it = items[blockIdx.x];
+    constexpr int RW = 32 / LX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane % LX, ly = lane / LX;
+    const int i0 = it.i0 + lx * V;
+    const int j = it.j0 + warp * RW + ly;
+    const int set = it.set;
+    const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
+    if (kb >= ke) return;
+    Stager<T, V, NSLOT> sg; sg.base = sj_smem + threadIdx.x;
+    const bool ld = (j < g.j_hi) && (i0 + V <= p.pitch);
+    const bool st = (j < g.j_hi) && (i0 < g.i_hi);
+    const T C = p.courant;
+    const long long step = *p.step;
+    const int parity = (int)(step & 1);
+    const long long xl0 = (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    long long xg = (long long)set * p.set_stride + xl0;
+    const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
+    T *pE = p.F + xg;
+    const T *pH = p.F + 3 * fcs + xg;
+    const long long mcs = p.set_stride, mcs2 = 2 * p.set_stride;
+    const uint8_t *pm = p.mat[0] + xl0;
+    const long long plane = p.plane;
+    const int pitch = p.pitch;
+    const bool edge = st && (lx == 0) && (i0 > 0);
+    const long long pcs = p.p_comp_stride;
+    const T *bcur = p.Pall + (long long)parity * p.n_slots * 3 * pcs;          // parity half read as "current"
+    T *bprv = p.Pall + (long long)(parity ^ 1) * p.n_slots * 3 * pcs;          // read as "previous", written as new
+
+    // which polarisation vectors the materials of a plane need: bit (3 s + c)
+    auto need_of = [&](const unsigned char (&ax)[V], const unsigned char (&ay)[V], const unsigned char (&az)[V]) {
+        unsigned nd = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int npmax = 0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) npmax = max(npmax, pole_count(p, c == 0 ? ax[v] : c == 1 ? ay[v] : az[v]));
+#pragma unroll
+            for (int s = 0; s < NS; ++s) if (npmax > s) nd |= 1u << (3 * s + c);
+        }
+        return nd;
+    };
+    // issue every vector load of the plane at offset `off` (0 = plane k of the current pointers)
+    auto issue_plane = [&](int stg, long long off, long long xgp, unsigned nd) {
+        sg.issue(stg, 0, pH + off, ld); sg.issue(stg, 1, pH + fcs + off, ld); sg.issue(stg, 2, pH + fcs2 + off, ld);
+        sg.issue(stg, 3, pH + fcs2 + off - pitch, ld); sg.issue(stg, 4, pH + off - pitch, ld);
+        sg.issue(stg, 5, pE + off, st); sg.issue(stg, 6, pE + fcs + off, st); sg.issue(stg, 7, pE + fcs2 + off, st);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const bool nd_ = st && ((nd >> (3 * s + c)) & 1u);
+                sg.issue(stg, 8 + (c * NS + s) * 2, bcur + (3 * s + c) * pcs + xgp, nd_);
+                sg.issue(stg, 9 + (c * NS + s) * 2, bprv + (3 * s + c) * pcs + xgp, nd_);
+            }
+    };
+
+    Vec<T, V> hxm, hym, hx0, hy0, hz0, hzj, hxj, ex, ey, ez;
+    unsigned char mx[V], my[V], mz[V], nx_[V], ny_[V], nz_[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = nx_[v] = ny_[v] = nz_[v] = 0;
+    if (ld) { hxm.load(pH - plane); hym.load((pH + fcs) - plane); } else { hxm.zero(); hym.zero(); }
+    if (st) {
+        load_bytes<V>(pm, mx); load_bytes<V>(pm + mcs, my); load_bytes<V>(pm + mcs2, mz);
+        load_bytes<V>(pm + plane, nx_); load_bytes<V>(pm + mcs + plane, ny_); load_bytes<V>(pm + mcs2 + plane, nz_);
+    }
+    unsigned need_c = need_of(mx, my, mz);
+    T hz_pc = T(0), hy_pc = T(0);
+    if (edge) { hz_pc = (pH + fcs2)[-1]; hy_pc = (pH + fcs)[-1]; }
+    issue_plane(0, 0, xg, need_c);
+    cp_async_commit();
+    for (int k = kb; k < ke; ++k) {
+        const int cur = (k - kb) & 1;
+        const unsigned need_n = need_of(nx_, ny_, nz_);
+        unsigned char fx[V], fy[V], fz[V];          // material bytes two planes ahead
+        T hz_pn = T(0), hy_pn = T(0);
+        if (k + 1 < ke) {
+            issue_plane(cur ^ 1, plane, xg + plane, need_n);
+            if (st) { load_bytes<V>(pm + 2 * plane, fx); load_bytes<V>(pm + mcs + 2 * plane, fy); load_bytes<V>(pm + mcs2 + 2 * plane, fz); }
+            if (edge) { hz_pn = (pH + fcs2 + plane)[-1]; hy_pn = (pH + fcs + plane)[-1]; }
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        sg.get(cur, 0, hx0); sg.get(cur, 1, hy0); sg.get(cur, 2, hz0); sg.get(cur, 3, hzj); sg.get(cur, 4, hxj);
+        T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
+        T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
+        if (edge) { hz_p = hz_pc; hy_p = hy_pc; }
+        const unsigned smask = src_plane_mask(p, k);
+        if (st) {
+            sg.get(cur, 5, ex); sg.get(cur, 6, ey); sg.get(cur, 7, ez);
+            Vec<T, V> pc[3][NS], pp[3][NS];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int s = 0; s < NS; ++s) { sg.get(cur, 8 + (c * NS + s) * 2, pc[c][s]); sg.get(cur, 9 + (c * NS + s) * 2, pp[c][s]); }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T hzi = (v > 0) ? hz0.v[v > 0 ? v - 1 : 0] : hz_p;
+                const T hyi = (v > 0) ? hy0.v[v > 0 ? v - 1 : 0] : hy_p;
+                T dD[3];
+                dD[0] = -(C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]));
+                dD[1] = -(C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi));
+                dD[2] = -(C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]));
+                if (smask) {
+                    T S0, S1, J;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { source_parts(p, smask, c, i0 + v, j, k, set, step, S0, S1, J); dD[c] -= (S1 - S0) + J; }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int m = c == 0 ? mx[v] : c == 1 ? my[v] : mz[v];
+                    T &e = c == 0 ? ex.v[v] : c == 1 ? ey.v[v] : ez.v[v];
+                    T dP = T(0);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const T *cf = p.mt_coef + ((long long)m * SJ_MAX_POLES + s) * 3;
+                        const T pcur = pc[c][s].v[v];
+                        const T pn = cf[0] * pcur + cf[1] * pp[c][s].v[v] + cf[2] * e;
+                        pp[c][s].v[v] = pn;
+                        dP += pn - pcur;
+                    }
+                    e += p.mt_chi[m] * (dD[c] - dP);
+                }
+            }
+            ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if ((need_c >> (3 * s + c)) & 1u) pp[c][s].store(bprv + (3 * s + c) * pcs + xg);
+        }
+        hxm = hx0; hym = hy0;
+        hz_pc = hz_pn; hy_pc = hy_pn;
+        need_c = need_n;
+#pragma unroll
+        for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; nx_[v] = fx[v]; ny_[v] = fy[v]; nz_[v] = fz[v]; }
+        pE += plane; pH += plane; pm += plane; xg += plane;
+    }
+}
+
 // flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
 // from the first one anywhere in the tile or has poles
 __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, IntGeom g, int tile_w, int tile_h,
