@@ -1,0 +1,43 @@
+"""The C++ host (host/sim_geom.cpp: the reference's own argparse.h + CGS parser compiled in place, on
+the C ABI) against the Python mirror: same conf / geom files in, identical monitor series out."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from sim_juncs_b200.bound_geom import BoundGeom
+from sim_juncs_b200.scene import Scene
+from sim_juncs_b200.settings import ParseSettings
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "host", "_ref", "sim_geom")
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="host/_ref/sim_geom is built only where /root/reference exists")
+def test_cpp_cli_matches_python_mirror(tmp_path, scene_json):
+    conf = os.path.join(ROOT, "scenes", "tests", "graphene_short.conf")
+    out = subprocess.check_output([EXE, "--conf-file", conf, "--out-dir", str(tmp_path)], cwd=ROOT, timeout=600).decode()
+    assert "simulation completed in" in out and "initialization completed in" in out
+    z = np.load(os.path.join(str(tmp_path), "field_samples.npz"))
+    st = ParseSettings()
+    st.parse_args(["--conf-file", conf, "--out-dir", str(tmp_path)])
+    st.parse_conf_file(conf)
+    st.correct_defaults()
+    assert st.grid_cells() == 91
+    bg = BoundGeom(st, scene_json("Au_graphene_box"), n_sets=2)     # same scene through the JSON fixture
+    bg.run()
+    assert int(z["info/n_clusters"][0]) == 1 and z["cluster_0/locations"].shape == (50, 3)
+    assert np.allclose(z["info/time_bounds"], bg.time_bounds(), rtol=1e-13)
+    assert np.array_equal(z["cluster_0/locations"], np.array(bg.get_monitor_locs()))
+    assert abs(z["info/cgs_params/res"][0] - 181 / 18) < 1e-12
+    n_saves = bg.n_t_pts // st.save_span
+    worst = 0.0
+    for i, series in enumerate(bg.get_field_times()):
+        t = z["cluster_0/point_%02d/time" % i]
+        got = t[:, 0] + 1j * t[:, 1]
+        assert len(got) >= n_saves
+        worst = max(worst, float(np.abs(got[:len(series)] - series).max()))
+    assert worst == 0.0
+    assert max(np.abs(s_).max() for s_ in bg.get_field_times()) > 1e-6
