@@ -117,6 +117,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     for (int a = 0; a < SJ_N_AUX; ++a) { CK(cudaStreamCreateWithFlags(&s->aux[a], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&s->ev_join[a], cudaEventDisableTiming)); }
     s->fan_on = getenv("SJ_NO_FAN") == NULL; s->fan_next = 0; s->fan_main = s->stream;
+    s->n_aux = getenv("SJ_N_AUX") ? std::min(std::max(atoi(getenv("SJ_N_AUX")), 1), SJ_N_AUX) : 3;
     const int n[3] = {g->n[0], g->n[1], g->n[2]};
     for (int d = 0; d < 3; ++d) {
         build_pml_table(s->sig[d], n[d], g->a, s->dt, g->pml_thickness, s->g.pml_R);
@@ -708,18 +709,18 @@ static void fill_box(const sj_sim::Box &B, PmlBox<T> &b, int n_sets) {
 // round-robin over the main stream and the side streams between fan_begin / fan_end
 static cudaStream_t fan_stream(sj_sim *s) {
     if (!s->fan_on) return s->fan_main;
-    const int q = s->fan_next++ % (SJ_N_AUX + 1);
+    const int q = s->fan_next++ % (s->n_aux + 1);
     return q == 0 ? s->fan_main : s->aux[q - 1];
 }
 static void fan_begin(sj_sim *s, cudaStream_t st) {
     s->fan_main = st; s->fan_next = 0;
     if (!s->fan_on) return;
     cudaEventRecord(s->ev_fork, st);
-    for (int a = 0; a < SJ_N_AUX; ++a) cudaStreamWaitEvent(s->aux[a], s->ev_fork, 0);
+    for (int a = 0; a < s->n_aux; ++a) cudaStreamWaitEvent(s->aux[a], s->ev_fork, 0);
 }
 static void fan_end(sj_sim *s) {
     if (!s->fan_on) return;
-    for (int a = 0; a < SJ_N_AUX; ++a) { cudaEventRecord(s->ev_join[a], s->aux[a]); cudaStreamWaitEvent(s->fan_main, s->ev_join[a], 0); }
+    for (int a = 0; a < s->n_aux; ++a) { cudaEventRecord(s->ev_join[a], s->aux[a]); cudaStreamWaitEvent(s->fan_main, s->ev_join[a], 0); }
 }
 
 template <typename T, int V, int LX>
@@ -788,10 +789,12 @@ static int launch_pass(sj_sim *s, int which, int k_begin, int k_end, cudaStream_
     k_begin = std::max(k_begin, s->kz0); k_end = std::min(k_end, s->kz1);
     if (k_begin >= k_end) return 0;
     fan_begin(s, st);
+    static const bool pml_first = getenv("SJ_PML_LAST") == NULL;   // small latency-bound PML kernels first, interior fills in
+    if (pml_first) launch_pml<T, V>(s, p, which, k_begin, k_end, st);
     if (s->int_lx == 32) launch_interior<T, V, 32>(s, p, which, k_begin, k_end, st);
     else if (s->int_lx == 16) launch_interior<T, V, 16>(s, p, which, k_begin, k_end, st);
     else launch_interior<T, V, 8>(s, p, which, k_begin, k_end, st);
-    launch_pml<T, V>(s, p, which, k_begin, k_end, st);
+    if (!pml_first) launch_pml<T, V>(s, p, which, k_begin, k_end, st);
     fan_end(s);
     CK(cudaGetLastError());
     return 0;

@@ -10,7 +10,7 @@
 #define SJ_MAX_SRC 4
 #define SJ_MAX_MAT 256
 #define SJ_N_PML_BOX 6
-#define SJ_N_AUX 3
+#define SJ_N_AUX 7
 
 // ---- kernel parameter blocks (passed by value) ---------------------------------------------
 template <typename T>
@@ -153,7 +153,7 @@ struct sj_sim {
     cudaEvent_t ev_a, ev_b;
     cudaStream_t aux[SJ_N_AUX];           // side streams: the independent kernels of a half-pass run concurrently
     cudaEvent_t ev_fork, ev_join[SJ_N_AUX];
-    int fan_next; cudaStream_t fan_main; bool fan_on;
+    int fan_next; cudaStream_t fan_main; bool fan_on; int n_aux;
     long long launches;
     double pole_points;       // sum over E component points of n_poles (owned slab)
     double pole_points_int;   // same, restricted to the interior-kernel box
