@@ -38,6 +38,7 @@ CONFIGS = {
     "Au_SiO2_bowtie": (REF + "/junctions/Au_SiO2_bowtie/junc.geom", REF + "/junctions/Au_SiO2_bowtie/params.conf",
                        ["--grid-res", "12.0", "--opts", RUN_SH_OPTS], {}),
     "Au_graphene_box": (ROOT + "/scenes/Au_graphene_box/junc.geom", ROOT + "/scenes/Au_graphene_box/params.conf", [], {}),
+    "quartz_box": (ROOT + "/scenes/quartz_box/junc.geom", ROOT + "/scenes/quartz_box/params.conf", [], {}),
 }
 MASK_CONFIGS = ["tests_run_slabs", "Au_SiO2_box", "Au_SiO2_bowtie", "Au_graphene_box"]
 

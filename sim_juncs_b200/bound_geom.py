@@ -13,9 +13,15 @@ from .scene import COMPONENTS, LIGHT_SPEED, THICK_SCALE, Scene
 
 class BoundGeom:
     def __init__(self, settings, scene, precision="f64", n_sets=2, integrated=True, device=-1, kz=None,
-                 verbose=False):
+                 verbose=False, phases=None):
         """settings: ParseSettings (after correct_defaults); scene: Scene or path to a scene JSON.
-        n_sets = 2 reproduces meep's complex fields (the reference never calls use_real_fields)."""
+        n_sets = 2 reproduces meep's complex fields (the reference never calls use_real_fields).
+        phases = [phi_0, phi_1, ...] runs a CEP sweep as one batch instead (BASELINE config 5): one real
+        field set per extra source phase, all sharing the rasterized materials; field_times is then
+        indexed [phase][monitor]."""
+        self.phases = None if phases is None else [float(x) for x in phases]
+        if self.phases is not None:
+            n_sets = len(self.phases)
         if isinstance(scene, str):
             scene = Scene.load(scene)
         if scene.ercode != 0:
@@ -78,7 +84,7 @@ class BoundGeom:
             if verbose:
                 print("Adding Gaussian envelope: f=%f, w=%f, t_0=%f, t_f=%f (meep units)" % (frequency, width, start_time, end_time))
             self.sim.add_gaussian_source(info.component, lo, hi, info.amplitude, frequency, width, info.phase,
-                                         start_time, end_time, integrated)
+                                         start_time, end_time, integrated, set_phase=self.phases)
             self.sources.append(info)
             self.ttot = self.sim.last_source_time() + self.post_source_t * LIGHT_SPEED * settings.um_scale
         self.monitor_locs = [tuple(p) for p in scene.monitor_locs]
@@ -121,6 +127,10 @@ class BoundGeom:
             print("error on step %d: %s" % (self.n_t_pts, err))
         self.t_run = time.time() - t0
         series = self.sim.monitors()                 # [n_saves][n_mon][n_sets]
+        if self.phases is not None:
+            self.field_times = [[series[:, j, q].astype(np.complex128) for j in range(series.shape[1])]
+                                for q in range(series.shape[2])]
+            return
         if self.n_sets >= 2:
             cplx = series[:, :, 0] + 1j * series[:, :, 1]
         else:

