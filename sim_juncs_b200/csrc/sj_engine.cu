@@ -117,7 +117,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     for (int a = 0; a < SJ_N_AUX; ++a) { CK(cudaStreamCreateWithFlags(&s->aux[a], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&s->ev_join[a], cudaEventDisableTiming)); }
     s->fan_on = getenv("SJ_NO_FAN") == NULL; s->fan_next = 0; s->fan_main = s->stream;
-    s->n_aux = getenv("SJ_N_AUX") ? std::min(std::max(atoi(getenv("SJ_N_AUX")), 1), SJ_N_AUX) : 3;
+    s->trace_on = false;
+    s->n_aux = getenv("SJ_N_AUX") ? std::min(std::max(atoi(getenv("SJ_N_AUX")), 1), SJ_N_AUX) : 5;
     const int n[3] = {g->n[0], g->n[1], g->n[2]};
     for (int d = 0; d < 3; ++d) {
         build_pml_table(s->sig[d], n[d], g->a, s->dt, g->pml_thickness, s->g.pml_R);
@@ -706,14 +707,31 @@ static void fill_box(const sj_sim::Box &B, PmlBox<T> &b, int n_sets) {
     for (int c = 0; c < 3; ++c) { b.D[c] = (T *)B.D[c]; b.B[c] = (T *)B.B[c]; b.UD[c] = (T *)B.UD[c]; b.UB[c] = (T *)B.UB[c]; }
 }
 
+// debug timeline: TR(s, name, stream, launch-expression)
+#define TR(s, nm, strm, ...)                                                                        \
+    do {                                                                                           \
+        cudaStream_t st__ = (strm);                                                                \
+        if ((s)->trace_on) { cudaEvent_t a__; cudaEventCreate(&a__); cudaEventRecord(a__, st__); (s)->tr_ev.push_back(a__); (s)->tr_name.push_back(nm); } \
+        __VA_ARGS__;                                                                               \
+        if ((s)->trace_on) { cudaEvent_t b__; cudaEventCreate(&b__); cudaEventRecord(b__, st__); (s)->tr_ev.push_back(b__); } \
+    } while (0)
+
 // round-robin over the main stream and the side streams between fan_begin / fan_end
-static cudaStream_t fan_stream(sj_sim *s) {
+static cudaStream_t fan_stream(sj_sim *s, int cls = 1) {
+    // cls 0: the big interior kernels get the main stream / first side stream to themselves;
+    // cls 1: PML lists round-robin over the remaining side streams
     if (!s->fan_on) return s->fan_main;
-    const int q = s->fan_next++ % (s->n_aux + 1);
-    return q == 0 ? s->fan_main : s->aux[q - 1];
+    static const bool dedicated = getenv("SJ_FAN_SHARED") == NULL;
+    if (!dedicated || s->n_aux < 3) {
+        const int q = s->fan_next++ % (s->n_aux + 1);
+        return q == 0 ? s->fan_main : s->aux[q - 1];
+    }
+    if (cls == 0) { const int q = s->fan_int++ % 2; return q == 0 ? s->fan_main : s->aux[0]; }
+    const int q = s->fan_next++ % (s->n_aux - 1);
+    return s->aux[1 + q];
 }
 static void fan_begin(sj_sim *s, cudaStream_t st) {
-    s->fan_main = st; s->fan_next = 0;
+    s->fan_main = st; s->fan_next = 0; s->fan_int = 0;
     if (!s->fan_on) return;
     cudaEventRecord(s->ev_fork, st);
     for (int a = 0; a < s->n_aux; ++a) cudaStreamWaitEvent(s->aux[a], s->ev_fork, 0);
@@ -727,8 +745,8 @@ template <typename T, int V, int LX>
 static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_begin, int k_end, cudaStream_t st) {
     IntGeom g; dim3 grd; interior_geom(s, k_begin, k_end, g, grd);
     if (g.nzc <= 0 || !grd.x || !grd.y) return;
-    if (which == 0) { h_interior<T, V, LX><<<grd, 256, 0, fan_stream(s)>>>(p, g, k_begin, k_end); s->launches++; return; }
-    if (s->il_int[0].n) { e_interior<T, V, LX, 0><<<s->il_int[0].n, 256, 0, fan_stream(s)>>>(p, g, s->il_int[0].dev, k_begin, k_end); s->launches++; }
+    if (which == 0) { TR(s, "h_interior<LX>", fan_stream(s, 0), h_interior<T, V, LX><<<grd, 256, 0, st__>>>(p, g, k_begin, k_end)); s->launches++; return; }
+    if (s->il_int[0].n) { TR(s, "e_interior<LX, 0>", fan_stream(s, 0), e_interior<T, V, LX, 0><<<s->il_int[0].n, 256, 0, st__>>>(p, g, s->il_int[0].dev, k_begin, k_end)); s->launches++; }
     if (s->il_int[1].n) {
         const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;
         static const bool stg = getenv("SJ_NO_STAGE") == NULL;
@@ -738,13 +756,13 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
             const int ns = std::max(s->n_slots, 1);
             const size_t smem = (size_t)2 * (8 + 6 * ns) * 256 * 16;
             auto k1 = e_interior_stg<T, V, LX, 1>; auto k2 = e_interior_stg<T, V, LX, 2>;
-            if (ns == 1) { cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k1<<<n, 256, smem, fan_stream(s)>>>(p, g, d, k_begin, k_end); }
-            else { cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k2<<<n, 256, smem, fan_stream(s)>>>(p, g, d, k_begin, k_end); }
+            if (ns == 1) { cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); TR(s, "k1", fan_stream(s, 0), k1<<<n, 256, smem, st__>>>(p, g, d, k_begin, k_end)); }
+            else { cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); TR(s, "k2", fan_stream(s, 0), k2<<<n, 256, smem, st__>>>(p, g, d, k_begin, k_end)); }
             (void)attr_done;
         }
-        else if (s->n_slots <= 1) e_interior<T, V, LX, 1><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
-        else if (s->n_slots == 2) e_interior<T, V, LX, 2><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
-        else e_interior<T, V, LX, 4><<<n, 256, 0, fan_stream(s)>>>(p, g, d, k_begin, k_end);
+        else if (s->n_slots <= 1) TR(s, "e_interior<LX, 1>", fan_stream(s, 0), e_interior<T, V, LX, 1><<<n, 256, 0, st__>>>(p, g, d, k_begin, k_end));
+        else if (s->n_slots == 2) TR(s, "e_interior<LX, 2>", fan_stream(s, 0), e_interior<T, V, LX, 2><<<n, 256, 0, st__>>>(p, g, d, k_begin, k_end));
+        else TR(s, "e_interior<LX, 4>", fan_stream(s, 0), e_interior<T, V, LX, 4><<<n, 256, 0, st__>>>(p, g, d, k_begin, k_end));
         s->launches++;
     }
 }
@@ -752,11 +770,11 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
 template <typename T, int V, int LX, bool FACE>
 static void launch_e_pml(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, const ItemList (&L)[2], int k_begin, int k_end,
                          cudaStream_t st) {
-    if (L[0].n) { e_pml_tile<T, V, LX, 0, FACE><<<L[0].n, 256, 0, fan_stream(s)>>>(p, bs, L[0].dev, k_begin, k_end); s->launches++; }
+    if (L[0].n) { TR(s, "e_pml_tile<LX, 0, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 0, FACE><<<L[0].n, 256, 0, st__>>>(p, bs, L[0].dev, k_begin, k_end)); s->launches++; }
     if (L[1].n) {
-        if (s->n_slots <= 1) e_pml_tile<T, V, LX, 1, FACE><<<L[1].n, 256, 0, fan_stream(s)>>>(p, bs, L[1].dev, k_begin, k_end);
-        else if (s->n_slots == 2) e_pml_tile<T, V, LX, 2, FACE><<<L[1].n, 256, 0, fan_stream(s)>>>(p, bs, L[1].dev, k_begin, k_end);
-        else e_pml_tile<T, V, LX, 4, FACE><<<L[1].n, 256, 0, fan_stream(s)>>>(p, bs, L[1].dev, k_begin, k_end);
+        if (s->n_slots <= 1) TR(s, "e_pml_tile<LX, 1, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 1, FACE><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
+        else if (s->n_slots == 2) TR(s, "e_pml_tile<LX, 2, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 2, FACE><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
+        else TR(s, "e_pml_tile<LX, 4, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 4, FACE><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
         s->launches++;
     }
 }
@@ -765,8 +783,8 @@ template <typename T, int V, int LX>
 static void launch_pml_lx(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, int which, int wn, int k_begin, int k_end,
                           cudaStream_t st) {
     if (which == 0) {
-        if (s->il_h[0][wn].n) { h_pml_tile<T, V, LX, false><<<s->il_h[0][wn].n, 256, 0, fan_stream(s)>>>(p, bs, s->il_h[0][wn].dev, k_begin, k_end); s->launches++; }
-        if (s->il_h[1][wn].n) { h_pml_tile<T, V, LX, true><<<s->il_h[1][wn].n, 256, 0, fan_stream(s)>>>(p, bs, s->il_h[1][wn].dev, k_begin, k_end); s->launches++; }
+        if (s->il_h[0][wn].n) { TR(s, "h_pml_tile<LX, false>", fan_stream(s), h_pml_tile<T, V, LX, false><<<s->il_h[0][wn].n, 256, 0, st__>>>(p, bs, s->il_h[0][wn].dev, k_begin, k_end)); s->launches++; }
+        if (s->il_h[1][wn].n) { TR(s, "h_pml_tile<LX, true>", fan_stream(s), h_pml_tile<T, V, LX, true><<<s->il_h[1][wn].n, 256, 0, st__>>>(p, bs, s->il_h[1][wn].dev, k_begin, k_end)); s->launches++; }
         return;
     }
     launch_e_pml<T, V, LX, false>(s, p, bs, s->il_pml[0][wn], k_begin, k_end, st);
@@ -934,6 +952,29 @@ extern "C" int sj_get_counts(sj_sim *s, double out[6]) {
         inter[d] = cnt;
     }
     out[5] = out[0] - inter[0] * inter[1] * inter[2];
+    return SJ_OK;
+}
+
+extern "C" int sj_trace_step(sj_sim *s) {
+    if (!s) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
+    int rc = ensure_drive(s, s->steps_done + 2); if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    s->trace_on = true; s->tr_ev.clear(); s->tr_name.clear();
+    CK(cudaEventCreate(&s->tr_origin)); CK(cudaEventRecord(s->tr_origin, s->stream));
+    rc = do_pass(s, 0, s->kz0, s->kz1, s->stream); if (rc) return rc;
+    rc = do_pass(s, 1, s->kz0, s->kz1, s->stream); if (rc) return rc;
+    tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev); s->steps_done++;
+    s->trace_on = false;
+    CK(cudaStreamSynchronize(s->stream));
+    for (int a = 0; a < s->n_aux; ++a) CK(cudaStreamSynchronize(s->aux[a]));
+    for (size_t i = 0; i < s->tr_name.size(); ++i) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, s->tr_origin, s->tr_ev[2 * i]); cudaEventElapsedTime(&t1, s->tr_origin, s->tr_ev[2 * i + 1]);
+        printf("trace %-28s start %8.1f us  end %8.1f us  dur %7.1f us\n", s->tr_name[i].c_str(), t0 * 1e3, t1 * 1e3, (t1 - t0) * 1e3);
+    }
+    for (auto e : s->tr_ev) cudaEventDestroy(e);
+    s->tr_ev.clear(); s->tr_name.clear();
     return SJ_OK;
 }
 

@@ -153,7 +153,9 @@ struct sj_sim {
     cudaEvent_t ev_a, ev_b;
     cudaStream_t aux[SJ_N_AUX];           // side streams: the independent kernels of a half-pass run concurrently
     cudaEvent_t ev_fork, ev_join[SJ_N_AUX];
-    int fan_next; cudaStream_t fan_main; bool fan_on; int n_aux;
+    int fan_next, fan_int; cudaStream_t fan_main; bool fan_on; int n_aux;
+    // SJ_TRACE=1: per-launch CUDA events of one traced step (debug timeline, printed by sj_trace_dump)
+    bool trace_on; std::vector<cudaEvent_t> tr_ev; std::vector<std::string> tr_name; cudaEvent_t tr_origin;
     long long launches;
     double pole_points;       // sum over E component points of n_poles (owned slab)
     double pole_points_int;   // same, restricted to the interior-kernel box

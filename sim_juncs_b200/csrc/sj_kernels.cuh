@@ -19,6 +19,13 @@
 #pragma once
 #include "sj_internal.h"
 
+#ifndef SJ_HFACE_BLOCKS
+#define SJ_HFACE_BLOCKS 3
+#endif
+#ifndef SJ_EFACE_BLOCKS
+#define SJ_EFACE_BLOCKS 3
+#endif
+
 template <typename T, int V> struct VecOf;
 template <> struct VecOf<double, 2> { typedef double2 type; };
 template <> struct VecOf<float, 4> { typedef float4 type; };
@@ -665,7 +672,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
 
 // FACE = false: general tiles (PD 0); FACE = true: face tiles, normal direction taken from the item
 template <typename T, int V, int LX, bool FACE>
-__global__ void __launch_bounds__(256, 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+__global__ void __launch_bounds__(256, FACE ? SJ_HFACE_BLOCKS : 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
                                                      int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
     const PmlBox<T> &b = bs.b[it.box];
@@ -804,7 +811,7 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
 }
 
 template <typename T, int V, int LX, int NS, bool FACE>
-__global__ void __launch_bounds__(256, NS == 0 ? 2 : 1) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+__global__ void __launch_bounds__(256, NS == 0 ? (FACE ? SJ_EFACE_BLOCKS : 2) : 1) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
                                                                    int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
     const PmlBox<T> &b = bs.b[it.box];
