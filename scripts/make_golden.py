@@ -7,7 +7,7 @@ reference sources in place (oracle/Makefile target `ref`) and writes
   tests/golden/masks_<name>.npz      composite_object::in() over the whole Yee grid, per E component
   tests/golden/inside_points.npz     10 000 LCG points + the six known-answer points of
                                      reference src/main_test.cpp:1556-1561 through tests/test.geom
-Usage: python scripts/make_golden.py
+Usage: python scripts/make_golden.py [scene-name ...]
 """
 import json
 import os
@@ -39,6 +39,9 @@ CONFIGS = {
                        ["--grid-res", "12.0", "--opts", RUN_SH_OPTS], {}),
     "Au_graphene_box": (ROOT + "/scenes/Au_graphene_box/junc.geom", ROOT + "/scenes/Au_graphene_box/params.conf", [], {}),
     "quartz_box": (ROOT + "/scenes/quartz_box/junc.geom", ROOT + "/scenes/quartz_box/params.conf", [], {}),
+    # scene-language feature sweep for the own parser (tests/test_cgs_parser.py)
+    "parser_features": (ROOT + "/scenes/tests/parser_features.geom", REF + "/tests/run.conf", [],
+                        dict(pml_thickness=1.0, len=4.0, um_scale=2.0, resolution=4.0)),
 }
 MASK_CONFIGS = ["tests_run_slabs", "Au_SiO2_box", "Au_SiO2_bowtie", "Au_graphene_box"]
 
@@ -81,7 +84,8 @@ def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
     os.makedirs(os.path.join(ROOT, "scenes", "json"), exist_ok=True)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for name in CONFIGS:
+    only = sys.argv[1:]                      # optional: regenerate just these scene dumps
+    for name in (only or CONFIGS):
         s, geom = settings_for(name)
         out = subprocess.check_output(dump_args(s, geom, "dump"), cwd=REF)
         doc = json.loads(out)
@@ -90,6 +94,8 @@ def main():
         with open(os.path.join(ROOT, "scenes", "json", name + ".json"), "w") as fp:
             json.dump(doc, fp, separators=(",", ":"))
         print(name, "ercode", doc["ercode"], "roots", doc["n_roots"], "grid", s.grid_cells(), "a", s.resolution)
+    if only:
+        return
     for name in MASK_CONFIGS:
         s, geom = settings_for(name)
         n, a = s.grid_cells(), s.resolution

@@ -12,9 +12,10 @@ from .scene import COMPONENTS, LIGHT_SPEED, THICK_SCALE, Scene
 
 
 class BoundGeom:
-    def __init__(self, settings, scene, precision="f64", n_sets=2, integrated=True, device=-1, kz=None,
+    def __init__(self, settings, scene=None, precision="f64", n_sets=2, integrated=True, device=-1, kz=None,
                  verbose=False, phases=None):
-        """settings: ParseSettings (after correct_defaults); scene: Scene or path to a scene JSON.
+        """settings: ParseSettings (after correct_defaults); scene: Scene, a path to a .geom file or to a
+        scene JSON, or None to read settings.geom_fname as the reference does (disp.cpp:556).
         n_sets = 2 reproduces meep's complex fields (the reference never calls use_real_fields).
         phases = [phi_0, phi_1, ...] runs a CEP sweep as one batch instead (BASELINE config 5): one real
         field set per extra source phase, all sharing the rasterized materials; field_times is then
@@ -22,8 +23,10 @@ class BoundGeom:
         self.phases = None if phases is None else [float(x) for x in phases]
         if self.phases is not None:
             n_sets = len(self.phases)
+        if scene is None:
+            scene = settings.geom_fname
         if isinstance(scene, str):
-            scene = Scene.load(scene)
+            scene = Scene.load(scene) if scene.endswith(".json") else Scene.from_geom(scene, settings)
         if scene.ercode != 0:
             raise RuntimeError("Scene parsing failed (parse_ercode %d)" % scene.ercode)   # disp.cpp:562-565
         self.problem = scene

@@ -246,3 +246,10 @@ class Scene:
     def load(path):
         with open(path, "r") as fp:
             return Scene(json.load(fp))
+
+    @staticmethod
+    def from_geom(path, settings):
+        """read a .geom file with this repo's own CGS reader (sim_juncs_b200/cgs.py); the scene::scene(fname,
+        context) call of bound_geom's constructor, disp.cpp:556."""
+        from . import cgs
+        return Scene(cgs.parse_geom(path, settings))

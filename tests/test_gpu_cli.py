@@ -41,3 +41,28 @@ def test_cpp_cli_matches_python_mirror(tmp_path, scene_json):
         worst = max(worst, float(np.abs(got[:len(series)] - series).max()))
     assert worst == 0.0
     assert max(np.abs(s_).max() for s_ in bg.get_field_times()) > 1e-6
+
+
+def test_python_cli_with_own_parser_matches_reference_parser_path(tmp_path, scene_json):
+    """`python -m sim_juncs_b200` reads the .geom with this repo's own CGS reader; the run must be
+    bit-identical to the same scene entering through the reference parser's JSON dump."""
+    import sys
+    conf = os.path.join(ROOT, "scenes", "tests", "graphene_short.conf")
+    out = subprocess.check_output([sys.executable, "-m", "sim_juncs_b200", "--conf-file", conf, "--out-dir", str(tmp_path)],
+                                  cwd=ROOT, timeout=600).decode()
+    assert "simulation completed in" in out and "saving timeseries completed in" in out
+    z = np.load(os.path.join(str(tmp_path), "field_samples.npz"))
+    st = ParseSettings()
+    st.parse_args(["--conf-file", conf, "--out-dir", str(tmp_path)])
+    st.parse_conf_file(conf)
+    st.correct_defaults()
+    bg = BoundGeom(st, scene_json("Au_graphene_box"), n_sets=2)
+    bg.run()
+    assert np.array_equal(z["cluster_0/locations"], np.array(bg.get_monitor_locs()))
+    worst = 0.0
+    for i, series in enumerate(bg.get_field_times()):
+        t = z["cluster_0/point_%02d/time" % i]
+        got = t[:, 0] + 1j * t[:, 1]
+        worst = max(worst, float(np.abs(got[:len(series)] - series).max()))
+    assert worst == 0.0
+    assert max(np.abs(s_).max() for s_ in bg.get_field_times()) > 1e-6
