@@ -103,7 +103,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->mt_chi = s->mt_coef = NULL; s->mt_np = NULL;
     s->F = NULL;
     for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = s->siginvd[c] = NULL; }
-    s->flags_int = NULL; s->mt_eps = NULL; s->pml_lx = 32;
+    s->flags_int = NULL; s->mt_eps = NULL; s->src_dev = NULL; s->pml_lx = 32; s->pml_lx_n = 8; s->pml_v = 2;
     for (int a = 0; a < 2; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; for (int b = 0; b < 2; ++b) { s->il_h[a][b].dev = NULL; s->il_h[a][b].n = 0; for (int c = 0; c < 2; ++c) { s->il_pml[a][b][c].dev = NULL; s->il_pml[a][b][c].n = 0; } } } s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
     for (int i = 0; i < 256; ++i) s->lut_inv[i] = (uint8_t)i;
     s->Pall = NULL;
@@ -190,8 +190,13 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     // rectangles: the part with a single non-zero sigma ("face", kind = normal direction) and the
     // frame around it where sigmas overlap (kind 0, general kernel).
     {
-        const int V = s->prec == SJ_F64 ? 2 : 4;
-        s->pml_lx = std::max(s->int_lx, 16);
+        // PML kernels are instruction-latency bound at one or two blocks per SM with full 128-bit vectors
+        // (ncu: 2 warps per scheduler); half-width vectors halve the registers and double the resident warps
+        const bool half = getenv("SJ_PML_HALF") ? atoi(getenv("SJ_PML_HALF")) != 0 : true;
+        const int V = (s->prec == SJ_F64 ? 2 : 4) / (half ? 2 : 1);
+        s->pml_v = V;
+        s->pml_lx = half ? 32 : std::max(s->int_lx, 16);
+        s->pml_lx_n = half ? 16 : 8;
         const int zc_face = getenv("SJ_ZC_FACE") ? atoi(getenv("SJ_ZC_FACE")) : 8, zc_gen = getenv("SJ_ZC_GEN") ? atoi(getenv("SJ_ZC_GEN")) : 4;
         const int L[3] = {s->lo[0], s->lo[1], s->lo[2]}, Hh[3] = {s->hi[0], s->hi[1], s->hi[2]};
         const int N1x = n[0] + 1, N1y = n[1] + 1;
@@ -213,8 +218,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
             }
             for (const Rect &R : rects) {
                 if (R.i1 <= R.i0 || R.j1 <= R.j0) continue;
-                const bool nar = (R.i1 - R.i0 <= 8 * V);
-                const int tw = (nar ? 8 : s->pml_lx) * V, th = (32 / (nar ? 8 : s->pml_lx)) * 8;
+                const bool nar = (R.i1 - R.i0 <= s->pml_lx_n * V);
+                const int tw = (nar ? s->pml_lx_n : s->pml_lx) * V, th = (32 / (nar ? s->pml_lx_n : s->pml_lx)) * 8;
                 const int zchunk = R.kind ? zc_face : zc_gen;   // short marches: these lists are small, keep every SM busy
                 for (int q = 0; q < g->n_sets; ++q)
                     for (int kb = B.lo[2]; kb < B.hi[2]; kb += zchunk)
@@ -251,7 +256,7 @@ extern "C" void sj_destroy(sj_sim *s) {
     for (int c = 0; c < 3; ++c) { cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
     cudaFree(s->flags_int); cudaFree(s->mt_eps);
     for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) { cudaFree(s->il_h[a][b].dev); for (int c = 0; c < 2; ++c) cudaFree(s->il_pml[a][b][c].dev); } }
-    cudaFree(s->Pall);
+    cudaFree(s->Pall); cudaFree(s->src_dev);
     for (auto &B : s->boxes) cudaFree(B.base);
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
     cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
@@ -439,9 +444,9 @@ int sj_finish_materials(sj_sim *s) {
                 std::vector<unsigned> f2(std::max<size_t>(src.size(), 1), 0u);
                 if (!src.empty()) {
                     unsigned *df; CK(cudaMalloc((void **)&df, src.size() * sizeof(unsigned)));
-                    const int lxw = wn ? 8 : s->pml_lx;
+                    const int lxw = wn ? s->pml_lx_n : s->pml_lx;
                     item_flags_kernel<<<(unsigned)src.size(), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->il_h[f][wn].dev,
-                        lxw * V, (32 / lxw) * 8, s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df);
+                        lxw * s->pml_v, (32 / lxw) * 8, s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df);
                     CK(cudaMemcpyAsync(f2.data(), df, src.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
                     CK(cudaStreamSynchronize(s->stream));
                     cudaFree(df);
@@ -542,6 +547,22 @@ static int source_axis(const sj_sim *s, int comp, int d, double lo, double hi, i
     return 0;
 }
 
+// source descriptors live in device memory (the kernels read them on the source planes only)
+template <typename T>
+static int upload_sources(sj_sim *s) {
+    SrcDev<T> h[SJ_MAX_SRC];
+    memset(h, 0, sizeof h);
+    for (size_t q = 0; q < s->srcs.size(); ++q) {
+        const HostSource &g = s->srcs[q];
+        h[q].comp = g.comp;
+        for (int d = 0; d < 3; ++d) { h[q].lo[d] = g.lo[d]; h[q].hi[d] = g.hi[d]; h[q].w[d] = (const T *)s->srcw[q][d]; }
+        h[q].amp_re = (T)g.amp_re; h[q].amp_im = (T)g.amp_im;
+    }
+    if (!s->src_dev) CK(cudaMalloc(&s->src_dev, sizeof(SrcDev<double>) * SJ_MAX_SRC));
+    CK(cudaMemcpy(s->src_dev, h, sizeof h, cudaMemcpyHostToDevice));
+    return SJ_OK;
+}
+
 extern "C" int sj_add_gaussian_source(sj_sim *s, int comp, const double lo[3], const double hi[3], double amp_re,
                                       double amp_im, double freq, double width, double phase, double t_start,
                                       double t_end, int integrated, const double *set_phase) {
@@ -570,7 +591,7 @@ extern "C" int sj_add_gaussian_source(sj_sim *s, int comp, const double lo[3], c
     }
     s->srcs.push_back(g);
     s->drive_dirty = true;
-    return SJ_OK;
+    return s->prec == SJ_F64 ? upload_sources<double>(s) : upload_sources<float>(s);
 }
 
 // drive table [step][src][set][2]: {S_n, dt*J_n}; S_n = Re/Im(amp * dipole(n dt)) for integrated
@@ -689,12 +710,8 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     p.mt_eps = (const T *)s->mt_eps; p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef; p.first_disp = s->first_disp;
     p.courant = (T)s->g.courant;
     p.n_src = (int)s->srcs.size();
-    for (int q = 0; q < p.n_src; ++q) {
-        const HostSource &g = s->srcs[q];
-        p.src[q].comp = g.comp;
-        for (int d = 0; d < 3; ++d) { p.src[q].lo[d] = g.lo[d]; p.src[q].hi[d] = g.hi[d]; p.src[q].w[d] = (const T *)s->srcw[q][d]; }
-        p.src[q].amp_re = (T)g.amp_re; p.src[q].amp_im = (T)g.amp_im;
-    }
+    for (int q = 0; q < p.n_src; ++q) { p.src_klo[q] = s->srcs[q].lo[2]; p.src_khi[q] = s->srcs[q].hi[2]; }
+    p.srcd = (const SrcDev<T> *)s->src_dev;
     p.drive = (const T *)s->drive;
     p.step = s->step_dev;
 }
@@ -796,6 +813,11 @@ static void launch_pml(sj_sim *s, const KParams<T> &p, int which, int k_begin, i
     PmlBoxSet<T> bs;
     memset(&bs, 0, sizeof bs);
     for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi], s->g.n_sets);
+    if (s->pml_v != V) {       // half-width vectors: wide tiles 32 lanes, narrow tiles 16
+        launch_pml_lx<T, V / 2, 32>(s, p, bs, which, 0, k_begin, k_end, st);
+        launch_pml_lx<T, V / 2, 16>(s, p, bs, which, 1, k_begin, k_end, st);
+        return;
+    }
     if (s->pml_lx == 32) launch_pml_lx<T, V, 32>(s, p, bs, which, 0, k_begin, k_end, st);
     else launch_pml_lx<T, V, 16>(s, p, bs, which, 0, k_begin, k_end, st);
     launch_pml_lx<T, V, 8>(s, p, bs, which, 1, k_begin, k_end, st);

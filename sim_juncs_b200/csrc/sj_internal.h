@@ -49,7 +49,8 @@ struct KParams {
     const T *siginv[3];   // 1/(1+sig), meep's siginv table (kappa == 1)
     T courant;
     int n_src;
-    SrcDev<T> src[SJ_MAX_SRC];
+    int src_klo[SJ_MAX_SRC], src_khi[SJ_MAX_SRC];   // z index range of every source (block-uniform plane test)
+    const SrcDev<T> *srcd;                          // [n_src] descriptors in device memory (read on source planes only)
     const T *drive;       // [step][src][set][2] = {S (integrated dipole), dt*current}
     const long long *step;// device step counter
 };
@@ -125,12 +126,14 @@ struct sj_sim {
     std::vector<WorkItem> h_items[2][2];   // PML tiles: [general|face][wide|narrow]
     ItemList il_h[2][2];                   // H-pass PML lists, same indexing
     ItemList il_int[2], il_pml[2][2][2];   // E-pass lists: interior [uniform|general]; PML [general|face][wide|narrow][uniform|general]
-    int pml_lx;                            // lanes along x of the wide PML tiles
+    int pml_lx, pml_lx_n;                  // lanes along x of the wide / narrow PML tiles
+    int pml_v;                             // elements per thread in the PML kernels (full or half vector)
     int int_lx, int_zchunk;   // interior tiling: lanes along x per warp, planes per chunk
     int first_disp;
     bool present[256];        // material id (sorted order) occurs in the slab
     uint8_t lut_inv[256];     // material id -> id as given by the caller
     bool materials_set;
+    void *src_dev;            // SrcDev<T>[SJ_MAX_SRC] on the device
     std::vector<sj_material> mats;         // as given by the caller / rasterizer (id = caller id)
     std::vector<sj_material> mats_sorted;  // device order: non-dispersive first
 

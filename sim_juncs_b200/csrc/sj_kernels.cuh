@@ -22,6 +22,9 @@
 #ifndef SJ_HFACE_BLOCKS
 #define SJ_HFACE_BLOCKS 3
 #endif
+#ifndef SJ_EINT0_BLOCKS
+#define SJ_EINT0_BLOCKS 4
+#endif
 #ifndef SJ_EFACE_BLOCKS
 #define SJ_EFACE_BLOCKS 3
 #endif
@@ -29,6 +32,8 @@
 template <typename T, int V> struct VecOf;
 template <> struct VecOf<double, 2> { typedef double2 type; };
 template <> struct VecOf<float, 4> { typedef float4 type; };
+template <> struct VecOf<double, 1> { typedef double type; };
+template <> struct VecOf<float, 2> { typedef float2 type; };
 
 template <typename T, int V>
 struct Vec {
@@ -56,7 +61,8 @@ struct Vec {
 
 template <int V>
 __device__ __forceinline__ void load_bytes(const uint8_t *p, unsigned char (&m)[V]) {
-    if (V == 2) { const uchar2 t = *reinterpret_cast<const uchar2 *>(p); m[0] = t.x; m[1] = t.y; }
+    if (V == 1) m[0] = *p;
+    else if (V == 2) { const uchar2 t = *reinterpret_cast<const uchar2 *>(p); m[0] = t.x; m[V > 1 ? 1 : 0] = t.y; }
     else { const uchar4 t = *reinterpret_cast<const uchar4 *>(p); m[0] = t.x; m[1] = t.y; m[V > 2 ? 2 : 0] = t.z; m[V > 3 ? 3 : 0] = t.w; }
 }
 
@@ -66,17 +72,27 @@ template <typename T>
 __device__ __forceinline__ unsigned src_plane_mask(const KParams<T> &p, int k) {
     unsigned m = 0;
     for (int s = 0; s < p.n_src; ++s)
-        if (k >= p.src[s].lo[2] && k <= p.src[s].hi[2]) m |= 1u << s;
+        if (k >= p.src_klo[s] && k <= p.src_khi[s]) m |= 1u << s;
     return m;
 }
-// S_n, S_{n+1} (integrated dipole) and dt*J_n (current) weights at a Yee point of component c
+// does any source touch the planes [kb, ke)?  Evaluated once per block: away from the source planes
+// the per-plane test and the injection code are skipped by one uniform branch.
+template <typename T>
+__device__ __forceinline__ bool src_in_chunk(const KParams<T> &p, int kb, int ke) {
+    bool any = false;
+    for (int s = 0; s < p.n_src; ++s) any |= (ke > p.src_klo[s] && kb <= p.src_khi[s]);
+    return any;
+}
+// S_n, S_{n+1} (integrated dipole) and dt*J_n (current) weights at a Yee point of component c.
+// Only the SRC = true instantiation of a kernel body contains this code; blocks whose planes hold no
+// source take the SRC = false body (one uniform branch per block), which has no source arithmetic.
 template <typename T>
 __device__ __forceinline__ void source_parts(const KParams<T> &p, unsigned smask, int c, int i, int j, int k, int set,
                                              long long step, T &S0, T &S1, T &J) {
     S0 = S1 = J = T(0);
     for (int s = 0; s < p.n_src; ++s) {
         if (!((smask >> s) & 1u)) continue;
-        const SrcDev<T> &g = p.src[s];
+        const SrcDev<T> &g = p.srcd[s];
         if (g.comp != c || j < g.lo[1] || j > g.hi[1] || i < g.lo[0] || i > g.hi[0]) continue;
         const T wgt = g.w[0][i - g.lo[0]] * g.w[1][j - g.lo[1]] * g.w[2][k - g.lo[2]];
         const T *d0 = p.drive + ((step * p.n_src + s) * p.n_sets + set) * 2;
@@ -210,7 +226,7 @@ __global__ void __launch_bounds__(256, 4) h_interior(KParams<T> p, IntGeom g, in
 // ------------------------------------------------------------------------------------------
 // NS = 0: uniform non-dispersive material (chi_u), no material bytes read; NS > 0: general path for
 // materials with up to NS poles (every polarisation load is issued with the field loads).
-template <typename T, int V, int LX, int NS>
+template <typename T, int V, int LX, int NS, bool SRC>
 __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGeom &g, int i0, int j, int lx, int set, int kb,
                                                 int ke, T chi_u) {
     constexpr bool GEN = NS > 0;
@@ -254,7 +270,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
         if (edge) { hz_p = (pH + fcs2)[-1]; hy_p = (pH + fcs)[-1]; }
-        const unsigned smask = src_plane_mask(p, k);
+        const unsigned smask = SRC ? src_plane_mask(p, k) : 0u;
         if (st) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -263,7 +279,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
                 T dDx = -(C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]));
                 T dDy = -(C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi));
                 T dDz = -(C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]));
-                if (smask) {
+                if (SRC && smask) {
                     T S0, S1, J;
                     source_parts(p, smask, 0, i0 + v, j, k, set, step, S0, S1, J); dDx -= (S1 - S0) + J;
                     source_parts(p, smask, 1, i0 + v, j, k, set, step, S0, S1, J); dDy -= (S1 - S0) + J;
@@ -292,7 +308,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
 }
 
 template <typename T, int V, int LX, int NS>
-__global__ void __launch_bounds__(256, NS == 0 ? 3 : 1) e_interior(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
+__global__ void __launch_bounds__(256, NS == 0 ? SJ_EINT0_BLOCKS : 1) e_interior(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
                                                                    int k_begin, int k_end) {
     const WorkItem it = items[blockIdx.x];
     constexpr int RW = 32 / LX;
@@ -302,7 +318,9 @@ __global__ void __launch_bounds__(256, NS == 0 ? 3 : 1) e_interior(KParams<T> p,
     const int j = it.j0 + warp * RW + ly;
     const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
     if (kb >= ke) return;
-    e_interior_body<T, V, LX, NS>(p, g, i0, j, lx, it.set, kb, ke, NS > 0 ? T(0) : p.mt_chi[it.mat]);
+    const T chi_u = NS > 0 ? T(0) : p.mt_chi[it.mat];
+    if (src_in_chunk(p, kb, ke)) e_interior_body<T, V, LX, NS, true>(p, g, i0, j, lx, it.set, kb, ke, chi_u);
+    else e_interior_body<T, V, LX, NS, false>(p, g, i0, j, lx, it.set, kb, ke, chi_u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -335,21 +353,17 @@ struct Stager {
     }
 };
 
-template <typename T, int V, int LX, int NS>
-__global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
-                                                         int k_begin, int k_end) {
+template <typename T, int V, int LX, int NS, bool SRC>
+__device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const IntGeom &g, const WorkItem &it, int kb, int ke,
+                                                    uint4 *smem) {
     constexpr int NSLOT = 8 + 6 * NS;
-    extern __shared__ uint4 sj_smem[];
-    const WorkItem it = items[blockIdx.x];
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane % LX, ly = lane / LX;
     const int i0 = it.i0 + lx * V;
     const int j = it.j0 + warp * RW + ly;
     const int set = it.set;
-    const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
-    if (kb >= ke) return;
-    Stager<T, V, NSLOT> sg; sg.base = sj_smem + threadIdx.x;
+    Stager<T, V, NSLOT> sg; sg.base = smem + threadIdx.x;
     const bool ld = (j < g.j_hi) && (i0 + V <= p.pitch);
     const bool st = (j < g.j_hi) && (i0 < g.i_hi);
     const T C = p.courant;
@@ -427,7 +441,7 @@ __global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
         if (edge) { hz_p = hz_pc; hy_p = hy_pc; }
-        const unsigned smask = src_plane_mask(p, k);
+        const unsigned smask = SRC ? src_plane_mask(p, k) : 0u;
         if (st) {
             sg.get(cur, 5, ex); sg.get(cur, 6, ey); sg.get(cur, 7, ez);
             Vec<T, V> pc[3][NS], pp[3][NS];
@@ -443,7 +457,7 @@ __global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g
                 dD[0] = -(C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]));
                 dD[1] = -(C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi));
                 dD[2] = -(C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]));
-                if (smask) {
+                if (SRC && smask) {
                     T S0, S1, J;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { source_parts(p, smask, c, i0 + v, j, k, set, step, S0, S1, J); dD[c] -= (S1 - S0) + J; }
@@ -478,6 +492,17 @@ __global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g
         for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; nx_[v] = fx[v]; ny_[v] = fy[v]; nz_[v] = fz[v]; }
         pE += plane; pH += plane; pm += plane; xg += plane;
     }
+}
+
+template <typename T, int V, int LX, int NS>
+__global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
+                                                         int k_begin, int k_end) {
+    extern __shared__ uint4 sj_smem[];
+    const WorkItem it = items[blockIdx.x];
+    const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
+    if (kb >= ke) return;
+    if (src_in_chunk(p, kb, ke)) e_interior_stg_body<T, V, LX, NS, true>(p, g, it, kb, ke, sj_smem);
+    else e_interior_stg_body<T, V, LX, NS, false>(p, g, it, kb, ke, sj_smem);
 }
 
 // flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
@@ -524,7 +549,7 @@ __device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu,
 
 // MODE 0: general; 1: tangential component of a face (sigma sf/isf, no D array); 2: normal
 // component of a face (sigma sw on W, D stored, no sigma on D).
-template <typename T, int V, int NS, int MODE>
+template <typename T, int V, int NS, int MODE, bool SRC>
 __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, NS> &pol, int c, int v, T &e, T &d, T curl, T sk,
                                            T ik, T su, T iu, T sw, T &U, int m, T chi_u, T eps_u, T S0, T S1, T J) {
     const T chi = NS > 0 ? p.mt_chi[m] : chi_u;
@@ -532,20 +557,21 @@ __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, N
     T pnew = T(0);
     if (MODE == 1) {
         const T eps = NS > 0 ? p.mt_eps[m] : eps_u;
-        const T dold = (eps * e + pold) + S0;
-        const T dnew = ((T(1) - sk) * dold - curl) * ik - J;
+        const T dold = SRC ? (eps * e + pold) + S0 : (eps * e + pold);
+        T dnew = ((T(1) - sk) * dold - curl) * ik;
+        if (SRC) dnew -= J;
         if (NS > 0) pol.advance(p, c, v, m, e, pnew);          // W == E here
-        e = chi * ((dnew - pnew) - S1);
+        e = SRC ? chi * ((dnew - pnew) - S1) : chi * (dnew - pnew);
         return;
     }
     const T dold = d;
     T dnew = (MODE == 2) ? dold - curl : pml_step_db(dold, curl, sk, ik, su, iu, U);
-    dnew -= J;
+    if (SRC) dnew -= J;
     d = dnew;
     // W^n = chi (D^n - sum P^n - S^n) drives the poles (meep update_pols runs on W)
-    const T wold = chi * ((dold - pold) - S0);
+    const T wold = SRC ? chi * ((dold - pold) - S0) : chi * (dold - pold);
     if (NS > 0) pol.advance(p, c, v, m, wold, pnew);
-    const T wnew = chi * ((dnew - pnew) - S1);
+    const T wnew = SRC ? chi * ((dnew - pnew) - S1) : chi * (dnew - pnew);
     e = (MODE == 2 || sw != T(0)) ? e + (T(1) + sw) * wnew - (T(1) - sw) * wold : wnew;
 }
 
@@ -672,7 +698,7 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
 
 // FACE = false: general tiles (PD 0); FACE = true: face tiles, normal direction taken from the item
 template <typename T, int V, int LX, bool FACE>
-__global__ void __launch_bounds__(256, FACE ? SJ_HFACE_BLOCKS : 2) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+__global__ void __launch_bounds__(256, (V * sizeof(T) == 8) ? (FACE ? 4 : 3) : (FACE ? SJ_HFACE_BLOCKS : 2)) h_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
                                                      int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
     const PmlBox<T> &b = bs.b[it.box];
@@ -682,7 +708,7 @@ __global__ void __launch_bounds__(256, FACE ? SJ_HFACE_BLOCKS : 2) h_pml_tile(KP
     else h_pml_body<T, V, LX, 3>(p, b, it, k_lo, k_hi);
 }
 
-template <typename T, int V, int LX, int NS, int PD>
+template <typename T, int V, int LX, int NS, int PD, bool SRC>
 __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> &b, const WorkItem &it, int k_lo, int k_hi,
                                            T chi_u, T eps_u) {
     constexpr bool GEN = NS > 0;
@@ -756,7 +782,7 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
         if (edge) { hz_p = (pH + fcs2)[-1]; hy_p = (pH + fcs)[-1]; }
         else if (first) { hz_p = T(0); hy_p = T(0); }
-        const unsigned smask = src_plane_mask(p, k);
+        const unsigned smask = SRC ? src_plane_mask(p, k) : 0u;
         if (act) {
             T szi = T(0), izi = T(1), szh = T(0);
             if (PD == 0 || PD == 3) { szi = p.sig[2][2 * k]; izi = p.siginv[2][2 * k]; szh = p.sig[2][2 * k + 1]; }
@@ -772,24 +798,24 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
                 T S0 = T(0), S1 = T(0), J = T(0);
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
-                    if (smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 1) pml_e_elem<T, V, NS, 2>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
+                    if (SRC && smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 1) pml_e_elem<T, V, NS, 2, SRC>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1, SRC>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
-                    if (smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 2) pml_e_elem<T, V, NS, 2>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
+                    if (SRC && smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 2) pml_e_elem<T, V, NS, 2, SRC>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1, SRC>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
-                    if (smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 3) pml_e_elem<T, V, NS, 2>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
+                    if (SRC && smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
+                    else if (PD == 3) pml_e_elem<T, V, NS, 2, SRC>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
+                    else pml_e_elem<T, V, NS, 1, SRC>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
                 }
             }
             ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
@@ -811,15 +837,22 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
 }
 
 template <typename T, int V, int LX, int NS, bool FACE>
-__global__ void __launch_bounds__(256, NS == 0 ? (FACE ? SJ_EFACE_BLOCKS : 2) : 1) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
+__global__ void __launch_bounds__(256, (V * sizeof(T) == 8) ? (NS == 0 ? (FACE ? 4 : 3) : 2) : (NS == 0 ? (FACE ? SJ_EFACE_BLOCKS : 2) : 1)) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
                                                                    int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
     const PmlBox<T> &b = bs.b[it.box];
     const T chi_u = NS > 0 ? T(0) : p.mt_chi[it.mat], eps_u = NS > 0 ? T(0) : p.mt_eps[it.mat];
-    if (!FACE) e_pml_body<T, V, LX, NS, 0>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-    else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-    else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-    else e_pml_body<T, V, LX, NS, 3>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    if (src_in_chunk(p, max(it.kb, k_lo), min(it.ke, k_hi))) {
+        if (!FACE) e_pml_body<T, V, LX, NS, 0, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        else e_pml_body<T, V, LX, NS, 3, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        return;
+    }
+    if (!FACE) e_pml_body<T, V, LX, NS, 0, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else e_pml_body<T, V, LX, NS, 3, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
 }
 
 // material flags of the PML work items (one block per item)
