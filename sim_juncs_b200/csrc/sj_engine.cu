@@ -140,7 +140,11 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
             if (eff > best + 0.04) { best = eff; s->int_lx = lx; }
         }
         if (getenv("SJ_INT_LX")) s->int_lx = atoi(getenv("SJ_INT_LX"));
-        if (getenv("SJ_ZCHUNK")) s->int_zchunk = atoi(getenv("SJ_ZCHUNK"));
+        // planes per block: about 16, evened out so the last chunk is not a stub (161 planes -> 11 x 15, not 10 x 16 + 1)
+        const int nk = std::max(std::min(s->hi[2], s->kz1) - std::max(s->lo[2], s->kz0), 1);
+        const int target = getenv("SJ_ZCHUNK") ? std::max(atoi(getenv("SJ_ZCHUNK")), 1) : 16;
+        const int nzc = (nk + target - 1) / target;
+        s->int_zchunk = (nk + nzc - 1) / nzc;
     }
     const size_t fbytes = (size_t)s->set_stride * g->n_sets * s->esz;
     {
@@ -762,7 +766,12 @@ template <typename T, int V, int LX>
 static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_begin, int k_end, cudaStream_t st) {
     IntGeom g; dim3 grd; interior_geom(s, k_begin, k_end, g, grd);
     if (g.nzc <= 0 || !grd.x || !grd.y) return;
-    if (which == 0) { TR(s, "h_interior<LX>", fan_stream(s, 0), h_interior<T, V, LX><<<grd, 256, 0, st__>>>(p, g, k_begin, k_end)); s->launches++; return; }
+    if (which == 0) {
+        static const bool pipe = getenv("SJ_H_PIPE") ? atoi(getenv("SJ_H_PIPE")) != 0 : true;
+        if (pipe) TR(s, "h_interior_pipe<LX>", fan_stream(s, 0), h_interior_pipe<T, V, LX><<<grd, 256, 0, st__>>>(p, g, k_begin, k_end));
+        else TR(s, "h_interior<LX>", fan_stream(s, 0), h_interior<T, V, LX><<<grd, 256, 0, st__>>>(p, g, k_begin, k_end));
+        s->launches++; return;
+    }
     if (s->il_int[0].n) { TR(s, "e_interior<LX, 0>", fan_stream(s, 0), e_interior<T, V, LX, 0><<<s->il_int[0].n, 256, 0, st__>>>(p, g, s->il_int[0].dev, k_begin, k_end)); s->launches++; }
     if (s->il_int[1].n) {
         const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;

@@ -221,6 +221,81 @@ __global__ void __launch_bounds__(256, 4) h_interior(KParams<T> p, IntGeom g, in
     }
 }
 
+// Software-pipelined variant: the loads of planes k+1 and k+2 are in flight while plane k is computed
+// (three register sets, rotated by unrolling the plane loop by three).  Measured on this GPU
+// (scripts/microbench/pipe.cu): one plane in flight per thread tops out near 5.1-6.3 TB/s whatever the
+// occupancy, two or more reach 6.8-6.9 TB/s even at one or two blocks per SM.
+template <typename T, int V>
+struct HPlane { Vec<T, V> ex1, ey1, ez0, ezj, exj, hx, hy, hz; T ez_e, ey_e; };
+
+template <typename T, int V, int LX>
+__global__ void __launch_bounds__(256, 2) h_interior_pipe(KParams<T> p, IntGeom g, int k_begin, int k_end) {
+    constexpr int RW = 32 / LX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane % LX, ly = lane / LX;
+    const int i0 = g.i_lo + (blockIdx.x * LX + lx) * V;
+    const int j = g.j_lo + (blockIdx.y * 8 + warp) * RW + ly;
+    const int set = blockIdx.z / g.nzc;
+    const int kc = g.c0 + blockIdx.z % g.nzc;
+    const int kb = max(g.k_lo + kc * g.zchunk, k_begin);
+    const int ke = min(min(g.k_lo + (kc + 1) * g.zchunk, g.k_hi), k_end);
+    if (kb >= ke) return;
+    const bool ld = (j < g.j_hi) && (i0 + V <= p.pitch);
+    const bool st = (j < g.j_hi) && (i0 < g.i_hi);
+    const T C = p.courant;
+    const long long x0 = (long long)set * p.set_stride + (long long)(kb - p.kz0 + 1) * p.plane + (long long)j * p.pitch + i0;
+    const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
+    const T *__restrict__ pE = p.F + x0;
+    T *pH = p.F + 3 * fcs + x0;
+    const long long plane = p.plane;
+    const int pitch = p.pitch;
+    const bool edge = st && (lx == LX - 1) && (i0 + V < pitch);
+
+    auto load_plane = [&](HPlane<T, V> &q, long long off) {
+        if (ld) {
+            q.ex1.load(pE + off + plane); q.ey1.load(pE + fcs + off + plane);
+            q.ez0.load(pE + fcs2 + off); q.ezj.load(pE + fcs2 + off + pitch); q.exj.load(pE + off + pitch);
+        } else { q.ex1.zero(); q.ey1.zero(); q.ez0.zero(); q.ezj.zero(); q.exj.zero(); }
+        if (st) { q.hx.load(pH + off); q.hy.load(pH + fcs + off); q.hz.load(pH + fcs2 + off); }
+        q.ez_e = T(0); q.ey_e = T(0);
+        if (edge) { q.ez_e = (pE + fcs2 + off)[V]; q.ey_e = (pE + fcs + off)[V]; }
+    };
+    Vec<T, V> ex0, ey0;
+    if (ld) { ex0.load(pE); ey0.load(pE + fcs); } else { ex0.zero(); ey0.zero(); }
+    auto finish_plane = [&](HPlane<T, V> &q, long long off) {
+        T ez_n = __shfl_down_sync(0xffffffffu, q.ez0.v[0], 1, LX);
+        T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
+        if (edge) { ez_n = q.ez_e; ey_n = q.ey_e; }
+        if (st) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T ezi = (v < V - 1) ? q.ez0.v[v + 1 < V ? v + 1 : v] : ez_n;
+                const T eyi = (v < V - 1) ? ey0.v[v + 1 < V ? v + 1 : v] : ey_n;
+                q.hx.v[v] -= C * (((q.ezj.v[v] - q.ez0.v[v]) + ey0.v[v]) - q.ey1.v[v]);
+                q.hy.v[v] -= C * (((q.ex1.v[v] - ex0.v[v]) + q.ez0.v[v]) - ezi);
+                q.hz.v[v] -= C * (((eyi - ey0.v[v]) + ex0.v[v]) - q.exj.v[v]);
+            }
+            q.hx.store(pH + off); q.hy.store(pH + fcs + off); q.hz.store(pH + fcs2 + off);
+        }
+        ex0 = q.ex1; ey0 = q.ey1;
+    };
+    HPlane<T, V> q0, q1, q2;
+    load_plane(q0, 0);
+    if (kb + 1 < ke) load_plane(q1, plane);
+    long long off = 0;
+    for (int k = kb; k < ke; k += 3) {
+        if (k + 2 < ke) load_plane(q2, off + 2 * plane);
+        finish_plane(q0, off);
+        if (k + 1 >= ke) break;
+        if (k + 3 < ke) load_plane(q0, off + 3 * plane);
+        finish_plane(q1, off + plane);
+        if (k + 2 >= ke) break;
+        if (k + 4 < ke) load_plane(q1, off + 4 * plane);
+        finish_plane(q2, off + 2 * plane);
+        off += 3 * plane;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Interior E-pass
 // ------------------------------------------------------------------------------------------
