@@ -115,7 +115,15 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     CK(cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-    for (int a = 0; a < SJ_N_AUX; ++a) { CK(cudaStreamCreateWithFlags(&s->aux[a], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&s->ev_join[a], cudaEventDisableTiming)); }
+    {   // side streams; the ones that carry the PML lists (aux[1..]) can be given scheduling priority over the interior kernels
+        int pr_lo = 0, pr_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+        const bool prio = getenv("SJ_PML_PRIO") ? atoi(getenv("SJ_PML_PRIO")) != 0 : false;
+        for (int a = 0; a < SJ_N_AUX; ++a) {
+            CK(cudaStreamCreateWithPriority(&s->aux[a], cudaStreamNonBlocking, (prio && a >= 1) ? pr_hi : pr_lo));
+            CK(cudaEventCreateWithFlags(&s->ev_join[a], cudaEventDisableTiming));
+        }
+    }
     s->fan_on = getenv("SJ_NO_FAN") == NULL; s->fan_next = 0; s->fan_main = s->stream;
     s->trace_on = false;
     s->n_aux = getenv("SJ_N_AUX") ? std::min(std::max(atoi(getenv("SJ_N_AUX")), 1), SJ_N_AUX) : 5;

@@ -10,7 +10,7 @@
 #define SJ_MAX_SRC 4
 #define SJ_MAX_MAT 256
 #define SJ_N_PML_BOX 6
-#define SJ_N_AUX 7
+#define SJ_N_AUX 10
 
 // ---- kernel parameter blocks (passed by value) ---------------------------------------------
 template <typename T>
