@@ -173,8 +173,12 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
                     printf("Adding Gaussian envelope: f=%f, w=%f, t_0=%f, t_f=%f (meep units)\n", frequency, width, t_start, t_end);
                     if (sj_add_gaussian_source(sim, info.component, lo, hi, info.amplitude, 0.0, frequency, width, info.phase, t_start,
                                                t_end, integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(sim)); exit(1); }
+                } else if (info.component <= 2) {
+                    printf("Adding continuous wave: f=%f, w=%f, t_0=%f, t_f=%f (meep units)\n", frequency, width, t_start, t_end);
+                    if (sj_add_cw_source(sim, info.component, lo, hi, info.amplitude, 0.0, frequency, width, t_start, t_end, 3.0,
+                                         integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(sim)); exit(1); }
                 } else {
-                    fprintf(stderr, "warning: CW / magnetic-current sources are not implemented in the CUDA engine; source skipped\n");
+                    fprintf(stderr, "warning: magnetic-current sources are not implemented in the CUDA engine; source skipped\n");
                 }
                 sources.push_back(info);
                 ttot = sj_last_source_time(sim) + post_source_t * SJ_LIGHT_SPEED * s.um_scale;

@@ -119,6 +119,12 @@ int sj_get_material_table(sj_sim *sim, int32_t *n_mat, sj_material *out, int32_t
 int sj_add_gaussian_source(sj_sim *sim, int comp, const double lo[3], const double hi[3],
                            double amp_re, double amp_im, double freq, double width, double phase,
                            double t_start, double t_end, int integrated, const double *set_phase);
+/* CW_source -> meep::continuous_src_time(freq, width, t_start, t_end) (src/disp.cpp:615-619; meep's default
+ * slowness 3.0): exp(-i w t)/(-i w) between t_start and t_end with tanh turn-on / turn-off of time
+ * constant `width` (0 = abrupt).  t_end must be finite.                                                  */
+int sj_add_cw_source(sj_sim *sim, int comp, const double lo[3], const double hi[3],
+                     double amp_re, double amp_im, double freq, double width,
+                     double t_start, double t_end, double slowness, int integrated, const double *set_phase);
 double sj_last_source_time(const sj_sim *sim);     /* fields.last_source_time(), disp.cpp:625 */
 
 /* ---- monitors: fields.get_field(component, loc) at fixed points (src/disp.cpp:724) ------- */

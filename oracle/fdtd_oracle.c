@@ -63,6 +63,8 @@ typedef struct {
 typedef struct {
     int comp;              /* 0..2 = Ex,Ey,Ez */
     int integrated;        /* meep src_time::is_integrated */
+    int kind;              /* 0: gaussian_src_time_phase (disp.hpp:112); 1: meep::continuous_src_time (disp.cpp:618) */
+    double t_start, t_end, slowness;   /* kind 1 */
     double omega, width, phi, peak, cutoff;
     double _Complex amp_t; /* 1/(-i omega), disp.cpp:387 */
     double _Complex amp;   /* user amplitude times a^(zero-size dims) */
@@ -214,6 +216,17 @@ int orc_set_regions(orc_sim *s, double ambient_eps, int n_regions, const double 
 
 /* ---- source waveform: gaussian_src_time_phase (src/disp.cpp:378-400) ---- */
 static double _Complex src_dipole(const orc_src *g, double time) {
+    if (g->kind == 1) {
+        /* meep continuous_src_time::dipole [meep-recall, v1.2x sources.cpp]: zero outside [start, end] (float
+         * compare), exp(-i w t) / (-i w), times tanh ramps (1+tanh(ts))(1+tanh(te))/4 when width != 0 */
+        float rtime = (float)time;
+        if (rtime < g->t_start || rtime > g->t_end) return 0.0;
+        double _Complex osc = (cos(-g->omega * time) + I * sin(-g->omega * time)) * g->amp_t;
+        if (g->width == 0.0) return osc;
+        double ts = (time - g->t_start) / g->width - g->slowness;
+        double te = (g->t_end - time) / g->width - g->slowness;
+        return osc * (1.0 + tanh(ts)) * (1.0 + tanh(te)) * 0.25;
+    }
     double tt = time - g->peak;
     if ((float)fabs(tt) > g->cutoff) return 0.0;
     double _Complex pol = cos(-g->omega * tt - g->phi) + I * sin(-g->omega * tt - g->phi);
@@ -230,7 +243,8 @@ static void calc_sources(orc_sim *s, double tim) {
 double orc_src_last_time(const orc_sim *s) {
     double t = 0;
     for (int i = 0; i < s->n_src; ++i) {
-        double lt = (float)(s->src[i].peak + s->src[i].cutoff); /* disp.hpp:119 */
+        double lt = s->src[i].kind == 1 ? s->src[i].t_end               /* continuous_src_time::last_time */
+                                        : (float)(s->src[i].peak + s->src[i].cutoff); /* disp.hpp:119 */
         if (lt > t) t = lt;
     }
     return t;
@@ -245,19 +259,7 @@ void orc_src_dipole(const orc_sim *s, int isrc, double time, double *out2) {
  * is..ie (half-pixel indices, step 2) with linear-interpolation end weights
  * s0,s1,(1...),e1,e0; a zero-thickness direction degenerates to the two bracketing
  * planes with weights (1-f, f) and multiplies the amplitude by a (delta function). */
-int orc_add_gaussian_source(orc_sim *s, int comp, const double *lo, const double *hi,
-                            double amp_re, double amp_im, double freq, double width, double phase,
-                            double t_start, double t_end, int integrated) {
-    if (s->n_src >= ORC_MAX_SRC || comp < 0 || comp > 2) return -1;
-    orc_src *g = &s->src[s->n_src];
-    memset(g, 0, sizeof(*g));
-    g->comp = comp; g->integrated = integrated;
-    g->omega = 2 * M_PI * freq; g->width = width; g->phi = phase + M_PI;
-    g->peak = 0.5 * (t_start + t_end); g->cutoff = (t_end - t_start) * 0.5;
-    g->amp_t = 1.0 / (0.0 - I * g->omega);
-    while (exp(-g->cutoff * g->cutoff / (2 * g->width * g->width)) < 1e-100) g->cutoff *= 0.9;
-    g->cutoff = (float)g->cutoff;
-    double _Complex amp = amp_re + I * amp_im;
+static int place_source(orc_sim *s, orc_src *g, int comp, const double *lo, const double *hi, double _Complex amp) {
     for (int d = 0; d < 3; ++d) {
         const int sh = (d == comp) ? 1 : 0;     /* iyee_shift of an E component */
         const int iyc = 1 - sh;                 /* iyee_shift(Centered) - iyee_shift(c) */
@@ -300,6 +302,34 @@ int orc_add_gaussian_source(orc_sim *s, int comp, const double *lo, const double
     g->amp = amp;
     s->n_src++;
     return 0;
+}
+
+int orc_add_gaussian_source(orc_sim *s, int comp, const double *lo, const double *hi,
+                            double amp_re, double amp_im, double freq, double width, double phase,
+                            double t_start, double t_end, int integrated) {
+    if (s->n_src >= ORC_MAX_SRC || comp < 0 || comp > 2) return -1;
+    orc_src *g = &s->src[s->n_src];
+    memset(g, 0, sizeof(*g));
+    g->comp = comp; g->integrated = integrated; g->kind = 0;
+    g->omega = 2 * M_PI * freq; g->width = width; g->phi = phase + M_PI;
+    g->peak = 0.5 * (t_start + t_end); g->cutoff = (t_end - t_start) * 0.5;
+    g->amp_t = 1.0 / (0.0 - I * g->omega);
+    while (exp(-g->cutoff * g->cutoff / (2 * g->width * g->width)) < 1e-100) g->cutoff *= 0.9;
+    g->cutoff = (float)g->cutoff;
+    return place_source(s, g, comp, lo, hi, amp_re + I * amp_im);
+}
+
+/* meep::continuous_src_time(freq, width, start, end, slowness) as the reference builds it (disp.cpp:618; the
+ * reference leaves slowness at meep's default 3.0 and feeds the scene's `slowness` argument in as the width) */
+int orc_add_cw_source(orc_sim *s, int comp, const double *lo, const double *hi, double amp_re, double amp_im,
+                      double freq, double width, double t_start, double t_end, double slowness, int integrated) {
+    if (s->n_src >= ORC_MAX_SRC || comp < 0 || comp > 2) return -1;
+    orc_src *g = &s->src[s->n_src];
+    memset(g, 0, sizeof(*g));
+    g->comp = comp; g->integrated = integrated; g->kind = 1;
+    g->omega = 2 * M_PI * freq; g->width = width; g->t_start = t_start; g->t_end = t_end; g->slowness = slowness;
+    g->amp_t = 1.0 / (0.0 - I * g->omega);
+    return place_source(s, g, comp, lo, hi, amp_re + I * amp_im);
 }
 
 /* Monitors: meep fields::get_field -> grid_volume::interpolate (linear in each direction

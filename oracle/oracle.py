@@ -37,6 +37,7 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_regions.argtypes = [C.c_void_p, C.c_double, C.c_int, dp, ip, dp, u8p, u8p, u8p]
         L.orc_add_gaussian_source.argtypes = [C.c_void_p, C.c_int, dp, dp] + [C.c_double] * 7 + [C.c_int]
+        L.orc_add_cw_source.argtypes = [C.c_void_p, C.c_int, dp, dp] + [C.c_double] * 7 + [C.c_int]
         L.orc_add_monitors.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
         L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_step.argtypes = [C.c_void_p]
@@ -114,6 +115,16 @@ class OracleSim:
                                             phase, t_start, t_end, int(integrated))
         if rc:
             raise RuntimeError("orc_add_gaussian_source failed: %d" % rc)
+        self.n_src += 1
+
+    def add_cw_source(self, comp, lo, hi, amp, freq, width, t_start, t_end, slowness=3.0, integrated=True):
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        amp = complex(amp)
+        rc = self.L.orc_add_cw_source(self.h, comp, _dp(lo), _dp(hi), amp.real, amp.imag, freq, width,
+                                      t_start, t_end, slowness, int(integrated))
+        if rc:
+            raise RuntimeError("orc_add_cw_source failed: %d" % rc)
         self.n_src += 1
 
     def add_monitors(self, xyz, comp=0):

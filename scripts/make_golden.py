@@ -39,6 +39,7 @@ CONFIGS = {
                        ["--grid-res", "12.0", "--opts", RUN_SH_OPTS], {}),
     "Au_graphene_box": (ROOT + "/scenes/Au_graphene_box/junc.geom", ROOT + "/scenes/Au_graphene_box/params.conf", [], {}),
     "quartz_box": (ROOT + "/scenes/quartz_box/junc.geom", ROOT + "/scenes/quartz_box/params.conf", [], {}),
+    "tests_cw_slab": (ROOT + "/scenes/tests/cw_slab.geom", ROOT + "/scenes/tests/cw_slab.conf", [], {}),
     # scene-language feature sweep for the own parser (tests/test_cgs_parser.py)
     "parser_features": (ROOT + "/scenes/tests/parser_features.geom", REF + "/tests/run.conf", [],
                         dict(pml_thickness=1.0, len=4.0, um_scale=2.0, resolution=4.0)),

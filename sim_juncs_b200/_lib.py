@@ -52,6 +52,7 @@ SYMBOLS = {
     "sj_get_region_masks": (C.c_int, [_vp, C.c_int, _u8p]),
     "sj_get_material_table": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(SjMaterial), C.c_int32]),
     "sj_add_gaussian_source": (C.c_int, [_vp, C.c_int, _dp, _dp] + [C.c_double] * 7 + [C.c_int, _dp]),
+    "sj_add_cw_source": (C.c_int, [_vp, C.c_int, _dp, _dp] + [C.c_double] * 7 + [C.c_int, _dp]),
     "sj_last_source_time": (C.c_double, [_vp]),
     "sj_add_monitors": (C.c_int, [_vp, C.c_int, C.c_int32, _dp]),
     "sj_run": (C.c_int, [_vp, C.c_int64, C.c_int32]),

@@ -80,14 +80,22 @@ class BoundGeom:
             width = info.width * c_by_a
             start_time = info.start_time * c_by_a
             end_time = info.end_time * c_by_a
-            if info.type != "gaussian":
-                raise NotImplementedError("CW_source is not implemented in the CUDA engine yet")
             if info.component > 2:
                 raise NotImplementedError("magnetic-current sources (%s) are not implemented" % COMPONENTS[info.component])
-            if verbose:
-                print("Adding Gaussian envelope: f=%f, w=%f, t_0=%f, t_f=%f (meep units)" % (frequency, width, start_time, end_time))
-            self.sim.add_gaussian_source(info.component, lo, hi, info.amplitude, frequency, width, info.phase,
-                                         start_time, end_time, integrated, set_phase=self.phases)
+            if info.type == "gaussian":
+                if verbose:
+                    print("Adding Gaussian envelope: f=%f, w=%f, t_0=%f, t_f=%f (meep units)" % (frequency, width, start_time, end_time))
+                self.sim.add_gaussian_source(info.component, lo, hi, info.amplitude, frequency, width, info.phase,
+                                             start_time, end_time, integrated, set_phase=self.phases)
+            else:
+                # meep::continuous_src_time(frequency, width, start_time, end_time), disp.cpp:615-619 (slowness stays at
+                # meep's default 3; the scene's `slowness` argument arrives here as the width, disp.cpp:343-347)
+                if verbose:
+                    print("Adding continuous wave: f=%f, w=%f, t_0=%f, t_f=%f (meep units)" % (frequency, width, start_time, end_time))
+                if not math.isfinite(end_time) or end_time > 1e300:
+                    raise ValueError("CW_source without end_time never ends: the reference's run() would not terminate either")
+                self.sim.add_cw_source(info.component, lo, hi, info.amplitude, frequency, width, start_time, end_time,
+                                       3.0, integrated, set_phase=self.phases)
             self.sources.append(info)
             self.ttot = self.sim.last_source_time() + self.post_source_t * LIGHT_SPEED * settings.um_scale
         self.monitor_locs = [tuple(p) for p in scene.monitor_locs]

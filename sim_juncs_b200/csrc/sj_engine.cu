@@ -519,6 +519,16 @@ extern "C" int sj_get_region_masks(sj_sim *s, int comp, uint8_t *out) {
 // ---- sources -------------------------------------------------------------------------------
 // gaussian_src_time_phase (reference src/disp.cpp:378-400) evaluated on the host in fp64
 static std::complex<double> src_dipole(const HostSource &g, double time) {
+    if (g.kind == 1) {
+        // meep::continuous_src_time::dipole (what the reference instantiates for CW_source, src/disp.cpp:618):
+        // zero outside [start, end] (float compare), exp(-i w t)/(-i w), tanh turn-on/off when width != 0
+        const float rtime = float(time);
+        if (rtime < g.t_start || rtime > g.t_end) return 0.0;
+        const std::complex<double> osc = std::polar(1.0, -g.omega * time) * std::complex<double>(g.amp_t_re, g.amp_t_im);
+        if (g.width == 0.0) return osc;
+        const double ts = (time - g.t_start) / g.width - g.slowness, te = (g.t_end - time) / g.width - g.slowness;
+        return osc * (1.0 + tanh(ts)) * (1.0 + tanh(te)) * 0.25;
+    }
     const double tt = time - g.peak;
     if (float(fabs(tt)) > g.cutoff) return 0.0;
     return exp(-tt * tt / (2 * g.width * g.width)) * std::polar(1.0, -g.omega * tt - g.phi) *
@@ -527,7 +537,7 @@ static std::complex<double> src_dipole(const HostSource &g, double time) {
 
 extern "C" double sj_last_source_time(const sj_sim *s) {
     double t = 0;
-    for (const auto &g : s->srcs) t = std::max(t, (double)float(g.peak + g.cutoff));
+    for (const auto &g : s->srcs) t = std::max(t, g.kind == 1 ? g.t_end : (double)float(g.peak + g.cutoff));
     return t;
 }
 
@@ -575,23 +585,13 @@ static int upload_sources(sj_sim *s) {
     return SJ_OK;
 }
 
-extern "C" int sj_add_gaussian_source(sj_sim *s, int comp, const double lo[3], const double hi[3], double amp_re,
-                                      double amp_im, double freq, double width, double phase, double t_start,
-                                      double t_end, int integrated, const double *set_phase) {
-    if (!s || comp < 0 || comp > 2 || !lo || !hi) return fail(s, SJ_ERR_ARG, "bad source arguments (E components only)");
-    if ((int)s->srcs.size() >= SJ_MAX_SRC) return fail(s, SJ_ERR_ARG, "too many sources");
-    HostSource g;
-    g.comp = comp; g.integrated = integrated;
-    g.omega = 2 * M_PI * freq; g.width = width; g.phi = phase + M_PI;
-    g.peak = 0.5 * (t_start + t_end); g.cutoff = (t_end - t_start) * 0.5;
-    std::complex<double> at = 1.0 / std::complex<double>(0, -g.omega);
-    g.amp_t_re = at.real(); g.amp_t_im = at.imag();
-    while (exp(-g.cutoff * g.cutoff / (2 * g.width * g.width)) < 1e-100) g.cutoff *= 0.9;
-    g.cutoff = float(g.cutoff);
+// place a source volume on the grid (meep fields::add_volume_source weights) and register it
+static int place_source(sj_sim *s, HostSource &g, const double lo[3], const double hi[3], double amp_re, double amp_im,
+                        const double *set_phase) {
     std::complex<double> amp(amp_re, amp_im);
     for (int d = 0; d < 3; ++d) {
         bool delta;
-        if (source_axis(s, comp, d, lo[d], hi[d], g.lo[d], g.hi[d], g.w[d], delta)) return fail(s, SJ_ERR_ARG, "bad source volume");
+        if (source_axis(s, g.comp, d, lo[d], hi[d], g.lo[d], g.hi[d], g.w[d], delta)) return fail(s, SJ_ERR_ARG, "bad source volume");
         if (delta) amp *= s->g.a;
     }
     g.amp_re = amp.real(); g.amp_im = amp.imag();
@@ -604,6 +604,37 @@ extern "C" int sj_add_gaussian_source(sj_sim *s, int comp, const double lo[3], c
     s->srcs.push_back(g);
     s->drive_dirty = true;
     return s->prec == SJ_F64 ? upload_sources<double>(s) : upload_sources<float>(s);
+}
+
+extern "C" int sj_add_gaussian_source(sj_sim *s, int comp, const double lo[3], const double hi[3], double amp_re,
+                                      double amp_im, double freq, double width, double phase, double t_start,
+                                      double t_end, int integrated, const double *set_phase) {
+    if (!s || comp < 0 || comp > 2 || !lo || !hi) return fail(s, SJ_ERR_ARG, "bad source arguments (E components only)");
+    if ((int)s->srcs.size() >= SJ_MAX_SRC) return fail(s, SJ_ERR_ARG, "too many sources");
+    HostSource g;
+    g.comp = comp; g.integrated = integrated; g.kind = 0; g.t_start = g.t_end = g.slowness = 0;
+    g.omega = 2 * M_PI * freq; g.width = width; g.phi = phase + M_PI;
+    g.peak = 0.5 * (t_start + t_end); g.cutoff = (t_end - t_start) * 0.5;
+    std::complex<double> at = 1.0 / std::complex<double>(0, -g.omega);
+    g.amp_t_re = at.real(); g.amp_t_im = at.imag();
+    while (exp(-g.cutoff * g.cutoff / (2 * g.width * g.width)) < 1e-100) g.cutoff *= 0.9;
+    g.cutoff = float(g.cutoff);
+    return place_source(s, g, lo, hi, amp_re, amp_im, set_phase);
+}
+
+extern "C" int sj_add_cw_source(sj_sim *s, int comp, const double lo[3], const double hi[3], double amp_re, double amp_im,
+                                double freq, double width, double t_start, double t_end, double slowness, int integrated,
+                                const double *set_phase) {
+    if (!s || comp < 0 || comp > 2 || !lo || !hi) return fail(s, SJ_ERR_ARG, "bad source arguments (E components only)");
+    if ((int)s->srcs.size() >= SJ_MAX_SRC) return fail(s, SJ_ERR_ARG, "too many sources");
+    if (!(t_end >= t_start) || !(t_end < 1e300)) return fail(s, SJ_ERR_ARG, "a CW source needs a finite end time");
+    HostSource g;
+    g.comp = comp; g.integrated = integrated; g.kind = 1;
+    g.omega = 2 * M_PI * freq; g.width = width; g.phi = 0; g.peak = 0; g.cutoff = 0;
+    g.t_start = t_start; g.t_end = t_end; g.slowness = slowness;
+    std::complex<double> at = 1.0 / std::complex<double>(0, -g.omega);
+    g.amp_t_re = at.real(); g.amp_t_im = at.imag();
+    return place_source(s, g, lo, hi, amp_re, amp_im, set_phase);
 }
 
 // drive table [step][src][set][2]: {S_n, dt*J_n}; S_n = Re/Im(amp * dipole(n dt)) for integrated

@@ -94,6 +94,8 @@ struct MonDev {
 // ---- host-side state -------------------------------------------------------------------
 struct HostSource {
     int comp, integrated;
+    int kind;                     // 0: gaussian_src_time_phase, 1: meep::continuous_src_time
+    double t_start, t_end, slowness;   // kind 1
     double omega, width, phi, peak, cutoff;
     double amp_t_re, amp_t_im;    // 1/(-i omega)
     double amp_re, amp_im;

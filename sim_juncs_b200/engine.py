@@ -117,6 +117,19 @@ class Sim:
         self._ck(self.L.sj_add_gaussian_source(self.h, comp, _dp(lo), _dp(hi), amp.real, amp.imag, freq, width, phase,
                                                t_start, t_end, int(integrated), sp))
 
+    def add_cw_source(self, comp, lo, hi, amp, freq, width, t_start, t_end, slowness=3.0, integrated=True, set_phase=None):
+        """meep::continuous_src_time over a volume (reference CW_source, src/disp.cpp:615-619)."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        amp = complex(amp)
+        sp = None
+        if set_phase is not None:
+            spa = np.ascontiguousarray(set_phase, dtype=np.float64)
+            assert spa.size == self.n_sets
+            sp = _dp(spa)
+        self._ck(self.L.sj_add_cw_source(self.h, comp, _dp(lo), _dp(hi), amp.real, amp.imag, freq, width, t_start, t_end,
+                                         float(slowness), int(integrated), sp))
+
     def last_source_time(self):
         return self.L.sj_last_source_time(self.h)
 

@@ -85,8 +85,12 @@ def oracle_bound_geom(scene, settings, masks, nsets=2, integrated=True, mon_comp
     for info, (p1, p2) in zip(scene.sources, scene.source_boxes):
         lo = [min(p1[d], p2[d]) for d in range(3)]
         hi = [max(p1[d], p2[d]) for d in range(3)]
-        o.add_gaussian_source(info.component, lo, hi, info.amplitude, 1 / (info.wavelen * settings.um_scale),
-                              info.width * c_by_a, info.phase, info.start_time * c_by_a, info.end_time * c_by_a, integrated)
+        if info.type == "gaussian":
+            o.add_gaussian_source(info.component, lo, hi, info.amplitude, 1 / (info.wavelen * settings.um_scale),
+                                  info.width * c_by_a, info.phase, info.start_time * c_by_a, info.end_time * c_by_a, integrated)
+        else:       # disp.cpp:615-619
+            o.add_cw_source(info.component, lo, hi, info.amplitude, 1 / (info.wavelen * settings.um_scale),
+                            info.width * c_by_a, info.start_time * c_by_a, info.end_time * c_by_a, 3.0, integrated)
         ttot = o.last_source_time() + settings.post_source_t * LIGHT_SPEED * settings.um_scale
     if scene.monitor_locs:
         o.add_monitors(np.array(scene.monitor_locs), mon_comp)

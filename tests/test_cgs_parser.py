@@ -253,7 +253,8 @@ def _unsigned_zero(v):
 
 
 IN_REPO = {"tests_run_slabs": "scenes/tests/run_slabs.geom", "Au_graphene_box": "scenes/Au_graphene_box/junc.geom",
-           "quartz_box": "scenes/quartz_box/junc.geom", "parser_features": "scenes/tests/parser_features.geom"}
+           "quartz_box": "scenes/quartz_box/junc.geom", "parser_features": "scenes/tests/parser_features.geom",
+           "tests_cw_slab": "scenes/tests/cw_slab.geom"}
 IN_REF = {"tests_run": "tests/run.geom", "tests_span": "tests/span.geom", "tests_test": "tests/test.geom",
           "Au_SiO2_box": "junctions/Au_SiO2_box/junc.geom", "Au_SiO2_bowtie": "junctions/Au_SiO2_bowtie/junc.geom"}
 

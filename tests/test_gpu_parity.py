@@ -54,16 +54,21 @@ def _masks(n, a):
     return ms
 
 
-def _run_pair(n, a, pml, nsets, comp, lo, hi, mats, steps, prec, integrated=True, span=1, probe_step=None):
+def _run_pair(n, a, pml, nsets, comp, lo, hi, mats, steps, prec, integrated=True, span=1, probe_step=None, cw=False):
     o = OracleSim(n, a, pml=pml, nsets=nsets)
     g = Sim(n, a, pml=pml, n_sets=nsets, precision=prec)
     if mats is not None:
         amb, reps, rpoles, masks = mats
         o.set_regions(amb, reps, rpoles, masks)
         g.set_materials(materials_from_regions(amb, reps, rpoles), masks)
-    src = (1.0, 0.4, 1.5, 0.3, 1.0, 1.0 + 12 * 1.5, integrated)
-    o.add_gaussian_source(comp, lo, hi, *src)
-    g.add_gaussian_source(comp, lo, hi, *src)
+    if cw:      # CW_source -> meep::continuous_src_time(f, width, start, end), slowness 3 (disp.cpp:615-619)
+        src = (1.0, 0.4, 1.2, 0.5, 0.75 * steps * 0.5 / a, 3.0, integrated)
+        o.add_cw_source(comp, lo, hi, *src)
+        g.add_cw_source(comp, lo, hi, *src)
+    else:
+        src = (1.0, 0.4, 1.5, 0.3, 1.0, 1.0 + 12 * 1.5, integrated)
+        o.add_gaussian_source(comp, lo, hi, *src)
+        g.add_gaussian_source(comp, lo, hi, *src)
     L = [x / a for x in n]
     mon = [[L[0] / 2, L[1] / 2, L[2] / 2], [L[0] * 0.31, L[1] * 0.77, L[2] * 0.6], [L[0] / 3, L[1], L[2] / 3],
            [0.01, 0.02, 0.03], [L[0] * 0.5, L[1] * 0.5, 1.0]]
@@ -113,6 +118,16 @@ def test_dispersive_no_pml_volume_source(prec):
     assert merr < TOL[prec] and ferr < TOL[prec]
 
 
+@pytest.mark.parametrize("integrated", [True, False])
+def test_cw_source(integrated):
+    """CW_source: tanh turn-on, steady oscillation, turn-off at 3/4 of the run, then ring-down into the PML."""
+    n, a = (28, 24, 32), 6.0
+    mats = (1.0, [2.25, 1.0], [[(1.1, 0.05, 1.3, 0)], []], _masks(n, a))
+    merr, ferr = _run_pair(n, a, 1.0, 2, 0, [0, 0, 1.2], [n[0] / a, n[1] / a, 1.2], mats, 360, "f64", integrated,
+                           probe_step=200, cw=True)
+    assert merr < 1e-11 and ferr < 1e-11
+
+
 def test_ragged_grid_sizes():
     # odd / non-multiple-of-anything extents exercise every tile edge
     for n in [(21, 23, 25), (33, 20, 47), (70, 21, 22)]:
@@ -151,6 +166,30 @@ def test_tests_run_config(scene_json):
     # Ex is symmetry-suppressed (only edge/PML effects of the finite plane source feed it): tiny but not 0
     assert np.abs(ref).max() < 1e-4
     assert rel_l2(series, ref) < 1e-9
+
+
+def test_cw_scene_through_bound_geom(scene_json):
+    """CW_source end to end: own .geom reader -> bound_geom -> engine, against the oracle driven the same way.
+    (scene: scenes/tests/cw_slab.geom; run length = CW end time + post_source_t, disp.cpp:625)"""
+    import os
+    from sim_juncs_b200.settings import ParseSettings
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    series, ref, bg = _bound_geom_pair("tests_cw_slab", scene_json, "f64")
+    assert bg.get_sources()[0].type == "continuous" and series.shape[1] == 3
+    assert np.abs(ref).max() > 1e-2 and rel_l2(series, ref) < 1e-11
+    st = ParseSettings()
+    conf = os.path.join(root, "scenes", "tests", "cw_slab.conf")
+    st.parse_args(["--conf-file", conf])
+    cwd = os.getcwd()
+    os.chdir(root)                      # geom_fname in the conf is relative to the repo root
+    try:
+        st.parse_conf_file(conf)
+        st.correct_defaults()
+        bg2 = BoundGeom(st)             # scene read from st.geom_fname by sim_juncs_b200/cgs.py
+        bg2.run()
+    finally:
+        os.chdir(cwd)
+    assert np.array_equal(np.array(bg2.get_field_times()), np.array(bg.get_field_times()))
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])

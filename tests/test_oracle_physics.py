@@ -100,3 +100,28 @@ def test_pml_absorbs_and_lossy_medium_is_passive():
     tail = energy[7:]                      # the source is off after step ~102
     assert all(b <= a_ * 1.0000001 for a_, b in zip(tail, tail[1:])), energy
     assert energy[-1] < 1e-4 * max(energy)
+
+
+def test_cw_waveform_and_steady_state():
+    """meep::continuous_src_time as the reference uses it for CW_source (disp.cpp:615-619): exp(-i w t)/(-i w) with
+    tanh turn-on/off; zero outside [start, end]; a vacuum run settles into a sinusoid at the drive frequency."""
+    n, a = (10, 10, 40), 8.0
+    f, width, t0, t1 = 0.45, 1.0, 0.5, 30.0
+    o = OracleSim(n, a, pml=1.0, nsets=2)
+    o.add_cw_source(0, [0, 0, 1.5], [n[0] / a, n[1] / a, 1.5], 1.0, f, width, t0, t1, 3.0)
+    assert o.last_source_time() == t1
+    w = 2 * np.pi * f
+    for t in (0.0, 0.49, 0.5, 3.0, 15.0, 29.0, 30.01, 40.0):
+        ts, te = (t - t0) / width - 3.0, (t1 - t) / width - 3.0
+        want = 0.0 if (t < t0 or t > t1) else np.exp(-1j * w * t) / (-1j * w) * (1 + np.tanh(ts)) * (1 + np.tanh(te)) / 4
+        got = o.dipole(0, t)
+        assert abs(got - want) <= 1e-15 * max(1.0, abs(want)), t
+    o.add_monitors([[n[0] / a / 2, n[1] / a / 2, 3.0]], 0)
+    steps = int(25.0 / o.dt)
+    o.run(steps, 1)
+    m = o.monitors()[:, 0, 0] + 1j * o.monitors()[:, 0, 1]
+    tail = m[int(12.0 / o.dt):]                     # ramp finished (t0 + ~6 widths), well before turn-off
+    assert np.abs(tail).min() > 0.9 * np.abs(tail).max() > 0.0            # complex envelope is flat: a pure tone
+    phase = np.unwrap(np.angle(tail))
+    slope = np.polyfit(np.arange(len(tail)) * o.dt, phase, 1)[0]
+    assert abs(-slope / (2 * np.pi) - f) < 2e-3
