@@ -156,7 +156,7 @@ class BoundGeom:
         return [0.0, ttot_fs, ttot_fs * self.save_span / self.n_t_pts if self.n_t_pts else 0.0]
 
     def save_field_times(self, fname_prefix):
-        """disp.cpp:758-923.  HDF5 is not available in this image yet: the same datasets
-        are written to <prefix>/field_samples.npz with '/'-separated HDF5 paths as keys."""
+        """disp.cpp:758-923: <prefix>/field_samples.h5 through the package's own HDF5 encoder (no libhdf5 here),
+        plus <prefix>/field_samples.npz with the HDF5 paths as keys.  Returns the .h5 path."""
         from .output import save_field_samples
         return save_field_samples(self, fname_prefix)

@@ -1,8 +1,9 @@
 """save_field_times (reference src/disp.cpp:758-923) without libhdf5.
 
-HDF5 is not available in this image, so the same datasets are written to
-`<out_dir>/field_samples.npz` with the HDF5 paths as keys; compound types become 2-column arrays
-({Re,Im}, {x,y,z}) and a 6-column array for /info/sources.  `frequency` reproduces the reference's
+`<out_dir>/field_samples.h5` is written by the package's own HDF5 encoder (hdf5.py): the same groups,
+dataset names, shapes and compound types ({Re,Im}, {x,y,z}, source_info at its C++ struct offsets) as the
+reference.  The same datasets also go to `<out_dir>/field_samples.npz` with the HDF5 paths as keys (compound
+types as 2-, 3- and 6-column arrays) for environments without any HDF5 reader.  `frequency` reproduces the reference's
 transform (src/data_utils.cpp:370-427): only the first 2^floor(log2 N) samples are used while the
 phase step stays 2 pi / N of the FULL length, output in FFT order.
 """
@@ -70,8 +71,44 @@ def field_samples_dict(bg, with_frequency=True):
     return d
 
 
-def save_field_samples(bg, out_dir, with_frequency=True):
-    os.makedirs(out_dir, exist_ok=True)
-    path = os.path.join(out_dir, "field_samples.npz")
-    np.savez(path, **field_samples_dict(bg, with_frequency))
+FIELD_TYPE = np.dtype([("Re", "<f8"), ("Im", "<f8")])                       # disp.cpp:763-769, struct complex
+LOC_TYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8")])             # disp.cpp:777-780, struct sto_vec
+# disp.cpp:788-794: HOFFSET into class source_info (disp.hpp:96-109): two 4-byte enums, then six doubles
+SRC_TYPE = np.dtype({"names": ["wavelen", "width", "phase", "start_time", "end_time", "amplitude"],
+                     "formats": ["<f8"] * 6, "offsets": [8, 16, 24, 32, 40, 48], "itemsize": 56})
+
+
+def _compound(a, dt):
+    a = np.asarray(a, dtype=np.float64).reshape(-1, len(dt.names))
+    out = np.zeros(len(a), dtype=dt)
+    for c, name in enumerate(dt.names):
+        out[name] = a[:, c]
+    return out
+
+
+def write_field_samples_h5(d, path):
+    """The dict of field_samples_dict() as an HDF5 file with the reference's types."""
+    from .hdf5 import H5Writer
+    w = H5Writer(path)
+    w.create_group("info/cgs_params")
+    for key, val in d.items():
+        leaf = key.rsplit("/", 1)[-1]
+        if not key.startswith(("cluster", "info/sources")):
+            pass
+        elif leaf in ("time", "frequency"):
+            val = _compound(val, FIELD_TYPE)
+        elif leaf == "locations":
+            val = _compound(val, LOC_TYPE)
+        elif key == "info/sources":
+            val = _compound(val, SRC_TYPE)
+        w.create_dataset(key, val)
+    w.close()
     return path
+
+
+def save_field_samples(bg, out_dir, with_frequency=True):
+    """-> path of field_samples.h5 (field_samples.npz is written beside it)."""
+    os.makedirs(out_dir, exist_ok=True)
+    d = field_samples_dict(bg, with_frequency)
+    np.savez(os.path.join(out_dir, "field_samples.npz"), **d)
+    return write_field_samples_h5(d, os.path.join(out_dir, "field_samples.h5"))

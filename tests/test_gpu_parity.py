@@ -336,7 +336,20 @@ def test_save_field_samples_npz(tmp_path, scene_json):
     bg = BoundGeom(st, scene_json("tests_run_slabs"), n_sets=2)
     bg.run()
     path = bg.save_field_times(str(tmp_path))
-    z = np.load(path)
+    assert path.endswith("field_samples.h5")
+    from sim_juncs_b200 import hdf5
+    z = np.load(path[:-3] + ".npz")
+    with hdf5.File(path) as f:                                   # the read pattern of scripts/time_space.py:17-49
+        clusters = [k for k in f.keys() if "cluster" in k]
+        points = list(f[clusters[0]].keys())[1:]
+        assert clusters == ["cluster_0", "cluster_1"] and points == ["point_0", "point_1"]
+        assert len(f[clusters[0]][points[0]]["time"]) == 234 and len(f[clusters[0]][points[0]]["frequency"]) == 128
+        assert np.array_equal(np.array(f[clusters[0]][points[1]]["time"]["Re"]), z["cluster_0/point_1/time"][:, 0])
+        assert np.array_equal(np.array(f[clusters[0]][points[1]]["frequency"]["Im"]), z["cluster_0/point_1/frequency"][:, 1])
+        assert f["info"]["time_bounds"][1] == z["info/time_bounds"][1] and f["info"]["n_time_points"][0] == 234
+        assert f["info"]["sources"][0]["wavelen"] == z["info/sources"][0, 0]
+        assert f["info"]["cgs_params"]["l_per_um"][0] == 2
+        assert f[clusters[0]]["locations"][1][2] == z["cluster_0/locations"][1, 2] and len(f["cluster_1"]["locations"]) == 0
     assert z["info/n_clusters"][0] == 1 and z["info/n_time_points"][0] == 234
     assert z["cluster_0/locations"].shape == (2, 3) and z["cluster_1/locations"].shape == (0, 3)
     assert z["cluster_0/point_0/time"].shape == (234, 2) and z["cluster_0/point_0/frequency"].shape == (128, 2)
