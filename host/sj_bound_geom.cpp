@@ -1,6 +1,7 @@
 // sj_bound_geom.cpp -- `bound_geom` on the C ABI.  Construction order, unit conversions and the run
 // loop cadence are those of reference src/disp.cpp:482-749; every meep call is replaced by an sj_* call.
 #include "sj_host.hpp"
+#include "sj_hdf5.hpp"
 
 #include <chrono>
 #include <cstdio>
@@ -285,10 +286,83 @@ struct NpzWriter {
     }
 };
 
+// data_utils.cpp:370-427 as the reference calls it (disp.cpp:806): X[k] = sum_{n < T} x[n] exp(-i (2 pi / N) n k) over
+// the first T = 2^floor(log2 N) samples, phase step of the FULL length N, k in FFT order (0 .. T/2-1, -T/2 .. -1).
+static std::vector<std::complex<double> > reference_fft(const std::vector<std::complex<double> > &x) {
+    const size_t n_full = x.size();
+    if (!n_full) return std::vector<std::complex<double> >();
+    const size_t t = (size_t)1 << (size_t)(log((double)n_full) / log(2.0));
+    const double tau_by_n = 2 * M_PI / (double)n_full;
+    std::vector<std::complex<double> > out(t);
+    const long half = (long)(t / 2);
+    for (size_t q = 0; q < t; ++q) {
+        const long k = t > 1 ? ((long)q < half ? (long)q : (long)q - (long)t) : 0;
+        std::complex<double> acc = 0.0;
+        for (size_t n = 0; n < t; ++n) acc += x[n] * std::polar(1.0, -tau_by_n * (double)n * (double)k);
+        out[q] = acc;
+    }
+    return out;
+}
+
 int sj_bound_geom::save_field_times(const char *fname_prefix) {
     char path[1024];
-    snprintf(path, sizeof path, "%s/field_samples.npz", fname_prefix);
+    snprintf(path, sizeof path, "%s/field_samples.h5", fname_prefix);
     printf("saving field output to %s\n", path);
+    {   // field_samples.h5: the reference's groups, names and compound types (disp.cpp:758-923), own encoder
+        sj_h5::Writer h;
+        typedef std::vector<std::pair<std::string, unsigned> > members;
+        members cplx, loc, src;
+        cplx.push_back(std::make_pair("Re", 0u)); cplx.push_back(std::make_pair("Im", 8u));
+        loc.push_back(std::make_pair("x", 0u)); loc.push_back(std::make_pair("y", 8u)); loc.push_back(std::make_pair("z", 16u));
+        const char *sn[6] = {"wavelen", "width", "phase", "start_time", "end_time", "amplitude"};
+        for (int q = 0; q < 6; ++q) src.push_back(std::make_pair(std::string(sn[q]), 8u + 8u * q));   // HOFFSET in class source_info
+        const sj_h5::bytes t_cplx = sj_h5::compound_type(cplx, 16), t_loc = sj_h5::compound_type(loc, 24), t_src = sj_h5::compound_type(src, 56);
+        const size_t n_locs = monitor_locs.size();
+        const double ttot_fs = meep_time_to_fs(ttot);
+        const double tb[3] = {0.0, ttot_fs, n_t_pts ? ttot_fs * save_span / n_t_pts : 0.0};
+        h.dataset_f64("info/time_bounds", tb, 3);
+        uint64_t u = monitor_clusters.size(); h.dataset_u64("info/n_clusters", &u, 1);
+        u = n_t_pts / save_span; h.dataset_u64("info/n_time_points", &u, 1);
+        std::vector<double> sb(sources.size() * 7, 0.0);
+        for (size_t q = 0; q < sources.size(); ++q) {
+            const sj_source_info &g = sources[q];
+            const double row[6] = {g.wavelen, g.width, g.phase, g.start_time, g.end_time, g.amplitude};
+            memcpy(&sb[7 * q + 1], row, sizeof row);
+        }
+        h.dataset("info/sources", t_src, sb.data(), sources.size(), 56);
+        h.group("info/cgs_params");
+        context &cx = problem.get_context();
+        for (size_t q = cx.size(); q > 0; --q) {
+            name_val_pair nv = cx.peek(q);
+            if (nv.get_val().type == VAL_NUM && nv.get_name() && nv.get_name()[0]) {
+                const double x = nv.get_val().val.x;
+                h.dataset_f64(std::string("info/cgs_params/") + nv.get_name(), &x, 1);
+            }
+        }
+        const size_t ngd = (size_t)(log((double)std::max<size_t>(monitor_clusters.size(), 1)) / log(10.0)) + 1;
+        const size_t npd = (size_t)(log((double)std::max<size_t>(n_locs, 1)) / log(10.0)) + 1;
+        size_t i = 0, off = 0;
+        for (size_t j = 0; j < monitor_clusters.size() + 1; ++j) {      // sic: one empty trailing cluster (disp.cpp:879)
+            const size_t max_i = j >= monitor_clusters.size() ? n_locs : monitor_clusters[j];
+            char cname[64], pname[64];
+            strcpy(cname, "cluster_"); write_number(cname + 8, sizeof cname - 8, (int)j, ngd);
+            std::vector<double> locs((max_i - off) * 3 + 1);
+            for (size_t q = off; q < max_i; ++q) { locs[3 * (q - off)] = monitor_locs[q].x; locs[3 * (q - off) + 1] = monitor_locs[q].y; locs[3 * (q - off) + 2] = monitor_locs[q].z; }
+            h.dataset(std::string(cname) + "/locations", t_loc, locs.data(), max_i - off, 24);
+            off = max_i;
+            for (; i < max_i; ++i) {
+                if (field_times[i].size() < 2) break;
+                strcpy(pname, "point_"); write_number(pname + 6, sizeof pname - 6, (int)i, npd);
+                const std::string base = std::string(cname) + "/" + pname;
+                h.dataset(base + "/time", t_cplx, field_times[i].data(), field_times[i].size(), 16);
+                const std::vector<std::complex<double> > f = reference_fft(field_times[i]);
+                h.dataset(base + "/frequency", t_cplx, f.data(), f.size(), 16);
+            }
+        }
+        if (h.save(path)) { printf("cannot write %s\n", path); return -1; }
+        printf("finished writing hdf5 file!\n");
+    }
+    snprintf(path, sizeof path, "%s/field_samples.npz", fname_prefix);
     NpzWriter w(path);
     if (!w.fp) { printf("cannot open %s\n", path); return -1; }
     const size_t n_locs = monitor_locs.size();

@@ -40,7 +40,7 @@ public:
     std::vector<sj_source_info> get_sources() { return sources; }
     size_t get_n_monitor_clusters() const { return monitor_clusters.size(); }
     int run(const char *fname_prefix);
-    int save_field_times(const char *fname_prefix);       // field_samples.npz (HDF5 paths as keys)
+    int save_field_times(const char *fname_prefix);       // field_samples.h5 (own encoder, sj_hdf5.hpp) + field_samples.npz
     double fs_to_meep_time(double t) const { return t * SJ_LIGHT_SPEED * um_scale; }
     double meep_time_to_fs(double t) const { return t / (SJ_LIGHT_SPEED * um_scale); }
     std::vector<sj_pole_raw> parse_susceptibilities(value val, int *er);

@@ -24,6 +24,10 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
+static void graph_drop(sj_sim *s) {
+    if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = NULL; }
+}
+
 static int fail(sj_sim *s, int code, const char *msg) {
     if (s) s->err = msg; else g_create_err = msg;
     return code;
@@ -97,6 +101,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->nzl = s->kz1 - s->kz0 + 2;
     s->plane = (long long)s->pitch * s->rows;
     s->set_stride = s->plane * s->nzl;
+    s->step_graph = NULL; s->graph_launches = 0;
     s->materials_set = false; s->n_slots = 0; s->drive = NULL; s->drive_steps = 0; s->drive_dirty = true;
     s->n_mon = 0; s->mon_idx = NULL; s->mon_w = NULL; s->series = NULL; s->series_cap = 0; s->n_samples = 0;
     s->steps_done = 0; s->launches = 0; s->pole_points = 0; s->pml_cells = 0;
@@ -264,6 +269,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
 extern "C" void sj_destroy(sj_sim *s) {
     if (!s) return;
     cudaStreamSynchronize(s->stream);
+    graph_drop(s);
     cudaFree(s->F); cudaFree(s->mat[0]);
     for (int c = 0; c < 3; ++c) { cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
     cudaFree(s->flags_int); cudaFree(s->mt_eps);
@@ -382,6 +388,7 @@ static void interior_geom(const sj_sim *s, int k_begin, int k_end, IntGeom &g, d
 }
 
 int sj_finish_materials(sj_sim *s) {
+    graph_drop(s);                      // work lists and material tables are rebuilt below
     // sort the table: non-dispersive materials first, so "has poles" is a compare, not a load
     const int nm = (int)s->mats.size();
     std::vector<int> order;
@@ -664,6 +671,7 @@ static int ensure_drive(sj_sim *s, long long upto) {
             }
         }
     CK(cudaStreamSynchronize(s->stream));
+    graph_drop(s);                      // the captured kernels hold the old table pointer
     cudaFree(s->drive); s->drive = NULL;
     int rc = s->prec == SJ_F64 ? upload_vec<double>(s, tab, &s->drive) : upload_vec<float>(s, tab, &s->drive);
     if (rc) return rc;
@@ -926,6 +934,25 @@ extern "C" int sj_sample(sj_sim *s, void *stream) {
     return 0;
 }
 
+// Capture one full step on the simulation's stream.  Every kernel argument is step-invariant (the drive table is
+// indexed by the device-side step counter), so the same graph serves every step until a setter changes a pointer.
+static int graph_build(sj_sim *s) {
+    const long long l0 = s->launches;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = do_pass(s, 0, s->kz0, s->kz1, s->stream);
+    if (!rc) rc = do_pass(s, 1, s->kz0, s->kz1, s->stream);
+    if (!rc) { tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev); s->launches++; }
+    cudaGraph_t g = NULL;
+    const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+    s->graph_launches = s->launches - l0; s->launches = l0;
+    // a failed capture is not an error of the run: fall back to direct launches (graph_launches < 0 = disabled)
+    if (rc || ce != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); s->graph_launches = -1; return 0; }
+    const cudaError_t ci = cudaGraphInstantiate(&s->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ci != cudaSuccess) { cudaGetLastError(); s->step_graph = NULL; s->graph_launches = -1; }
+    return 0;
+}
+
 // bound_geom::run loop body (reference src/disp.cpp:719-741)
 extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
     if (s) cudaSetDevice(s->g.device);
@@ -935,8 +962,18 @@ extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
     const int n_new = (int)((n_steps + save_span - 1) / save_span);
     rc = ensure_series(s, s->n_samples + n_new); if (rc) return rc;
     const long long base_step = s->steps_done; const int base_cursor = s->n_samples;
+    static const bool graph_env = getenv("SJ_NO_GRAPH") == NULL;
+    const bool use_graph = graph_env && !s->trace_on;
     for (int64_t i = 0; i < n_steps; ++i) {
         if (i % save_span == 0) { rc = do_sample(s, s->stream, base_step, base_cursor, save_span); if (rc) return rc; s->n_samples++; }
+        if (use_graph && s->graph_launches >= 0) {
+            if (!s->step_graph) { rc = graph_build(s); if (rc) return rc; }
+            if (s->step_graph) {
+                CK(cudaGraphLaunch(s->step_graph, s->stream));
+                s->steps_done++; s->launches += s->graph_launches;
+                continue;
+            }
+        }
         rc = do_pass(s, 0, s->kz0, s->kz1, s->stream); if (rc) return rc;
         rc = do_pass(s, 1, s->kz0, s->kz1, s->stream); if (rc) return rc;
         tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev);

@@ -161,6 +161,9 @@ struct sj_sim {
     int fan_next, fan_int; cudaStream_t fan_main; bool fan_on; int n_aux;
     // SJ_TRACE=1: per-launch CUDA events of one traced step (debug timeline, printed by sj_trace_dump)
     bool trace_on; std::vector<cudaEvent_t> tr_ev; std::vector<std::string> tr_name; cudaEvent_t tr_origin;
+    // one full time step (H-pass, E-pass, tick; side-stream fan-out included) captured as a CUDA graph and
+    // replayed by sj_run; dropped whenever a pointer or a work list the kernels receive changes
+    cudaGraphExec_t step_graph; long long graph_launches;
     long long launches;
     double pole_points;       // sum over E component points of n_poles (owned slab)
     double pole_points_int;   // same, restricted to the interior-kernel box

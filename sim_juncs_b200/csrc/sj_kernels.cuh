@@ -333,6 +333,10 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
             hx0.load(pH); hy0.load((pH + fcs)); hz0.load((pH + fcs2));
             hzj.load((pH + fcs2) - pitch); hxj.load(pH - pitch);
         } else { hx0.zero(); hy0.zero(); hz0.zero(); hzj.zero(); hxj.zero(); }
+        // the tile-edge neighbours are fetched with the plane's other loads (a load placed after the shuffles
+        // would cost the whole warp a second memory round trip per plane)
+        T hz_e = T(0), hy_e = T(0);
+        if (edge) { hz_e = (pH + fcs2)[-1]; hy_e = (pH + fcs)[-1]; }
         unsigned char nx_[V], ny_[V], nz_[V];
         if (st) {
             ex.load(pE); ey.load((pE + fcs)); ez.load((pE + fcs2));
@@ -344,7 +348,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
         }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
-        if (edge) { hz_p = (pH + fcs2)[-1]; hy_p = (pH + fcs)[-1]; }
+        if (edge) { hz_p = hz_e; hy_p = hy_e; }
         const unsigned smask = SRC ? src_plane_mask(p, k) : 0u;
         if (st) {
 #pragma unroll
@@ -703,10 +707,11 @@ __device__ __forceinline__ void h_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0) { ux.load(pU); uy.load((pU + bcs)); uz.load((pU + bcs2)); }
         } else { ex1.zero(); ey1.zero(); ez0.zero(); }
         if (rowp) { ezj.load((pE + fcs2) + pitch); exj.load(pE + pitch); } else { ezj.zero(); exj.zero(); }
+        T ez_e = T(0), ey_e = T(0);       // tile-edge neighbours, issued with the plane's other loads
+        if (edge) { ez_e = (pE + fcs2)[V]; ey_e = (pE + fcs)[V]; }
         T ez_n = __shfl_down_sync(0xffffffffu, ez0.v[0], 1, LX);
         T ey_n = __shfl_down_sync(0xffffffffu, ey0.v[0], 1, LX);
-        if (edge) { ez_n = (pE + fcs2)[V]; ey_n = (pE + fcs)[V]; }
-        else if (last) { ez_n = T(0); ey_n = T(0); }
+        if (last) { ez_n = ez_e; ey_n = ey_e; }
         if (act) {
             T szi = T(0), szh = T(0), izh = T(1);
             if (PD == 0 || PD == 3) { szi = p.sig[2][2 * k]; szh = p.sig[2][2 * k + 1]; izh = p.siginv[2][2 * k + 1]; }
@@ -853,10 +858,11 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             }
         } else { hx0.zero(); hy0.zero(); hz0.zero(); }
         if (rowm) { hzj.load((pH + fcs2) - pitch); hxj.load(pH - pitch); } else { hzj.zero(); hxj.zero(); }
+        T hz_e = T(0), hy_e = T(0);       // tile-edge neighbours, issued with the plane's other loads
+        if (edge) { hz_e = (pH + fcs2)[-1]; hy_e = (pH + fcs)[-1]; }
         T hz_p = __shfl_up_sync(0xffffffffu, hz0.v[V - 1], 1, LX);
         T hy_p = __shfl_up_sync(0xffffffffu, hy0.v[V - 1], 1, LX);
-        if (edge) { hz_p = (pH + fcs2)[-1]; hy_p = (pH + fcs)[-1]; }
-        else if (first) { hz_p = T(0); hy_p = T(0); }
+        if (first) { hz_p = hz_e; hy_p = hy_e; }
         const unsigned smask = SRC ? src_plane_mask(p, k) : 0u;
         if (act) {
             T szi = T(0), izi = T(1), szh = T(0);

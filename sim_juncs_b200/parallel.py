@@ -56,6 +56,11 @@ class HaloExchanger:
                 if up < world:
                     self.ops_e.append(dist.P2POp(dist.irecv, plane(c, q, k1), up, group))
 
+    def post(self, which):
+        """Enqueue the exchange after the H-pass ("h") or the E-pass ("e"); returns the requests to wait on."""
+        ops = self.ops_h if which == "h" else self.ops_e
+        return dist.batch_isend_irecv(ops) if ops else []
+
     def _run(self, ops):
         if ops:
             for r in dist.batch_isend_irecv(ops):
@@ -89,22 +94,59 @@ def cuda_plane_view(sim, device):
     return plane
 
 
+def step_schedule(kz, rank, world, overlap):
+    """The order of one time step of a slab as a list of actions, executed stream-ordered by SlabRunner:
+      ("h", a, b) / ("e", a, b)  half-pass over the planes [a, b)
+      ("post_h",) / ("post_e",)  enqueue the halo sends/receives (they start when everything launched so far is done)
+      ("wait_h",) / ("wait_e",)  make the following launches wait for that exchange
+    Overlapped order: the plane a neighbour needs is computed first and is on the wire while the rest
+    of the slab runs -- the top owned H plane (rank+1's lower halo) and the bottom owned E plane (rank-1's upper
+    halo).  The E-pass's first plane needs the H halo, the next step's first H plane needs the E halo, hence the
+    waits sit right before them."""
+    k0, k1 = kz
+    up, down = rank + 1 < world, rank > 0
+    if not overlap or k1 - k0 < 2:
+        return [("h", k0, k1), ("post_h",), ("wait_h",), ("e", k0, k1), ("post_e",), ("wait_e",)]
+    acts = []
+    if up:
+        acts += [("h", k1 - 1, k1), ("post_h",), ("h", k0, k1 - 1)]
+    else:
+        acts += [("post_h",), ("h", k0, k1)]
+    acts += [("wait_h",)]
+    if down:
+        acts += [("e", k0, k0 + 1), ("post_e",), ("e", k0 + 1, k1)]
+    else:
+        acts += [("post_e",), ("e", k0, k1)]
+    acts += [("wait_e",)]
+    return acts
+
+
 class SlabRunner:
     """Drives one slab: sample / H-pass / exchange / E-pass / exchange / tick, all stream-ordered on
-    torch's current CUDA stream so that NCCL and the kernels serialise without host syncs."""
+    torch's current CUDA stream so that NCCL and the kernels serialise without host syncs.  With
+    `overlap` the boundary plane of each half-pass is computed first and exchanged while the rest of the
+    slab is updated (torch's NCCL stream runs beside the compute stream; `wait()` only orders streams)."""
 
-    def __init__(self, sim, kz, n_sets, device, save_span=20):
+    def __init__(self, sim, kz, n_sets, device, save_span=20, overlap=True):
         self.sim, self.kz, self.save_span = sim, kz, save_span
         self.stream = torch.cuda.current_stream(device).cuda_stream
         self.halo = HaloExchanger(cuda_plane_view(sim, device), kz, n_sets, dist.get_rank(), dist.get_world_size())
+        self.acts = step_schedule(kz, dist.get_rank(), dist.get_world_size(), overlap)
         self.i = 0
 
     def step(self):
         if self.i % self.save_span == 0:
             self.sim.sample(self.stream)
-        self.sim.h_pass(self.kz[0], self.kz[1], self.stream)
-        self.halo.after_h()
-        self.sim.e_pass(self.kz[0], self.kz[1], self.stream)
-        self.halo.after_e()
+        pending = {}
+        for act in self.acts:
+            if act[0] == "h":
+                self.sim.h_pass(act[1], act[2], self.stream)
+            elif act[0] == "e":
+                self.sim.e_pass(act[1], act[2], self.stream)
+            elif act[0] in ("post_h", "post_e"):
+                pending[act[0][-1]] = self.halo.post(act[0][-1])
+            else:
+                for r in pending.pop(act[0][-1]):
+                    r.wait()
         self.sim.tick(self.stream)
         self.i += 1

@@ -41,6 +41,21 @@ def test_cpp_cli_matches_python_mirror(tmp_path, scene_json):
         worst = max(worst, float(np.abs(got[:len(series)] - series).max()))
     assert worst == 0.0
     assert max(np.abs(s_).max() for s_ in bg.get_field_times()) > 1e-6
+    # field_samples.h5 of the C++ host (host/sj_hdf5.hpp) against the Python mirror's own file, dataset by dataset
+    from sim_juncs_b200 import hdf5
+    from sim_juncs_b200.output import reference_fft
+    mine = hdf5.File(bg.save_field_times(str(tmp_path / "py")))
+    cpp = hdf5.File(os.path.join(str(tmp_path), "field_samples.h5"))
+    assert cpp.keys() == mine.keys() and cpp["cluster_0"].keys() == mine["cluster_0"].keys()
+    assert cpp["info"]["cgs_params"].keys() == mine["info"]["cgs_params"].keys()
+    assert cpp["info"]["sources"].read().tobytes() == mine["info"]["sources"].read().tobytes()
+    assert cpp["info"]["n_time_points"][0] == mine["info"]["n_time_points"][0]
+    for pt in ("point_00", "point_49"):
+        a, b = cpp["cluster_0"][pt]["time"].read(), mine["cluster_0"][pt]["time"].read()
+        assert np.array_equal(a["Re"][:len(b)], b["Re"]) and np.array_equal(a["Im"][:len(b)], b["Im"])
+        fa = cpp["cluster_0"][pt]["frequency"].read()
+        fb = reference_fft(a["Re"] + 1j * a["Im"])
+        assert len(fa) == len(fb) and np.allclose(fa["Re"] + 1j * fa["Im"], fb, rtol=1e-9, atol=1e-12 * np.abs(fb).max())
 
 
 def test_python_cli_with_own_parser_matches_reference_parser_path(tmp_path, scene_json):

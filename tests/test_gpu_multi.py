@@ -26,7 +26,7 @@ def _small_settings(scene_json):
     return st
 
 
-def _worker(rank, world, port, scene_path, steps, out):
+def _worker(rank, world, port, scene_path, steps, overlap, out):
     import torch.distributed as dist
     from sim_juncs_b200.bound_geom import BoundGeom
     from sim_juncs_b200.parallel import SlabRunner, slab_range
@@ -42,7 +42,7 @@ def _worker(rank, world, port, scene_path, steps, out):
     n = st.grid_cells()
     kz = slab_range(n + 1, rank, world)
     bg = BoundGeom(st, scene_path, n_sets=2, kz=kz, device=rank)
-    runner = SlabRunner(bg.sim, kz, 2, dev, save_span=5)
+    runner = SlabRunner(bg.sim, kz, 2, dev, save_span=5, overlap=overlap)
     for _ in range(steps):
         runner.step()
     torch.cuda.synchronize()
@@ -53,7 +53,8 @@ def _worker(rank, world, port, scene_path, steps, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_slabs_bitwise(scene_json):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_gpu_slabs_bitwise(scene_json, overlap):
     import torch.multiprocessing as mp
     from sim_juncs_b200.bound_geom import BoundGeom
     steps, world = 60, 2
@@ -65,7 +66,7 @@ def test_two_gpu_slabs_bitwise(scene_json):
     ref_mon = whole.sim.monitors()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), path, steps, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), path, steps, overlap, out), nprocs=world, join=True)
         res = dict(out)
     mon = sum(res[r][2] for r in range(world))
     assert np.array_equal(mon, ref_mon)

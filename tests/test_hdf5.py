@@ -134,3 +134,36 @@ def test_field_samples_file_replays_the_reference_scripts_reads(tmp_path):
     assert np.array_equal(np.array(f[clust[1]][pts[0]]["time"]["Re"]), bg.field_times[4].real)
     assert f[clust[1]]["locations"]["z"][-1] == bg.monitor_locs[11, 2]
     assert len(f[clust[0]][keylist[1]]["frequency"]) == 128
+
+
+@pytest.mark.parametrize("n_points", [3, 300])
+def test_cpp_writer_is_byte_identical_to_the_python_writer(tmp_path, n_points):
+    """host/sj_hdf5.hpp (used by the C++ sim_geom host) and hdf5.py lay the same content out identically."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "h5w")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-I", os.path.join(root, "host"), "-o", exe,
+                           os.path.join(root, "tests", "cpp", "h5_writer_main.cpp")])
+    cpp_path, py_path = str(tmp_path / "cpp.h5"), str(tmp_path / "py.h5")
+    subprocess.check_call([exe, cpp_path, str(n_points)])
+    w = hdf5.H5Writer(py_path)
+    w.create_dataset("info/time_bounds", np.array([0.0, 300.0, 1.5]))
+    w.create_dataset("info/n_clusters", np.array([1], dtype=np.uint64))
+    src = np.zeros(1, dtype=SRC_TYPE)
+    src[0] = (0.76, 1.27, 0.25, 5.0, 20.2, 1.0)
+    w.create_dataset("info/sources", src)
+    w.create_group("info/cgs_params")
+    locs = np.zeros(n_points, dtype=LOC_TYPE)
+    flat = 0.25 * np.arange(3 * n_points).reshape(-1, 3)
+    locs["x"], locs["y"], locs["z"] = flat[:, 0], flat[:, 1], flat[:, 2]
+    w.create_dataset("cluster_0/locations", locs)
+    w.create_dataset("cluster_1/locations", np.zeros(0, dtype=LOC_TYPE))
+    for i in range(n_points):
+        t = np.zeros(9, dtype=FIELD_TYPE)
+        t["Re"], t["Im"] = i + 0.5 * np.arange(9), 0.0 - np.arange(9.0)
+        w.create_dataset("cluster_0/point_%04d/time" % i, t)
+    w.close()
+    a, b = open(cpp_path, "rb").read(), open(py_path, "rb").read()
+    assert len(a) == len(b) and a == b
+    f = hdf5.File(cpp_path)
+    assert f["info"]["sources"][0]["end_time"] == 20.2 and len(f["cluster_0"]) == n_points + 1

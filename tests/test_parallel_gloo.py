@@ -92,3 +92,30 @@ def test_halo_exchange_world3_gloo():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, _free_port(), 10, 1, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True, 2: True}
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_step_schedule_orders_boundary_planes_before_their_exchange(world, overlap):
+    from sim_juncs_b200.parallel import step_schedule
+    n = 37
+    for rank in range(world):
+        kz = slab_range(n, rank, world)
+        acts = step_schedule(kz, rank, world, overlap)
+        for which in "he":
+            spans = [(a[1], a[2]) for a in acts if a[0] == which]
+            covered = sorted(k for a, b in spans for k in range(a, b))
+            assert covered == list(range(kz[0], kz[1]))                      # every owned plane exactly once
+            post, wait = acts.index(("post_" + which,)), acts.index(("wait_" + which,))
+            assert post < wait
+            # the plane the neighbour receives is finished before the exchange is posted
+            need = kz[1] - 1 if which == "h" else kz[0]
+            has_peer = (rank + 1 < world) if which == "h" else (rank > 0)
+            if has_peer:
+                done = [k for a in acts[:post] if a[0] == which for k in range(a[1], a[2])]
+                assert need in done
+                if overlap and kz[1] - kz[0] >= 2:
+                    assert len(done) == 1                                    # ... and only that plane
+        # the E-pass starts after the H halo has arrived; the step ends with the E halo in place
+        first_e = min(i for i, a in enumerate(acts) if a[0] == "e")
+        assert acts.index(("wait_h",)) < first_e and acts[-1] == ("wait_e",)
