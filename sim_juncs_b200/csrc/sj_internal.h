@@ -171,7 +171,24 @@ struct sj_sim {
     std::string err;
 };
 
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            s->err = b_;                                                                           \
+            return SJ_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
 int sj_finish_materials(sj_sim *s);
+void sj_interior_geom(const sj_sim *s, int k_begin, int k_end, IntGeom &g, dim3 &grd);
+// sj_launch_f64.cu / sj_launch_f32.cu: one half-pass over the planes [k0, k1) on stream st; kernel-family timings
+int sj_launch_pass_f64(sj_sim *s, int which, int k0, int k1, cudaStream_t st);
+int sj_launch_pass_f32(sj_sim *s, int which, int k0, int k1, cudaStream_t st);
+int sj_profile_f64(sj_sim *s, int reps, double out[4]);
+int sj_profile_f32(sj_sim *s, int reps, double out[4]);
 // sj_raster.cu
 int sj_raster_launch(sj_sim *s, double ambient_eps, int n_nodes, const sj_csg_node *nodes, int n_regions,
                      const sj_region *regions);

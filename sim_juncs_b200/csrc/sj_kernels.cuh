@@ -416,10 +416,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <typename T, int V, int NSLOT>
+template <typename T, int V, int NSLOT, int NT = 256>
 struct Stager {
     uint4 *base;   // &smem[threadIdx.x]
-    __device__ __forceinline__ uint4 *addr(int st, int slot) const { return base + (st * NSLOT + slot) * 256; }
+    __device__ __forceinline__ uint4 *addr(int st, int slot) const { return base + (st * NSLOT + slot) * NT; }
     __device__ __forceinline__ void issue(int st, int slot, const T *g, bool pred) const {
         if (pred) cp_async16(addr(st, slot), g);
         else *addr(st, slot) = make_uint4(0u, 0u, 0u, 0u);
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g
 
 // flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
 // from the first one anywhere in the tile or has poles
-__global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, IntGeom g, int tile_w, int tile_h,
+static __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, IntGeom g, int tile_w, int tile_h,
                                   int pitch, long long plane, int kz0, int first_disp, unsigned *flags) {
     const int kc = blockIdx.z;
     const int kb = g.k_lo + kc * g.zchunk, ke = min(kb + g.zchunk, g.k_hi);
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(256, (V * sizeof(T) == 8) ? (NS == 0 ? (FACE ?
 }
 
 // material flags of the PML work items (one block per item)
-__global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, const WorkItem *items, int tile_w,
+static __global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, const WorkItem *items, int tile_w,
                                   int tile_h, int n0, int n1, int pitch, long long plane, int kz0, int first_disp,
                                   unsigned *flags) {
     const WorkItem it = items[blockIdx.x];
@@ -982,10 +982,10 @@ __global__ void sample_monitors(KParams<T> p, MonDev m, long long base_step, int
     if (set == 0 && (res > 1000.0 || res != res)) m.flags[0] = 1;
 }
 
-__global__ void tick_kernel(long long *step) { *step += 1; }
+static __global__ void tick_kernel(long long *step) { *step += 1; }
 
 // remap material bytes through a 256-entry LUT (non-dispersive materials first)
-__global__ void remap_bytes(uint8_t *a, long long n, const uint8_t *lut) {
+static __global__ void remap_bytes(uint8_t *a, long long n, const uint8_t *lut) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) a[t] = lut[a[t]];
 }

@@ -159,7 +159,14 @@ class H5Writer:
         return self._alloc(struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body)
 
     def _emit_dataset(self, a):
-        raw = a.tobytes()
+        if a.dtype.names and sum(a.dtype.fields[n][0].itemsize for n in a.dtype.names) != a.dtype.itemsize:
+            flat = np.zeros(a.size * a.dtype.itemsize, dtype=np.uint8)    # padding bytes of a struct are written as zeros
+            view = flat.view(a.dtype).reshape(a.shape)
+            for name in a.dtype.names:
+                view[name] = a[name]
+            raw = flat.tobytes()
+        else:
+            raw = a.tobytes()
         addr = self._alloc(raw) if raw else UNDEF
         shape = a.shape if a.ndim else (1,)
         space = struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", d) for d in shape)

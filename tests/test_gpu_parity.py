@@ -6,7 +6,7 @@ oracle, so the fp64 bound asserted here is 1e-11."""
 import numpy as np
 import pytest
 
-from helpers import oracle_bound_geom, region_tables, rel_l2, settings_from_doc
+from helpers import early_pulse, oracle_bound_geom, region_tables, rel_l2, settings_from_doc
 from oracle.oracle import OracleSim
 from sim_juncs_b200 import Sim
 from sim_juncs_b200.bound_geom import BoundGeom
@@ -253,12 +253,13 @@ def test_slab_decomposition_is_bitwise(scene_json):
     (fields and monitors): the N-GPU path cannot change results."""
     name = "Au_graphene_box"
     st = settings_from_doc(scene_json(name))
-    whole = BoundGeom(st, scene_json(name), n_sets=1)
+    mk = lambda: early_pulse(Scene.load(scene_json(name)))      # the pulse must cross the cut within the run
+    whole = BoundGeom(st, mk(), n_sets=1)
     n = st.grid_cells()
-    cut = 97
-    lo = BoundGeom(st, scene_json(name), n_sets=1, kz=(0, cut))
-    up = BoundGeom(st, scene_json(name), n_sets=1, kz=(cut, n + 1))
-    steps = 30
+    cut = 49
+    lo = BoundGeom(st, mk(), n_sets=1, kz=(0, cut))
+    up = BoundGeom(st, mk(), n_sets=1, kz=(cut, n + 1))
+    steps = 200
     whole.sim.run(steps, 5)
     for i in range(steps):
         if i % 5 == 0:
@@ -277,8 +278,53 @@ def test_slab_decomposition_is_bitwise(scene_json):
     for comp in range(6):
         w = whole.sim.field(comp)
         assert np.array_equal(w[:cut], lo.sim.field(comp)) and np.array_equal(w[cut:], up.sim.field(comp)), comp
+        if comp in (0, 4):                                        # Ex / Hy of the Ex-polarised pulse, both sides of the cut
+            assert np.abs(w[cut - 2:cut]).max() > 1e-6 and np.abs(w[cut:cut + 20]).max() > 1e-6
     m = lo.sim.monitors() + up.sim.monitors()          # each rank fills the monitors it owns, 0 elsewhere
     assert np.array_equal(m, whole.sim.monitors())
+
+
+def test_graph_replay_equals_direct_launches(scene_json):
+    """sj_run replays one captured CUDA graph per step; stepping the same scene pass by pass through sj_pass /
+    sj_tick launches the kernels directly.  Fields and monitors must agree bit for bit, across a drive-table
+    reallocation (which re-captures the graph) as well."""
+    name = "Au_graphene_box"
+    st = settings_from_doc(scene_json(name))
+    n = st.grid_cells()
+    a = BoundGeom(st, early_pulse(Scene.load(scene_json(name))), n_sets=2)
+    b = BoundGeom(st, early_pulse(Scene.load(scene_json(name))), n_sets=2)
+    steps = 120
+    a.sim.run(20, 5)
+    a.sim.run(steps - 20, 5)                        # second call: the drive table grows, the graph is rebuilt
+    for i in range(steps):
+        if i % 5 == 0:
+            b.sim.sample()
+        b.sim.h_pass(0, n + 1)
+        b.sim.e_pass(0, n + 1)
+        b.sim.tick()
+    b.sim.sync()
+    assert a.sim.steps_done() == b.sim.steps_done() == steps
+    for q in range(2):
+        for comp in range(6):
+            assert np.array_equal(a.sim.field(comp, q), b.sim.field(comp, q)), (comp, q)
+    assert np.array_equal(a.sim.monitors(), b.sim.monitors())
+    assert np.abs(a.sim.field(0, 0)).max() > 1e-6 and np.abs(a.sim.field(0, 1)).max() > 1e-6
+
+
+def test_linearity_in_source_amplitude_at_full_size(scene_json):
+    """The path is linear in the drive: at the full 181^3 bench size, a source 3x as strong gives monitor series
+    3x as large (to round-off), and fields stay finite."""
+    name = "Au_graphene_box"
+    st = settings_from_doc(scene_json(name))
+    a = BoundGeom(st, scene_json(name), n_sets=1)
+    sc = Scene.load(scene_json(name))
+    sc.sources[0].amplitude *= 3.0
+    b = BoundGeom(st, sc, n_sets=1)
+    for bg in (a, b):
+        bg.sim.run(1600, 20)
+    ma, mb = a.sim.monitors(), b.sim.monitors()
+    assert np.isfinite(mb).all() and np.abs(ma).max() > 1e-6
+    assert rel_l2(mb, 3.0 * ma) < 1e-13
 
 
 def test_quadrature_sets_are_phase_shifted_copies(scene_json):
