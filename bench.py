@@ -144,6 +144,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, where the one JSON line belongs
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     st = load_settings()
@@ -264,8 +266,8 @@ def run_ours(args):
                             info.phase, info.start_time * cba, info.end_time * cba, True)
     sim.add_monitors(np.array(sc.monitor_locs), comp=0)
     from sim_juncs_b200.parallel import SlabRunner
-    stream = torch.cuda.current_stream(dev)
     runner = SlabRunner(sim, kz, n_sets, dev, save_span=SAVE_SPAN, overlap=not args.no_overlap)
+    stream = runner.tstream                    # the stream the kernels and the NCCL ordering live on
 
     def step(i):
         runner.step()
@@ -308,6 +310,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
+    runner.synchronize()
     mon = sim.monitors()
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)

@@ -131,8 +131,21 @@ class BoundGeom:
         dt = self.sim.dt
         self.n_t_pts = int((self.ttot + dt / 2) / dt)
         t0 = time.time()
-        self.sim.run(self.n_t_pts, self.save_span, sync=False)
+        if fname_prefix is not None:                 # fields.output_hdf5(meep::Dielectric, ...), disp.cpp:696
+            from .output import write_eps_h5
+            write_eps_h5(self, fname_prefix)
         try:
+            if self.dump_raw and fname_prefix is not None:
+                # disp.cpp:719-741 with dump_raw: at every save point the whole Ex field goes to ex-<time>.h5 first
+                from .output import write_ex_h5
+                done = 0
+                while done < self.n_t_pts:
+                    write_ex_h5(self, fname_prefix, done * dt)
+                    chunk = min(self.save_span, self.n_t_pts - done)
+                    self.sim.run(chunk, self.save_span, sync=False)
+                    done += chunk
+            else:
+                self.sim.run(self.n_t_pts, self.save_span, sync=False)
             self.sim.sync()
         except Exception as err:                     # divergence is reported, the save still happens
             print("error on step %d: %s" % (self.n_t_pts, err))

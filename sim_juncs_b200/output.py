@@ -112,3 +112,69 @@ def save_field_samples(bg, out_dir, with_frequency=True):
     d = field_samples_dict(bg, with_frequency)
     np.savez(os.path.join(out_dir, "field_samples.npz"), **d)
     return write_field_samples_h5(d, os.path.join(out_dir, "field_samples.h5"))
+
+
+# ---- whole-grid dumps: eps-000000.00.h5 at the start of run(), ex-<time>.h5 per save when dump_raw -------------
+def make_dec_str(t, n_digits_a, n_digits_b, dec_char="."):
+    """argparse.h:390-431: zero-padded `aaa.bbb`; None where the reference returns -2 (too many integer digits)."""
+    bef = int(t)
+    t -= float(bef)
+    digits = []
+    while True:
+        if len(digits) == n_digits_a:
+            return None
+        digits.append(chr(ord("0") + bef % 10))
+        bef //= 10
+        if not bef:
+            break
+    out = "0" * (n_digits_a - len(digits)) + "".join(reversed(digits)) + dec_char
+    for _ in range(n_digits_b):
+        t *= 10
+        out += chr(ord("0") + int(t))
+        t -= math.floor(t)
+    return out
+
+
+def field_dump_name(time, ttot, dt):
+    """disp.cpp:709-713,733: "ex-" + make_dec_str(fields.time(), ceil(log10 ttot), ceil(-log10 dt) + 1) + ".h5"."""
+    n_digits_a = int(math.ceil(math.log(ttot) / math.log(10)))
+    n_digits_b = int(math.ceil(-math.log(float(dt)) / math.log(10.0))) + 1
+    return "ex-" + (make_dec_str(time, n_digits_a, n_digits_b) or "") + ".h5"
+
+
+def centred(a, comp):
+    """An E-component Yee array [k][j][i] of (n+1)^3 points -> (nx, ny, nz) values at the pixel centres, x slowest
+    (meep's output grid and axis order): the mean of the four Yee points of that component around each centre."""
+    if comp == 0:
+        c = 0.25 * (a[:-1, :-1, :-1] + a[1:, :-1, :-1] + a[:-1, 1:, :-1] + a[1:, 1:, :-1])
+    elif comp == 1:
+        c = 0.25 * (a[:-1, :-1, :-1] + a[1:, :-1, :-1] + a[:-1, :-1, 1:] + a[1:, :-1, 1:])
+    else:
+        c = 0.25 * (a[:-1, :-1, :-1] + a[:-1, 1:, :-1] + a[:-1, :-1, 1:] + a[:-1, 1:, 1:])
+    return np.ascontiguousarray(c.transpose(2, 1, 0))
+
+
+def write_eps_h5(bg, out_dir):
+    """fields.output_hdf5(meep::Dielectric, total_volume) (disp.cpp:696): dataset "eps" = n_c / sum_c <chi1inv_c> at the
+    pixel centres, chi1inv_c = 1 / eps_inf at the Yee points of E component c (meep fields::get_eps, recalled)."""
+    from .hdf5 import H5Writer
+    table = np.array([m[0] for m in bg.sim.material_table()])
+    tr = 0.0
+    for c in range(3):
+        tr = tr + centred(1.0 / table[bg.sim.region_masks(c)], c)
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, "eps-000000.00.h5")
+    with H5Writer(path) as w:
+        w.create_dataset("eps", 3.0 / tr)
+    return path
+
+
+def write_ex_h5(bg, out_dir, time):
+    """fields.output_hdf5(meep::Ex, vol.surroundings(), file) per save (disp.cpp:732-737): datasets "ex.r", "ex.i"."""
+    from .hdf5 import H5Writer
+    path = os.path.join(out_dir, field_dump_name(time, bg.ttot, bg.sim.dt))
+    with H5Writer(path) as w:
+        w.create_dataset("ex.r", centred(bg.sim.field(0, 0), 0))
+        if bg.n_sets >= 2 and bg.phases is None:
+            w.create_dataset("ex.i", centred(bg.sim.field(0, 1), 0))
+    return path

@@ -401,3 +401,33 @@ def test_save_field_samples_npz(tmp_path, scene_json):
     assert z["cluster_0/point_0/time"].shape == (234, 2) and z["cluster_0/point_0/frequency"].shape == (128, 2)
     assert z["info/cgs_params/l_per_um"][0] == 2 and z["info/cgs_params/tot_len"][0] == 4     # main_test.cpp:1968-1977
     assert z["info/sources"].shape == (1, 6)
+
+
+def test_raw_dumps_eps_and_ex_files(tmp_path, scene_json):
+    """run(out_dir) writes eps-000000.00.h5 (disp.cpp:696) and, with dump_raw, one ex-<time>.h5 per save (disp.cpp:732-737)
+    with meep's dataset names and axis order (x slowest)."""
+    import glob
+    from sim_juncs_b200 import hdf5
+    from sim_juncs_b200.output import centred
+    st = settings_from_doc(scene_json("tests_run_slabs"))
+    st.dump_raw = 1
+    st.save_span = 13
+    bg = BoundGeom(st, scene_json("tests_run_slabs"), n_sets=2)
+    bg.run(str(tmp_path))
+    n = st.grid_cells()
+    eps = hdf5.File(str(tmp_path / "eps-000000.00.h5"))["eps"].read()
+    assert eps.shape == (n, n, n)
+    table = sorted(m[0] for m in bg.sim.material_table())
+    assert abs(eps.min() - table[0]) < 1e-12 and abs(eps.max() - table[-1]) < 1e-12      # slabs of eps 3.5 in the ambient
+    assert len(np.unique(np.round(eps, 9))) > 2                                          # interface pixels are blended
+    files = sorted(glob.glob(str(tmp_path / "ex-*.h5")))
+    assert len(files) == (bg.n_t_pts + st.save_span - 1) // st.save_span == len(bg.get_field_times()[0])
+    first, last = hdf5.File(files[0]), hdf5.File(files[-1])
+    assert first.keys() == ["ex.i", "ex.r"] and not first["ex.r"].read().any()
+    lr = last["ex.r"].read()
+    assert lr.shape == (n, n, n) and np.abs(lr).max() > 1e-6
+    # the run continued for the steps after the last save, so compare against a second run stopped at that save
+    ref = BoundGeom(st, scene_json("tests_run_slabs"), n_sets=2)
+    ref.sim.run(st.save_span * (len(files) - 1), st.save_span)
+    assert np.array_equal(lr, centred(ref.sim.field(0, 0), 0))
+    assert np.array_equal(last["ex.i"].read(), centred(ref.sim.field(0, 1), 0))

@@ -38,3 +38,27 @@ def test_zero_padded_names():
     assert point_name(7, 1600) == "point_0007" and point_name(1599, 1600) == "point_1599"
     assert cluster_name(3, 40) == "cluster_03" and cluster_name(40, 40) == "cluster_40"
     assert point_name(1, 2) == "point_1" and cluster_name(0, 1) == "cluster_0"
+
+
+def test_make_dec_str_reference_kats():
+    # src/main_test.cpp:5-15
+    from sim_juncs_b200.output import field_dump_name, make_dec_str
+    assert make_dec_str(0.25, 1, 2, ".") == "0.25"
+    assert make_dec_str(0.25, 2, 2, "_") == "00_25"
+    assert make_dec_str(123.5, 2, 1) is None                      # more integer digits than allotted: the reference's -2
+    # disp.cpp:709-713: digits from ttot and dt; run.conf-like numbers (ttot = 23.4, dt = 0.1)
+    assert field_dump_name(1.5, 23.4, 0.1) == "ex-01.50.h5"
+    assert field_dump_name(0.0, 174.9, 0.04972) == "ex-000.000.h5"
+
+
+def test_centred_interpolation_of_yee_arrays():
+    from sim_juncs_b200.output import centred
+    n = 5
+    k, j, i = np.meshgrid(np.arange(n + 1.0), np.arange(n + 1.0), np.arange(n + 1.0), indexing="ij")
+    # a field linear in the coordinates is reproduced exactly at the pixel centres by the four-point mean
+    for comp, off in ((0, (0.5, 0.0, 0.0)), (1, (0.0, 0.5, 0.0)), (2, (0.0, 0.0, 0.5))):
+        f = 2.0 * (i + off[0]) - 3.0 * (j + off[1]) + 0.5 * (k + off[2])      # value at the component's own Yee point
+        c = centred(f, comp)
+        assert c.shape == (n, n, n)
+        x, y, z = np.meshgrid(np.arange(n) + 0.5, np.arange(n) + 0.5, np.arange(n) + 0.5, indexing="ij")
+        assert np.allclose(c, 2.0 * x - 3.0 * y + 0.5 * z, atol=1e-12)
