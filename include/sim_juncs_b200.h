@@ -148,6 +148,9 @@ int sj_read_monitors(sj_sim *sim, double *out);
  * ranges so boundary planes can be computed first and exchanged while the rest runs.         */
 int sj_pass(sj_sim *sim, int which /*0 = H-pass, 1 = E-pass*/, int32_t k_begin, int32_t k_end,
             void *cuda_stream);
+/* cuda_stream (here and below): the cudaStream_t the launches are ordered on.  NULL selects the simulation's own
+ * non-blocking stream, which is NOT ordered with the legacy default stream (handle 0): a caller that moves the
+ * halos with NCCL / MPI on its own stream must pass that stream. */
 int sj_tick(sj_sim *sim, void *cuda_stream);        /* end of step: advance device step counter */
 int sj_sample(sj_sim *sim, void *cuda_stream);      /* sample monitors now */
 /* Device pointer + byte count of plane k (global index, may be a halo plane kz0-1 / kz1) of a
