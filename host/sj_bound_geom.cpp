@@ -286,24 +286,6 @@ struct NpzWriter {
     }
 };
 
-// data_utils.cpp:370-427 as the reference calls it (disp.cpp:806): X[k] = sum_{n < T} x[n] exp(-i (2 pi / N) n k) over
-// the first T = 2^floor(log2 N) samples, phase step of the FULL length N, k in FFT order (0 .. T/2-1, -T/2 .. -1).
-static std::vector<std::complex<double> > reference_fft(const std::vector<std::complex<double> > &x) {
-    const size_t n_full = x.size();
-    if (!n_full) return std::vector<std::complex<double> >();
-    const size_t t = (size_t)1 << (size_t)(log((double)n_full) / log(2.0));
-    const double tau_by_n = 2 * M_PI / (double)n_full;
-    std::vector<std::complex<double> > out(t);
-    const long half = (long)(t / 2);
-    for (size_t q = 0; q < t; ++q) {
-        const long k = t > 1 ? ((long)q < half ? (long)q : (long)q - (long)t) : 0;
-        std::complex<double> acc = 0.0;
-        for (size_t n = 0; n < t; ++n) acc += x[n] * std::polar(1.0, -tau_by_n * (double)n * (double)k);
-        out[q] = acc;
-    }
-    return out;
-}
-
 int sj_bound_geom::save_field_times(const char *fname_prefix) {
     char path[1024];
     snprintf(path, sizeof path, "%s/field_samples.h5", fname_prefix);
@@ -339,6 +321,11 @@ int sj_bound_geom::save_field_times(const char *fname_prefix) {
                 h.dataset_f64(std::string("info/cgs_params/") + nv.get_name(), &x, 1);
             }
         }
+        // `frequency` (data_utils.cpp:370-427 as called at disp.cpp:806) on the device: [n_locs][n_freq]{re, im}
+        int32_t n_freq = 0;
+        sj_read_spectra(sim, 0, n_sets > 1 ? 1 : -1, &n_freq, NULL);
+        std::vector<double> spec(std::max<size_t>((size_t)n_locs * n_freq * 2, 1));
+        if (n_freq && n_locs && sj_read_spectra(sim, 0, n_sets > 1 ? 1 : -1, &n_freq, spec.data())) { printf("%s\n", sj_last_error(sim)); return -1; }
         const size_t ngd = (size_t)(log((double)std::max<size_t>(monitor_clusters.size(), 1)) / log(10.0)) + 1;
         const size_t npd = (size_t)(log((double)std::max<size_t>(n_locs, 1)) / log(10.0)) + 1;
         size_t i = 0, off = 0;
@@ -355,8 +342,7 @@ int sj_bound_geom::save_field_times(const char *fname_prefix) {
                 strcpy(pname, "point_"); write_number(pname + 6, sizeof pname - 6, (int)i, npd);
                 const std::string base = std::string(cname) + "/" + pname;
                 h.dataset(base + "/time", t_cplx, field_times[i].data(), field_times[i].size(), 16);
-                const std::vector<std::complex<double> > f = reference_fft(field_times[i]);
-                h.dataset(base + "/frequency", t_cplx, f.data(), f.size(), 16);
+                h.dataset(base + "/frequency", t_cplx, &spec[(size_t)i * n_freq * 2], n_freq, 16);
             }
         }
         if (h.save(path)) { printf("cannot write %s\n", path); return -1; }

@@ -142,6 +142,11 @@ double sj_dt(const sj_sim *sim);
 /* out: [n_samples][n_monitors][n_sets] doubles (set 0 = Re, set 1 = Im in complex mode).
  * In a z-slab run each rank fills the monitors it owns and leaves the others 0. */
 int sj_read_monitors(sj_sim *sim, double *out);
+/* Spectra of the monitor series, computed on the device: the reference's fft() (src/data_utils.cpp:370-427) as
+ * save_field_times calls it (src/disp.cpp:806) -- only the first T = 2^floor(log2 N) of the N samples enter, the phase
+ * step is 2 pi / N of the full length, output in FFT order.  The complex series is (set_re, set_im); set_im = -1 for a
+ * real series.  *n_freq = T; out (may be NULL to query T): [n_monitors][T]{re, im} doubles. */
+int sj_read_spectra(sj_sim *sim, int32_t set_re, int32_t set_im, int32_t *n_freq, double *out);
 
 /* ---- z-slab halo exchange (one process per GPU; the caller moves the bytes) -------------
  * Fine-grained stepping used by the multi-GPU driver: half-passes restricted to local plane

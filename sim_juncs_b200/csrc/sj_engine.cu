@@ -916,6 +916,55 @@ extern "C" int sj_read_monitors(sj_sim *s, double *out) {
     return SJ_OK;
 }
 
+// ---- spectra of the monitor series on the device (reference: fft() of src/data_utils.cpp:370-427 as called from
+// save_field_times, disp.cpp:806).  X[m][q] = sum_{n < T} x_m[n] exp(-i (2 pi / N) n k(q)), T = 2^floor(log2 N) samples of
+// the N taken, k(q) = q for q < T/2 and q - T above (FFT order).  One warp per (monitor, q): the lanes stride over n and
+// the partial sums are combined with shuffles; the phase is reduced exactly in integers (n k mod N) before sincospi.
+static __global__ void monitor_dft_kernel(const double *__restrict__ series, int n_mon, int n_sets, int set_re, int set_im, int T,
+                                          int N, double *__restrict__ out) {
+    const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_mon * T) return;
+    const int mon = w / T, q = w % T;
+    const long long k = (T > 1 && q >= T / 2) ? (long long)q - T : q;
+    double ar = 0.0, ai = 0.0;
+    for (int n = lane; n < T; n += 32) {
+        long long r = (n * k) % N;
+        if (r < 0) r += N;
+        double sn, cs;
+        sincospi(-2.0 * (double)r / (double)N, &sn, &cs);
+        const double *x = series + ((long long)n * n_mon + mon) * n_sets;
+        const double xr = x[set_re], xi = set_im >= 0 ? x[set_im] : 0.0;
+        ar += xr * cs - xi * sn;
+        ai += xr * sn + xi * cs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ar += __shfl_down_sync(0xffffffffu, ar, o); ai += __shfl_down_sync(0xffffffffu, ai, o); }
+    if (lane == 0) { out[2 * (long long)w] = ar; out[2 * (long long)w + 1] = ai; }
+}
+
+extern "C" int sj_read_spectra(sj_sim *s, int32_t set_re, int32_t set_im, int32_t *n_freq, double *out) {
+    if (s) cudaSetDevice(s->g.device);
+    if (!s || !n_freq) return SJ_ERR_ARG;
+    if (set_re < 0 || set_re >= s->g.n_sets || set_im >= s->g.n_sets) return fail(s, SJ_ERR_ARG, "bad field set");
+    const int N = s->n_samples;
+    int T = 0;
+    if (N > 0) T = 1 << (int)(log((double)N) / log(2.0));       // the reference's own expression (data_utils.cpp:417)
+    *n_freq = T;
+    if (!out || !T || !s->n_mon) return SJ_OK;
+    double *dev = NULL;
+    const size_t cnt = (size_t)s->n_mon * T * 2;
+    CK(cudaMalloc((void **)&dev, cnt * sizeof(double)));
+    const long long threads = (long long)s->n_mon * T * 32;
+    monitor_dft_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s->stream>>>(s->series, s->n_mon, s->g.n_sets, set_re, set_im, T, N, dev);
+    s->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dev, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(s, SJ_ERR_CUDA, cudaGetErrorString(e));
+    return SJ_OK;
+}
+
 extern "C" int sj_plane_ptr(sj_sim *s, int comp, int set, int32_t k, void **ptr, size_t *bytes) {
     if (!s || comp < 0 || comp > 5 || set < 0 || set >= s->g.n_sets || !ptr) return SJ_ERR_ARG;
     const int kl = k - s->kz0 + 1;

@@ -154,6 +154,16 @@ class Sim:
             self._ck(self.L.sj_read_monitors(self.h, _dp(out)))
         return out
 
+    def spectra(self, set_re=0, set_im=None):
+        """[n_monitors][T] complex: the reference's `frequency` transform of every monitor series, on the device."""
+        t = C.c_int32()
+        im = -1 if set_im is None else int(set_im)
+        self._ck(self.L.sj_read_spectra(self.h, int(set_re), im, C.byref(t), None))
+        out = np.zeros((self.n_mon, t.value, 2))
+        if out.size:
+            self._ck(self.L.sj_read_spectra(self.h, int(set_re), im, C.byref(t), _dp(out)))
+        return out[:, :, 0] + 1j * out[:, :, 1]
+
     def field(self, comp, iset=0):
         out = np.zeros(self.shape)
         self._ck(self.L.sj_get_field(self.h, comp, iset, _dp(out)))

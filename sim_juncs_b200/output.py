@@ -51,6 +51,12 @@ def field_samples_dict(bg, with_frequency=True):
         d["info/cgs_params/" + name] = np.array([val])
     locs = np.array(bg.monitor_locs, dtype=np.float64).reshape(-1, 3)
     n_locs = len(locs)
+    # `frequency`: on the device (sj_read_spectra, one warp per monitor and bin) when the series are the simulation's own
+    spectra = None
+    sim = getattr(bg, "sim", None)
+    if with_frequency and sim is not None and getattr(bg, "phases", None) is None and len(bg.field_times) == n_locs \
+            and n_locs and all(len(f) == sim.L.sj_n_samples(sim.h) for f in bg.field_times):
+        spectra = sim.spectra(0, 1 if bg.n_sets >= 2 else None)
     n_cl = len(bg.monitor_clusters)
     i = off = 0
     for j in range(n_cl + 1):                 # sic: the reference writes one empty trailing cluster (disp.cpp:879)
@@ -65,7 +71,7 @@ def field_samples_dict(bg, with_frequency=True):
             pn = cn + "/" + point_name(i, n_locs)
             d[pn + "/time"] = np.stack([series.real, series.imag], axis=1)
             if with_frequency:
-                f = reference_fft(series)
+                f = spectra[i] if spectra is not None else reference_fft(series)
                 d[pn + "/frequency"] = np.stack([f.real, f.imag], axis=1)
             i += 1
     return d

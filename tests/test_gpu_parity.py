@@ -247,6 +247,36 @@ def test_au_graphene_box_short(prec, scene_json):
     assert mo.shape == mg.shape == (28, 50, 2)
 
 
+@pytest.mark.parametrize("name", ["Au_SiO2_bowtie", "Au_SiO2_box", "quartz_box"])
+def test_junction_scenes_reduced_grid(name, scene_json):
+    """configs[2], [3], [4] (bowtie with the gold tips, box, quartz) on a 91^3 grid with the pulse moved to the start
+    of the run, so that within 420 steps the wave has crossed the junction and entered the PML on every side: whole E
+    and H fields and the monitor series against the oracle."""
+    st = settings_from_doc(scene_json(name))
+    st.grid_num = 91
+    st.resolution = 91 / (2 * (st.len / 2 + st.pml_thickness))
+    n = st.grid_cells()
+    sc = early_pulse(Scene.load(scene_json(name)), 0.3)
+    bg = BoundGeom(st, sc, n_sets=2)
+    masks = [bg.sim.region_masks(c) for c in range(3)]
+    o, _ = oracle_bound_geom(sc, st, masks, nsets=2)
+    steps = 420
+    o.run(steps, 10)
+    bg.sim.run(steps, 10)
+    worst = 0.0
+    for kind, off in (("E", 0), ("H", 3)):
+        for q in range(2):
+            scale = max(np.linalg.norm(o.field(kind, c, q)) for c in range(3))
+            assert scale > 1e-3, (kind, q, scale)
+            for c in range(3):
+                worst = max(worst, np.linalg.norm(bg.sim.field(off + c, q) - o.field(kind, c, q)) / scale)
+    assert worst < TOL["f64"], worst
+    mo, mg = o.monitors(), bg.sim.monitors()
+    assert mo.shape == mg.shape and np.abs(mo).max() > 1e-4
+    assert rel_l2(mg, mo) < TOL["f64"]
+    assert n == 91
+
+
 # ---------------------------------------------------------------- size-independent properties at full size
 def test_slab_decomposition_is_bitwise(scene_json):
     """Two stacked z-slabs on one GPU with explicit halo exchange == the single-slab run, bit for bit
@@ -403,6 +433,33 @@ def test_save_field_samples_npz(tmp_path, scene_json):
     assert z["info/sources"].shape == (1, 6)
 
 
+def test_device_spectra_equal_reference_transform(scene_json):
+    """sj_read_spectra (warp-reduced DFT of the device-resident monitor series) against the host restatement of the
+    reference's fft() quirks (2^k truncation, 2 pi / N of the full length, FFT order); 131 saves -> 128 bins."""
+    from sim_juncs_b200.output import field_samples_dict, reference_fft
+    name = "Au_SiO2_box"
+    st = settings_from_doc(scene_json(name))
+    st.grid_num = 91
+    st.resolution = 91 / (2 * (st.len / 2 + st.pml_thickness))
+    st.save_span = 2
+    bg = BoundGeom(st, early_pulse(Scene.load(scene_json(name)), 0.3), n_sets=2)
+    bg.run()
+    n_saves = len(bg.get_field_times()[0])
+    assert 128 <= n_saves < 256
+    spec = bg.sim.spectra(0, 1)
+    assert spec.shape == (len(bg.get_monitor_locs()), 128)
+    peak = max(np.abs(reference_fft(f)).max() for f in bg.get_field_times())
+    assert peak > 1e-4
+    for j in (0, 7, len(bg.get_monitor_locs()) - 1):
+        want = reference_fft(bg.get_field_times()[j])
+        assert np.abs(spec[j] - want).max() < 1e-12 * peak
+    real_only = bg.sim.spectra(0, None)
+    assert np.abs(real_only[7] - reference_fft(np.array(bg.get_field_times()[7]).real)).max() < 1e-12 * peak
+    d = field_samples_dict(bg)                       # the save path takes the device spectra
+    f = d["cluster_00/point_0007/frequency"]
+    assert np.array_equal(f[:, 0] + 1j * f[:, 1], spec[7])
+
+
 def test_raw_dumps_eps_and_ex_files(tmp_path, scene_json):
     """run(out_dir) writes eps-000000.00.h5 (disp.cpp:696) and, with dump_raw, one ex-<time>.h5 per save (disp.cpp:732-737)
     with meep's dataset names and axis order (x slowest)."""
@@ -417,8 +474,10 @@ def test_raw_dumps_eps_and_ex_files(tmp_path, scene_json):
     n = st.grid_cells()
     eps = hdf5.File(str(tmp_path / "eps-000000.00.h5"))["eps"].read()
     assert eps.shape == (n, n, n)
-    table = sorted(m[0] for m in bg.sim.material_table())
-    assert abs(eps.min() - table[0]) < 1e-12 and abs(eps.max() - table[-1]) < 1e-12      # slabs of eps 3.5 in the ambient
+    table = [m[0] for m in bg.sim.material_table()]
+    present = sorted({table[m] for c in range(3) for m in np.unique(bg.sim.region_masks(c))})
+    assert len(present) >= 2                                                             # slabs of eps 3.5 in the ambient
+    assert abs(eps.min() - present[0]) < 1e-12 and abs(eps.max() - present[-1]) < 1e-12
     assert len(np.unique(np.round(eps, 9))) > 2                                          # interface pixels are blended
     files = sorted(glob.glob(str(tmp_path / "ex-*.h5")))
     assert len(files) == (bg.n_t_pts + st.save_span - 1) // st.save_span == len(bg.get_field_times()[0])
