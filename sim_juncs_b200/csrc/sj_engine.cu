@@ -98,7 +98,9 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     s->F = NULL;
     for (int c = 0; c < 3; ++c) { s->E[c] = s->H[c] = NULL; s->mat[c] = s->masks[c] = NULL; s->sigd[c] = s->siginvd[c] = NULL; }
     s->flags_int = NULL; s->mt_eps = NULL; s->src_dev = NULL; s->pml_lx = 32; s->pml_lx_n = 8; s->pml_v = 2;
-    for (int a = 0; a < 2; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; for (int b = 0; b < 2; ++b) { s->il_h[a][b].dev = NULL; s->il_h[a][b].n = 0; for (int c = 0; c < 2; ++c) { s->il_pml[a][b][c].dev = NULL; s->il_pml[a][b][c].n = 0; } } } s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
+    for (int a = 0; a < 4; ++a) { s->il_int[a].dev = NULL; s->il_int[a].n = 0; }
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { s->il_h[a][b].dev = NULL; s->il_h[a][b].n = 0; for (int c = 0; c < 4; ++c) { s->il_pml[a][b][c].dev = NULL; s->il_pml[a][b][c].n = 0; } }
+    s->first_disp = 0; s->int_lx = 32; s->int_zchunk = 16;
     for (int i = 0; i < 256; ++i) s->lut_inv[i] = (uint8_t)i;
     s->Pall = NULL;
     for (int q = 0; q < SJ_MAX_POLES; ++q) s->np_thr[q] = 1 << 30;
@@ -262,7 +264,8 @@ extern "C" void sj_destroy(sj_sim *s) {
     cudaFree(s->F); cudaFree(s->mat[0]);
     for (int c = 0; c < 3; ++c) { cudaFree(s->masks[c]); cudaFree(s->sigd[c]); cudaFree(s->siginvd[c]); }
     cudaFree(s->flags_int); cudaFree(s->mt_eps);
-    for (int a = 0; a < 2; ++a) { cudaFree(s->il_int[a].dev); for (int b = 0; b < 2; ++b) { cudaFree(s->il_h[a][b].dev); for (int c = 0; c < 2; ++c) cudaFree(s->il_pml[a][b][c].dev); } }
+    for (int a = 0; a < 4; ++a) cudaFree(s->il_int[a].dev);
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { cudaFree(s->il_h[a][b].dev); for (int c = 0; c < 4; ++c) cudaFree(s->il_pml[a][b][c].dev); }
     cudaFree(s->Pall); cudaFree(s->src_dev);
     for (auto &B : s->boxes) cudaFree(B.base);
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
@@ -432,7 +435,16 @@ int sj_finish_materials(sj_sim *s) {
             if (!v.empty()) CK(cudaMemcpy(L.dev, v.data(), v.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
             return 0;
         };
-        std::vector<WorkItem> lst[2];
+        // class of a tile from its flag word (tile_flags_kernel / item_flags_kernel): mixed -> 1; one material without
+        // poles -> 0; one material with 1 or 2 poles -> 2 / 3 (SJ_NO_UNI=1 sends those through the general path too)
+        static const bool uni_on = getenv("SJ_NO_UNI") == NULL;
+        auto tile_class = [&](unsigned f) -> int {
+            if (f & 1u) return 1;
+            if (!(f & 2u)) return 0;
+            const int np = s->mats_sorted[f >> 8].n_poles;
+            return (uni_on && np >= 1 && np <= 2 && s->n_slots <= 2) ? 1 + np : 1;
+        };
+        std::vector<WorkItem> lst[4];
         std::vector<unsigned> fl(std::max<size_t>(nfl, 1));
         if (nfl) CK(cudaMemcpy(fl.data(), s->flags_int, nfl * sizeof(unsigned), cudaMemcpyDeviceToHost));
         const int tw = s->int_lx * V, th = (32 / s->int_lx) * 8;
@@ -443,9 +455,9 @@ int sj_finish_materials(sj_sim *s) {
                         const unsigned f = fl[((size_t)kc * grd.y + ty) * grd.x + tx];
                         WorkItem w = {-1, q, g.i_lo + (int)tx * tw, g.j_lo + (int)ty * th, g.k_lo + kc * g.zchunk,
                                       std::min(g.k_lo + (kc + 1) * g.zchunk, g.k_hi), (int)(f >> 8), 0};
-                        lst[f & 1u].push_back(w);
+                        lst[tile_class(f)].push_back(w);
                     }
-        for (int a = 0; a < 2; ++a) { rc = upload(s->il_int[a], lst[a]); if (rc) return rc; }
+        for (int a = 0; a < 4; ++a) { rc = upload(s->il_int[a], lst[a]); if (rc) return rc; }
         for (int f = 0; f < 2; ++f)
             for (int wn = 0; wn < 2; ++wn) {
                 const std::vector<WorkItem> &src = s->h_items[f][wn];
@@ -459,9 +471,9 @@ int sj_finish_materials(sj_sim *s) {
                     CK(cudaStreamSynchronize(s->stream));
                     cudaFree(df);
                 }
-                std::vector<WorkItem> l2[2];
-                for (size_t i = 0; i < src.size(); ++i) { WorkItem w = src[i]; w.mat = (int)(f2[i] >> 8); l2[f2[i] & 1u].push_back(w); }
-                for (int a2 = 0; a2 < 2; ++a2) { rc = upload(s->il_pml[f][wn][a2], l2[a2]); if (rc) return rc; }
+                std::vector<WorkItem> l2[4];
+                for (size_t i = 0; i < src.size(); ++i) { WorkItem w = src[i]; w.mat = (int)(f2[i] >> 8); l2[tile_class(f2[i])].push_back(w); }
+                for (int a2 = 0; a2 < 4; ++a2) { rc = upload(s->il_pml[f][wn][a2], l2[a2]); if (rc) return rc; }
             }
     }
     s->materials_set = true;
@@ -645,7 +657,9 @@ static int ensure_drive(sj_sim *s, long long upto) {
             const HostSource &g = s->srcs[q];
             const std::complex<double> amp(g.amp_re, g.amp_im);
             std::complex<double> S = 0.0, J = 0.0;
-            if (g.integrated) S = src_dipole(g, n * s->dt);
+            // The E kernels advance E by chi (dD - dP - (S_{n+1} - S_n)); with E = 0 at step 0 that equals meep's
+            // E = chi (D - P - S) only if S_0 = 0, so a source that is already on at t = 0 enters with S_0 = 0.
+            if (g.integrated) { if (n > 0) S = src_dipole(g, n * s->dt); }
             else {
                 const double tm = n * s->dt + 0.5 * s->dt;
                 J = ((src_dipole(g, tm + s->dt) - src_dipole(g, tm)) / s->dt) * s->dt;

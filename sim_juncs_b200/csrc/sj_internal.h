@@ -127,7 +127,9 @@ struct sj_sim {
     unsigned *flags_int;
     std::vector<WorkItem> h_items[2][2];   // PML tiles: [general|face][wide|narrow]
     ItemList il_h[2][2];                   // H-pass PML lists, same indexing
-    ItemList il_int[2], il_pml[2][2][2];   // E-pass lists: interior [uniform|general]; PML [general|face][wide|narrow][uniform|general]
+    // E-pass lists by material class of the tile: 0 = one non-dispersive material, 1 = mixed (general path),
+    // 2 / 3 = one material with exactly 1 / 2 poles (uniform-dispersive fast path).  interior; PML [general|face][wide|narrow]
+    ItemList il_int[4], il_pml[2][2][4];
     int pml_lx, pml_lx_n;                  // lanes along x of the wide / narrow PML tiles
     int pml_v;                             // elements per thread in the PML kernels (full or half vector)
     int int_lx, int_zchunk;   // interior tiling: lanes along x per warp, planes per chunk

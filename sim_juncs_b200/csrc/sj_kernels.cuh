@@ -151,6 +151,28 @@ struct PolState {
         sum_new = sn;
         return dP;
     }
+    // same arithmetic with the coefficients of a block-uniform material held in registers (cfu[s] = {a, b, c})
+    __device__ __forceinline__ T advance_u(int c, int v, T drive, T &sum_new, const T (&cfu)[NS > 0 ? NS : 1][3]) {
+        T dP = T(0), sn = T(0);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const T pc = cur[c][s].v[v];
+            const T pn = cfu[s][0] * pc + cfu[s][1] * prv[c][s].v[v] + cfu[s][2] * drive;
+            prv[c][s].v[v] = pn;
+            dP += pn - pc; sn += pn;
+        }
+        sum_new = sn;
+        return dP;
+    }
+    // every slot of every component (uniform material with exactly NS poles)
+    __device__ __forceinline__ void load_all(const KParams<T> &p, int parity, long long xg) {
+        const T *bc = pol_base(p, parity) + xg, *bp = pol_base(p, parity ^ 1) + xg;
+        const long long cs = p.p_comp_stride;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) { need[c][s] = true; cur[c][s].load(bc + (3 * s + c) * cs); prv[c][s].load(bp + (3 * s + c) * cs); }
+    }
     __device__ __forceinline__ T sum_cur(int c, int v) const {
         T so = T(0);
 #pragma unroll
@@ -432,7 +454,9 @@ struct Stager {
     }
 };
 
-template <typename T, int V, int LX, int NS, bool SRC>
+// UNI: the tile holds one material with exactly NS poles (it.mat): no material bytes, coefficients in registers,
+// every polarisation vector loaded unconditionally.  Same arithmetic as the general path.
+template <typename T, int V, int LX, int NS, bool SRC, bool UNI>
 __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const IntGeom &g, const WorkItem &it, int kb, int ke,
                                                     uint4 *smem) {
     constexpr int NSLOT = 8 + 6 * NS;
@@ -495,23 +519,34 @@ __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const I
 #pragma unroll
     for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = nx_[v] = ny_[v] = nz_[v] = 0;
     if (ld) { hxm.load(pH - plane); hym.load((pH + fcs) - plane); } else { hxm.zero(); hym.zero(); }
-    if (st) {
+    if (!UNI && st) {
         load_bytes<V>(pm, mx); load_bytes<V>(pm + mcs, my); load_bytes<V>(pm + mcs2, mz);
         load_bytes<V>(pm + plane, nx_); load_bytes<V>(pm + mcs + plane, ny_); load_bytes<V>(pm + mcs2 + plane, nz_);
     }
-    unsigned need_c = need_of(mx, my, mz);
+    constexpr unsigned NEED_ALL = (1u << (3 * NS)) - 1u;
+    T cfu[NS][3], chi_m = T(0);
+    if (UNI) {
+        chi_m = p.mt_chi[it.mat];
+#pragma unroll
+        for (int s_ = 0; s_ < NS; ++s_)
+#pragma unroll
+            for (int q_ = 0; q_ < 3; ++q_) cfu[s_][q_] = p.mt_coef[((long long)it.mat * SJ_MAX_POLES + s_) * 3 + q_];
+    }
+    unsigned need_c = UNI ? NEED_ALL : need_of(mx, my, mz);
     T hz_pc = T(0), hy_pc = T(0);
     if (edge) { hz_pc = (pH + fcs2)[-1]; hy_pc = (pH + fcs)[-1]; }
     issue_plane(0, 0, xg, need_c);
     cp_async_commit();
     for (int k = kb; k < ke; ++k) {
         const int cur = (k - kb) & 1;
-        const unsigned need_n = need_of(nx_, ny_, nz_);
+        const unsigned need_n = UNI ? NEED_ALL : need_of(nx_, ny_, nz_);
         unsigned char fx[V], fy[V], fz[V];          // material bytes two planes ahead
+#pragma unroll
+        for (int v = 0; v < V; ++v) fx[v] = fy[v] = fz[v] = 0;
         T hz_pn = T(0), hy_pn = T(0);
         if (k + 1 < ke) {
             issue_plane(cur ^ 1, plane, xg + plane, need_n);
-            if (st) { load_bytes<V>(pm + 2 * plane, fx); load_bytes<V>(pm + mcs + 2 * plane, fy); load_bytes<V>(pm + mcs2 + 2 * plane, fz); }
+            if (!UNI && st) { load_bytes<V>(pm + 2 * plane, fx); load_bytes<V>(pm + mcs + 2 * plane, fy); load_bytes<V>(pm + mcs2 + 2 * plane, fz); }
             if (edge) { hz_pn = (pH + fcs2 + plane)[-1]; hy_pn = (pH + fcs + plane)[-1]; }
         }
         cp_async_commit();
@@ -549,12 +584,13 @@ __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const I
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         const T *cf = p.mt_coef + ((long long)m * SJ_MAX_POLES + s) * 3;
+                        const T c0 = UNI ? cfu[s][0] : cf[0], c1 = UNI ? cfu[s][1] : cf[1], c2 = UNI ? cfu[s][2] : cf[2];
                         const T pcur = pc[c][s].v[v];
-                        const T pn = cf[0] * pcur + cf[1] * pp[c][s].v[v] + cf[2] * e;
+                        const T pn = c0 * pcur + c1 * pp[c][s].v[v] + c2 * e;
                         pp[c][s].v[v] = pn;
                         dP += pn - pcur;
                     }
-                    e += p.mt_chi[m] * (dD[c] - dP);
+                    e += (UNI ? chi_m : p.mt_chi[m]) * (dD[c] - dP);
                 }
             }
             ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
@@ -573,15 +609,15 @@ __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const I
     }
 }
 
-template <typename T, int V, int LX, int NS>
+template <typename T, int V, int LX, int NS, bool UNI>
 __global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g, const WorkItem *__restrict__ items,
                                                          int k_begin, int k_end) {
     extern __shared__ uint4 sj_smem[];
     const WorkItem it = items[blockIdx.x];
     const int kb = max(it.kb, k_begin), ke = min(it.ke, k_end);
     if (kb >= ke) return;
-    if (src_in_chunk(p, kb, ke)) e_interior_stg_body<T, V, LX, NS, true>(p, g, it, kb, ke, sj_smem);
-    else e_interior_stg_body<T, V, LX, NS, false>(p, g, it, kb, ke, sj_smem);
+    if (src_in_chunk(p, kb, ke)) e_interior_stg_body<T, V, LX, NS, true, UNI>(p, g, it, kb, ke, sj_smem);
+    else e_interior_stg_body<T, V, LX, NS, false, UNI>(p, g, it, kb, ke, sj_smem);
 }
 
 // flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
@@ -597,7 +633,7 @@ static __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, c
     __syncthreads();
     const int nx = max(i_hi - i_lo, 0), ny = max(j_hi - j_lo, 0), nz = max(ke - kb, 0);
     const int ref = (nx && ny && nz) ? m0[(long long)(kb - kz0 + 1) * plane + (long long)j_lo * pitch + i_lo] : 0;
-    int gen = (ref >= first_disp);
+    int gen = 0;
     for (int t = threadIdx.x; t < nx * ny * nz && !gen; t += blockDim.x) {
         const int i = i_lo + t % nx, j = j_lo + (t / nx) % ny, k = kb + t / (nx * ny);
         const long long x = (long long)(k - kz0 + 1) * plane + (long long)j * pitch + i;
@@ -605,7 +641,9 @@ static __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, c
     }
     if (gen) s_gen = 1;
     __syncthreads();
-    if (threadIdx.x == 0) flags[((long long)kc * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s_gen ? 1u : ((unsigned)ref << 8);
+    // bit 0: mixed materials; bit 1: one material, with poles; bits 8..: that material
+    if (threadIdx.x == 0) flags[((long long)kc * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] =
+        s_gen ? 1u : (((unsigned)ref << 8) | (ref >= first_disp ? 2u : 0u));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -628,18 +666,20 @@ __device__ __forceinline__ T pml_step_db(T fold, T curl, T sk, T ik, T su, T iu,
 
 // MODE 0: general; 1: tangential component of a face (sigma sf/isf, no D array); 2: normal
 // component of a face (sigma sw on W, D stored, no sigma on D).
-template <typename T, int V, int NS, int MODE, bool SRC>
+// UNI: block-uniform material (chi_u, eps_u, cfu hold its table entries), also when it has poles
+template <typename T, int V, int NS, int MODE, bool SRC, bool UNI>
 __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, NS> &pol, int c, int v, T &e, T &d, T curl, T sk,
-                                           T ik, T su, T iu, T sw, T &U, int m, T chi_u, T eps_u, T S0, T S1, T J) {
-    const T chi = NS > 0 ? p.mt_chi[m] : chi_u;
+                                           T ik, T su, T iu, T sw, T &U, int m, T chi_u, T eps_u, T S0, T S1, T J,
+                                           const T (&cfu)[NS > 0 ? NS : 1][3]) {
+    const T chi = (NS > 0 && !UNI) ? p.mt_chi[m] : chi_u;
     const T pold = NS > 0 ? pol.sum_cur(c, v) : T(0);
     T pnew = T(0);
     if (MODE == 1) {
-        const T eps = NS > 0 ? p.mt_eps[m] : eps_u;
+        const T eps = (NS > 0 && !UNI) ? p.mt_eps[m] : eps_u;
         const T dold = SRC ? (eps * e + pold) + S0 : (eps * e + pold);
         T dnew = ((T(1) - sk) * dold - curl) * ik;
         if (SRC) dnew -= J;
-        if (NS > 0) pol.advance(p, c, v, m, e, pnew);          // W == E here
+        if (NS > 0) { if (UNI) pol.advance_u(c, v, e, pnew, cfu); else pol.advance(p, c, v, m, e, pnew); }   // W == E here
         e = SRC ? chi * ((dnew - pnew) - S1) : chi * (dnew - pnew);
         return;
     }
@@ -649,7 +689,7 @@ __device__ __forceinline__ void pml_e_elem(const KParams<T> &p, PolState<T, V, N
     d = dnew;
     // W^n = chi (D^n - sum P^n - S^n) drives the poles (meep update_pols runs on W)
     const T wold = SRC ? chi * ((dold - pold) - S0) : chi * (dold - pold);
-    if (NS > 0) pol.advance(p, c, v, m, wold, pnew);
+    if (NS > 0) { if (UNI) pol.advance_u(c, v, wold, pnew, cfu); else pol.advance(p, c, v, m, wold, pnew); }
     const T wnew = SRC ? chi * ((dnew - pnew) - S1) : chi * (dnew - pnew);
     e = (MODE == 2 || sw != T(0)) ? e + (T(1) + sw) * wnew - (T(1) - sw) * wold : wnew;
 }
@@ -788,10 +828,11 @@ __global__ void __launch_bounds__(256, (V * sizeof(T) == 8) ? (FACE ? 4 : 3) : (
     else h_pml_body<T, V, LX, 3>(p, b, it, k_lo, k_hi);
 }
 
-template <typename T, int V, int LX, int NS, int PD, bool SRC>
+template <typename T, int V, int LX, int NS, int PD, bool SRC, bool UNI>
 __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> &b, const WorkItem &it, int k_lo, int k_hi,
                                            T chi_u, T eps_u) {
-    constexpr bool GEN = NS > 0;
+    constexpr bool GEN = NS > 0 && !UNI;          // per-cell material bytes and table look-ups
+    constexpr bool POL = NS > 0;
     constexpr int RW = 32 / LX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane % LX, ly = lane / LX;
@@ -841,6 +882,11 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
 #pragma unroll
     for (int v = 0; v < V; ++v) mx[v] = my[v] = mz[v] = 0;
     PolState<T, V, NS> pol;
+    T cfu[NS > 0 ? NS : 1][3];
+#pragma unroll
+    for (int s_ = 0; s_ < (NS > 0 ? NS : 1); ++s_)
+#pragma unroll
+        for (int q_ = 0; q_ < 3; ++q_) cfu[s_][q_] = (UNI && POL) ? p.mt_coef[((long long)it.mat * SJ_MAX_POLES + s_) * 3 + q_] : T(0);
     if (act) { hxm.load(pH - plane); hym.load((pH + fcs) - plane); } else { hxm.zero(); hym.zero(); }
     if (GEN && act) { load_bytes<V>(pm, mx); load_bytes<V>((pm + mcs), my); load_bytes<V>((pm + mcs2), mz); }
     for (int k = kb; k < ke; ++k) {
@@ -855,7 +901,7 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (GEN) {
                 pol.load(p, parity, xg, mx, my, mz);
                 load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
-            }
+            } else if (POL) pol.load_all(p, parity, xg);
         } else { hx0.zero(); hy0.zero(); hz0.zero(); }
         if (rowm) { hzj.load((pH + fcs2) - pitch); hxj.load(pH - pitch); } else { hzj.zero(); hxj.zero(); }
         T hz_e = T(0), hy_e = T(0);       // tile-edge neighbours, issued with the plane's other loads
@@ -880,23 +926,23 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
                 if (i <= p.n[0] - 1 && jin && kin) {     // Ex: k-dir y, u-dir z, w-dir x
                     const T curl = C * (((hzj.v[v] - hz0.v[v]) + hy0.v[v]) - hym.v[v]);
                     if (SRC && smask) source_parts(p, smask, 0, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 1) pml_e_elem<T, V, NS, 2, SRC>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1, SRC>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), ux.v[v], mx[v], chi_u, eps_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC, UNI>(p, pol, 0, v, ex.v[v], dx.v[v], curl, syi, iyi, szi, izi, sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J, cfu);
+                    else if (PD == 1) pml_e_elem<T, V, NS, 2, SRC, UNI>(p, pol, 0, v, ex.v[v], dx.v[v], curl, T(0), T(1), T(0), T(1), sxh[v], ux.v[v], mx[v], chi_u, eps_u, S0, S1, J, cfu);
+                    else pml_e_elem<T, V, NS, 1, SRC, UNI>(p, pol, 0, v, ex.v[v], dx.v[v], curl, sf, isf, T(0), T(1), T(0), ux.v[v], mx[v], chi_u, eps_u, S0, S1, J, cfu);
                 }
                 if (j <= p.n[1] - 1 && iin && kin) {     // Ey: k-dir z, u-dir x, w-dir y
                     const T curl = C * (((hxm.v[v] - hx0.v[v]) + hz0.v[v]) - hzi);
                     if (SRC && smask) source_parts(p, smask, 1, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 2) pml_e_elem<T, V, NS, 2, SRC>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1, SRC>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), uy.v[v], my[v], chi_u, eps_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC, UNI>(p, pol, 1, v, ey.v[v], dy.v[v], curl, szi, izi, sxi[v], ixi[v], syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J, cfu);
+                    else if (PD == 2) pml_e_elem<T, V, NS, 2, SRC, UNI>(p, pol, 1, v, ey.v[v], dy.v[v], curl, T(0), T(1), T(0), T(1), syh, uy.v[v], my[v], chi_u, eps_u, S0, S1, J, cfu);
+                    else pml_e_elem<T, V, NS, 1, SRC, UNI>(p, pol, 1, v, ey.v[v], dy.v[v], curl, sf, isf, T(0), T(1), T(0), uy.v[v], my[v], chi_u, eps_u, S0, S1, J, cfu);
                 }
                 if (k <= p.n[2] - 1 && iin && jin) {     // Ez: k-dir x, u-dir y, w-dir z
                     const T curl = C * (((hyi - hy0.v[v]) + hx0.v[v]) - hxj.v[v]);
                     if (SRC && smask) source_parts(p, smask, 2, i, j, k, set, step, S0, S1, J);
-                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
-                    else if (PD == 3) pml_e_elem<T, V, NS, 2, SRC>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
-                    else pml_e_elem<T, V, NS, 1, SRC>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), uz.v[v], mz[v], chi_u, eps_u, S0, S1, J);
+                    if (PD == 0) pml_e_elem<T, V, NS, 0, SRC, UNI>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sxi[v], ixi[v], syi, iyi, szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J, cfu);
+                    else if (PD == 3) pml_e_elem<T, V, NS, 2, SRC, UNI>(p, pol, 2, v, ez.v[v], dz.v[v], curl, T(0), T(1), T(0), T(1), szh, uz.v[v], mz[v], chi_u, eps_u, S0, S1, J, cfu);
+                    else pml_e_elem<T, V, NS, 1, SRC, UNI>(p, pol, 2, v, ez.v[v], dz.v[v], curl, sf, isf, T(0), T(1), T(0), uz.v[v], mz[v], chi_u, eps_u, S0, S1, J, cfu);
                 }
             }
             ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
@@ -904,8 +950,8 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0 || PD == 2) dy.store((pD + bcs));
             if (PD == 0 || PD == 3) dz.store((pD + bcs2));
             if (PD == 0) { ux.store(pU); uy.store((pU + bcs)); uz.store((pU + bcs2)); }
+            if (POL) pol.store(p, parity, xg);
             if (GEN) {
-                pol.store(p, parity, xg);
 #pragma unroll
                 for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; }
             }
@@ -917,23 +963,23 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
     }
 }
 
-template <typename T, int V, int LX, int NS, bool FACE>
+template <typename T, int V, int LX, int NS, bool FACE, bool UNI>
 __global__ void __launch_bounds__(256, (V * sizeof(T) == 8) ? (NS == 0 ? (FACE ? 4 : 3) : 2) : (NS == 0 ? (FACE ? SJ_EFACE_BLOCKS : 2) : 1)) e_pml_tile(KParams<T> p, PmlBoxSet<T> bs, const WorkItem *__restrict__ items,
                                                                    int k_lo, int k_hi) {
     const WorkItem it = items[blockIdx.x];
     const PmlBox<T> &b = bs.b[it.box];
-    const T chi_u = NS > 0 ? T(0) : p.mt_chi[it.mat], eps_u = NS > 0 ? T(0) : p.mt_eps[it.mat];
+    const T chi_u = UNI ? p.mt_chi[it.mat] : T(0), eps_u = UNI ? p.mt_eps[it.mat] : T(0);
     if (src_in_chunk(p, max(it.kb, k_lo), min(it.ke, k_hi))) {
-        if (!FACE) e_pml_body<T, V, LX, NS, 0, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-        else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-        else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-        else e_pml_body<T, V, LX, NS, 3, true>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        if (!FACE) e_pml_body<T, V, LX, NS, 0, true, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1, true, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2, true, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+        else e_pml_body<T, V, LX, NS, 3, true, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
         return;
     }
-    if (!FACE) e_pml_body<T, V, LX, NS, 0, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-    else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-    else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
-    else e_pml_body<T, V, LX, NS, 3, false>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    if (!FACE) e_pml_body<T, V, LX, NS, 0, false, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else if (it.kind == 1) e_pml_body<T, V, LX, NS, 1, false, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else if (it.kind == 2) e_pml_body<T, V, LX, NS, 2, false, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
+    else e_pml_body<T, V, LX, NS, 3, false, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
 }
 
 // material flags of the PML work items (one block per item)
@@ -947,7 +993,7 @@ static __global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, c
     __syncthreads();
     const int nx = max(i_hi - it.i0, 0), ny = max(j_hi - it.j0, 0), nz = max(it.ke - it.kb, 0);
     const int ref = (nx && ny && nz) ? m0[(long long)(it.kb - kz0 + 1) * plane + (long long)it.j0 * pitch + it.i0] : 0;
-    int gen = (ref >= first_disp);
+    int gen = 0;
     for (int t = threadIdx.x; t < nx * ny * nz && !gen; t += blockDim.x) {
         const int i = it.i0 + t % nx, j = it.j0 + (t / nx) % ny, k = it.kb + t / (nx * ny);
         const long long x = (long long)(k - kz0 + 1) * plane + (long long)j * pitch + i;
@@ -955,7 +1001,7 @@ static __global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, c
     }
     if (gen) s_gen = 1;
     __syncthreads();
-    if (threadIdx.x == 0) flags[blockIdx.x] = s_gen ? 1u : ((unsigned)ref << 8);
+    if (threadIdx.x == 0) flags[blockIdx.x] = s_gen ? 1u : (((unsigned)ref << 8) | (ref >= first_disp ? 2u : 0u));
 }
 
 // ------------------------------------------------------------------------------------------

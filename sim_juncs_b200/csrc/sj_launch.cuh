@@ -81,18 +81,20 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
         s->launches++; return;
     }
     if (s->il_int[0].n) { TR(s, "e_interior<LX, 0>", fan_stream(s, 0), e_interior<T, V, LX, 0><<<s->il_int[0].n, 256, 0, st__>>>(p, g, s->il_int[0].dev, k_begin, k_end)); s->launches++; }
-    if (s->il_int[1].n) {
-        const int n = s->il_int[1].n; const WorkItem *d = s->il_int[1].dev;
-        static const bool stg = getenv("SJ_NO_STAGE") == NULL;
+    static const bool stg = getenv("SJ_NO_STAGE") == NULL;
+    for (int cls = 1; cls < 4; ++cls) {       // 1: mixed tiles; 2 / 3: one material with exactly 1 / 2 poles
+        if (!s->il_int[cls].n) continue;
+        const int n = s->il_int[cls].n; const WorkItem *d = s->il_int[cls].dev;
         if (stg && s->n_slots <= 2) {
-            // cp.async-staged variant: 2 stages x (8 + 6 NS) slots x 256 threads x 16 B of dynamic shared memory
-            static bool attr_done[2][3] = {{false, false, false}, {false, false, false}};
-            const int ns = std::max(s->n_slots, 1);
+            // cp.async-staged variants: 2 stages x (8 + 6 NS) slots x 256 threads x 16 B of dynamic shared memory
+            const int ns = cls == 1 ? std::max(s->n_slots, 1) : cls - 1;
             const size_t smem = (size_t)2 * (8 + 6 * ns) * 256 * 16;
-            auto k1 = e_interior_stg<T, V, LX, 1>; auto k2 = e_interior_stg<T, V, LX, 2>;
-            if (ns == 1) { cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); TR(s, "k1", fan_stream(s, 0), k1<<<n, 256, smem, st__>>>(p, g, d, k_begin, k_end)); }
-            else { cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); TR(s, "k2", fan_stream(s, 0), k2<<<n, 256, smem, st__>>>(p, g, d, k_begin, k_end)); }
-            (void)attr_done;
+            auto k1 = e_interior_stg<T, V, LX, 1, false>; auto k2 = e_interior_stg<T, V, LX, 2, false>;
+            auto u1 = e_interior_stg<T, V, LX, 1, true>; auto u2 = e_interior_stg<T, V, LX, 2, true>;
+            auto kf = cls == 1 ? (ns == 1 ? k1 : k2) : (ns == 1 ? u1 : u2);
+            cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            TR(s, cls == 1 ? "e_interior_stg" : (ns == 1 ? "e_interior_stg<uni 1>" : "e_interior_stg<uni 2>"), fan_stream(s, 0),
+               kf<<<n, 256, smem, st__>>>(p, g, d, k_begin, k_end));
         }
         else if (s->n_slots <= 1) TR(s, "e_interior<LX, 1>", fan_stream(s, 0), e_interior<T, V, LX, 1><<<n, 256, 0, st__>>>(p, g, d, k_begin, k_end));
         else if (s->n_slots == 2) TR(s, "e_interior<LX, 2>", fan_stream(s, 0), e_interior<T, V, LX, 2><<<n, 256, 0, st__>>>(p, g, d, k_begin, k_end));
@@ -102,15 +104,18 @@ static void launch_interior(sj_sim *s, const KParams<T> &p, int which, int k_beg
 }
 
 template <typename T, int V, int LX, bool FACE>
-static void launch_e_pml(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, const ItemList (&L)[2], int k_begin, int k_end,
+static void launch_e_pml(sj_sim *s, const KParams<T> &p, const PmlBoxSet<T> &bs, const ItemList (&L)[4], int k_begin, int k_end,
                          cudaStream_t st) {
-    if (L[0].n) { TR(s, "e_pml_tile<LX, 0, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 0, FACE><<<L[0].n, 256, 0, st__>>>(p, bs, L[0].dev, k_begin, k_end)); s->launches++; }
+    if (L[0].n) { TR(s, "e_pml_tile<LX, 0, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 0, FACE, true><<<L[0].n, 256, 0, st__>>>(p, bs, L[0].dev, k_begin, k_end)); s->launches++; }
     if (L[1].n) {
-        if (s->n_slots <= 1) TR(s, "e_pml_tile<LX, 1, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 1, FACE><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
-        else if (s->n_slots == 2) TR(s, "e_pml_tile<LX, 2, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 2, FACE><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
-        else TR(s, "e_pml_tile<LX, 4, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 4, FACE><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
+        if (s->n_slots <= 1) TR(s, "e_pml_tile<LX, 1, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 1, FACE, false><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
+        else if (s->n_slots == 2) TR(s, "e_pml_tile<LX, 2, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 2, FACE, false><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
+        else TR(s, "e_pml_tile<LX, 4, FACE>", fan_stream(s), e_pml_tile<T, V, LX, 4, FACE, false><<<L[1].n, 256, 0, st__>>>(p, bs, L[1].dev, k_begin, k_end));
         s->launches++;
     }
+    // one material with exactly 1 / 2 poles: coefficients in registers, no material bytes
+    if (L[2].n) { TR(s, "e_pml_tile<LX, 1, FACE, uni>", fan_stream(s), e_pml_tile<T, V, LX, 1, FACE, true><<<L[2].n, 256, 0, st__>>>(p, bs, L[2].dev, k_begin, k_end)); s->launches++; }
+    if (L[3].n) { TR(s, "e_pml_tile<LX, 2, FACE, uni>", fan_stream(s), e_pml_tile<T, V, LX, 2, FACE, true><<<L[3].n, 256, 0, st__>>>(p, bs, L[3].dev, k_begin, k_end)); s->launches++; }
 }
 
 template <typename T, int V, int LX>
