@@ -58,12 +58,16 @@ typedef struct {
     int region;
     double sigma;         /* sigma/thickness, disp.cpp:541 */
     double *P[2][3], *Pp[2][3]; /* [set][comp] current and previous polarisation */
+    double *sigarr[3];    /* per-point sigma (orc_add_sus_pointwise) instead of sigma * region bit, or NULL */
 } orc_sus;
 
 typedef struct {
     int comp;              /* 0..2 = Ex,Ey,Ez */
     int integrated;        /* meep src_time::is_integrated */
-    int kind;              /* 0: gaussian_src_time_phase (disp.hpp:112); 1: meep::continuous_src_time (disp.cpp:618) */
+    int kind;              /* 0: gaussian_src_time_phase (disp.hpp:112); 1: meep::continuous_src_time (disp.cpp:618);
+                              2: waveform supplied by the caller (the reference's own src_time::dipole through oracle/shim) */
+    void (*fn)(void *ctx, double time, double *out2);
+    void *ctx;
     double t_start, t_end, slowness;   /* kind 1 */
     double omega, width, phi, peak, cutoff;
     double _Complex amp_t; /* 1/(-i omega), disp.cpp:387 */
@@ -169,6 +173,7 @@ void orc_destroy(orc_sim *s) {
     for (int u = 0; u < s->n_sus; ++u)
         for (int q = 0; q < 2; ++q)
             for (int c = 0; c < 3; ++c) { free(s->sus[u].P[q][c]); free(s->sus[u].Pp[q][c]); }
+    for (int u = 0; u < s->n_sus; ++u) for (int c = 0; c < 3; ++c) free(s->sus[u].sigarr[c]);
     for (int i = 0; i < s->n_src; ++i) for (int d = 0; d < 3; ++d) free(s->src[i].w[d]);
     free(s->mon_xyz); free(s->mon_idx); free(s->mon_w); free(s->series);
     free(s);
@@ -216,6 +221,7 @@ int orc_set_regions(orc_sim *s, double ambient_eps, int n_regions, const double 
 
 /* ---- source waveform: gaussian_src_time_phase (src/disp.cpp:378-400) ---- */
 static double _Complex src_dipole(const orc_src *g, double time) {
+    if (g->kind == 2) { double o[2]; g->fn(g->ctx, time, o); return o[0] + I * o[1]; }
     if (g->kind == 1) {
         /* meep continuous_src_time::dipole [meep-recall, v1.2x sources.cpp]: zero outside [start, end] (float
          * compare), exp(-i w t) / (-i w), times tanh ramps (1+tanh(ts))(1+tanh(te))/4 when width != 0 */
@@ -334,38 +340,88 @@ int orc_add_cw_source(orc_sim *s, int comp, const double *lo, const double *hi, 
 
 /* Monitors: meep fields::get_field -> grid_volume::interpolate (linear in each direction
  * between the two bracketing Yee points of the component). */
+/* ---- entry points for the meep-API shim (oracle/shim/): eps_inf, sigma and the source waveform come from the
+ * caller point by point -- there they are the reference's own cgs_material_function / src_time virtuals ---- */
+int orc_set_eps_pointwise(orc_sim *s, const double *ex, const double *ey, const double *ez) {
+    const double *e[3] = {ex, ey, ez};
+    for (int c = 0; c < 3; ++c) {
+        free(s->maskc[c]);
+        s->maskc[c] = (uint8_t *)calloc(s->ntot, 1);
+        for (size_t i = 0; i < s->ntot; ++i) s->chi1inv[c][i] = 1 / e[c][i];
+    }
+    return 0;
+}
+int orc_add_sus_pointwise(orc_sim *s, double omega0, double gamma, int drude, const double *sx, const double *sy,
+                          const double *sz) {
+    const double *sg[3] = {sx, sy, sz};
+    if (s->n_sus >= ORC_MAX_SUS) return -2;
+    orc_sus *u = &s->sus[s->n_sus++];
+    u->omega0 = omega0; u->gamma = gamma; u->sigma = 0; u->drude = drude; u->region = 0;
+    for (int c = 0; c < 3; ++c) {
+        u->sigarr[c] = zalloc(s->ntot);
+        memcpy(u->sigarr[c], sg[c], sizeof(double) * s->ntot);
+        for (int q = 0; q < s->nsets; ++q) { u->P[q][c] = zalloc(s->ntot); u->Pp[q][c] = zalloc(s->ntot); }
+    }
+    s->have_disp = 1;
+    return 0;
+}
+int orc_add_callback_source(orc_sim *s, int comp, const double *lo, const double *hi, double amp_re, double amp_im,
+                            int integrated, void (*fn)(void *, double, double *), void *ctx) {
+    if (s->n_src >= ORC_MAX_SRC || comp < 0 || comp > 2) return -1;
+    orc_src *g = &s->src[s->n_src];
+    memset(g, 0, sizeof(*g));
+    g->comp = comp; g->integrated = integrated; g->kind = 2; g->fn = fn; g->ctx = ctx;
+    return place_source(s, g, comp, lo, hi, amp_re + I * amp_im);
+}
+
+/* meep fields::get_field(c, loc): (tri)linear interpolation from the <= 8 surrounding points of component c */
+static void interp_weights(const orc_sim *s, int comp, const double *xyz, size_t *idx8, double *w8) {
+    int mid[3]; double dv[3];
+    for (int d = 0; d < 3; ++d) {
+        int sh = (d == comp) ? 1 : 0;
+        double pc = xyz[d];
+        double p = (pc - sh * (0.5 * s->inva)) * s->a;
+        mid[d] = ((int)floor(p)) * 2 + 1 + sh;
+        double midv = mid[d] * (0.5 * s->inva);
+        dv[d] = (pc - midv) * (2 * s->a);
+    }
+    for (int q = 0; q < 8; ++q) {
+        double w = 1.0; size_t idx = 0; int ok = 1;
+        for (int d = 0; d < 3; ++d) {
+            int sh = (d == comp) ? 1 : 0;
+            int hi = (q >> d) & 1;
+            int h = mid[d] + (hi ? 1 : -1);
+            w *= hi ? 0.5 * (1.0 + dv[d]) : 0.5 * (1.0 - dv[d]);
+            int i = (h - sh) / 2;
+            if (h - sh < 0 || i > s->n[d]) ok = 0; else idx += (size_t)i * s->st[d];
+        }
+        if (w < 0.0) w = 0.0;
+        if (!ok) { w = 0.0; idx = 0; }
+        idx8[q] = idx; w8[q] = w;
+    }
+}
+
 int orc_add_monitors(orc_sim *s, int comp, int n, const double *xyz) {
     s->mon_comp = comp; s->n_mon = n;
     s->mon_xyz = (double *)malloc(sizeof(double) * 3 * n);
     memcpy(s->mon_xyz, xyz, sizeof(double) * 3 * n);
     s->mon_idx = malloc(sizeof(size_t[8]) * n);
     s->mon_w = malloc(sizeof(double[8]) * n);
-    for (int m = 0; m < n; ++m) {
-        int mid[3]; double dv[3];
-        for (int d = 0; d < 3; ++d) {
-            int sh = (d == comp) ? 1 : 0;
-            double pc = xyz[3 * m + d];
-            double p = (pc - sh * (0.5 * s->inva)) * s->a;
-            mid[d] = ((int)floor(p)) * 2 + 1 + sh;
-            double midv = mid[d] * (0.5 * s->inva);
-            dv[d] = (pc - midv) * (2 * s->a);
-        }
-        for (int q = 0; q < 8; ++q) {
-            double w = 1.0; size_t idx = 0; int ok = 1;
-            for (int d = 0; d < 3; ++d) {
-                int sh = (d == comp) ? 1 : 0;
-                int hi = (q >> d) & 1;
-                int h = mid[d] + (hi ? 1 : -1);
-                w *= hi ? 0.5 * (1.0 + dv[d]) : 0.5 * (1.0 - dv[d]);
-                int i = (h - sh) / 2;
-                if (h - sh < 0 || i > s->n[d]) ok = 0; else idx += (size_t)i * s->st[d];
-            }
-            if (w < 0.0) w = 0.0;
-            if (!ok) { w = 0.0; idx = 0; }
-            s->mon_idx[m][q] = idx; s->mon_w[m][q] = w;
-        }
-    }
+    for (int m = 0; m < n; ++m) interp_weights(s, comp, xyz + 3 * m, s->mon_idx[m], s->mon_w[m]);
     return 0;
+}
+
+/* one get_field call, same summation order as sample_monitors */
+void orc_get_field_at(const orc_sim *s, int comp, const double *xyz, double *out2) {
+    size_t idx[8]; double w[8];
+    interp_weights(s, comp, xyz, idx, w);
+    for (int q = 0; q < 2; ++q) {
+        double res = 0.0;
+        if (q < s->nsets)
+            for (int p = 0; p < 8; ++p)
+                if (w[p] != 0) res += w[p] * s->E[q][comp][idx[p]];
+        out2[q] = res;
+    }
 }
 
 static void sample_monitors(orc_sim *s) {
@@ -534,7 +590,7 @@ static void update_e(orc_sim *s) {
                     for (int j = lo[1]; j <= hi[1]; ++j)
                         for (int i = lo[0]; i <= hi[0]; ++i) {
                             size_t x = (size_t)k * s->st[2] + (size_t)j * s->st[1] + i;
-                            double sg = su->sigma * ((mk[x] >> su->region) & 1);
+                            double sg = su->sigarr[c] ? su->sigarr[c][x] : su->sigma * ((mk[x] >> su->region) & 1);
                             double pcur = p[x];
                             p[x] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[x] + omega0dtsqr * (sg * w[x]));
                             pp[x] = pcur;

@@ -26,7 +26,7 @@ Gaussian_source("Ex", 0.75, 1.0, 1.5, 0.0, cutoff=4, Box([0,0,1], [length,length
 
 monitors(locations = [vec(x, mid, top-0.1) for x in range(1,11,0.2)])
 
-//Au: A.D. Rakic et al., Applied Optics 37, 5271 (1998); Drude term + first Lorentz term
+//Au: A.D. Rakic et al., Applied Optics 37, 5271 (1998), Drude term + first Lorentz term
 Composite(eps = 1.0, susceptibilities = [[1e-10, 0.04274738474121455, 4.0314052191361974e21, "drude"],[0.3347200880680007, 0.19437961740816426, 11.362935694585572, "lorentz"]], [
     Box([0, 0,    top], [length, left,   bot]),
     Box([0, rght, top], [length, length, bot])

@@ -1,0 +1,69 @@
+"""Golden monitor series from the REFERENCE's own driver.
+
+Runs only in the build container (needs /root/reference): oracle/_ref/sim_geom_ref is the reference's unmodified
+main.cpp + disp.cpp + cgs*.cpp + data_utils.cpp compiled in place against oracle/shim/ (meep API slice over
+oracle/fdtd_oracle.c, HDF5 recorder) -- see oracle/shim/meep.hpp.  For each case below the binary is launched with the
+reference's own command line and what its save_field_times handed to HDF5 is stored as
+  tests/golden/ref_<name>.npz   time (n_saves x n_monitors complex), frequency, locations, time_bounds, n_time_points,
+                                sources, cgs_param names / values, the launch (conf, argv), sha256 of eps / sigma dumps
+The -m gpu tests replay the same launch through BoundGeom on the CUDA engine and compare (tests/test_gpu_parity.py).
+Usage: python scripts/make_ref_golden.py [name ...]
+"""
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers  # noqa: E402
+
+# name -> (conf, extra argv)
+CASES = {
+    "run_slabs": ("scenes/tests/run.conf", []),
+    "cw_slab": ("scenes/tests/cw_slab.conf", []),
+    "graphene_res2p5": ("scenes/tests/graphene_short.conf", ["--grid-res", "2.5"]),
+    "graphene_short": ("scenes/tests/graphene_short.conf", []),
+    "run_slabs_smooth1": ("scenes/tests/run_smooth.conf", []),
+}
+
+
+def main(names):
+    assert helpers.have_ref_sim_geom(), "needs /root/reference"
+    for name in names:
+        conf, extra = CASES[name]
+        with tempfile.TemporaryDirectory() as tmp:
+            entries, blob, out = helpers.run_ref_sim_geom(conf, tmp, extra)
+            d = {"conf": conf, "argv": np.array(extra, dtype=str)}
+            d["time"] = helpers.ref_series(entries, blob)
+            freq = [helpers.ref_dataset(entries, blob, e["path"]) for e in entries
+                    if e["what"] == "dataset" and e["path"].endswith("/frequency")]
+            d["frequency"] = np.stack([f[:, 0] + 1j * f[:, 1] for f in freq], axis=1)
+            d["locations"] = np.concatenate([helpers.ref_dataset(entries, blob, e["path"]) for e in entries
+                                             if e["what"] == "dataset" and e["path"].endswith("/locations")])
+            for k in ("time_bounds", "n_time_points", "n_clusters", "sources"):
+                d[k] = helpers.ref_dataset(entries, blob, "/info/" + k)
+            cg = [e["path"] for e in entries if e["what"] == "dataset" and e["path"].startswith("/info/cgs_params/")]
+            d["cgs_names"] = np.array([p.rsplit("/", 1)[1] for p in cg], dtype=str)
+            d["cgs_values"] = np.array([helpers.ref_dataset(entries, blob, p)[0] for p in cg])
+            for f in sorted(os.listdir(tmp)):
+                if f.endswith(".f64"):
+                    with open(os.path.join(tmp, f), "rb") as fp:
+                        d["sha256_" + f[:-4]] = np.array(hashlib.sha256(fp.read()).hexdigest())
+            # small grids: keep eps itself (the smooth_n > 0 fixture is compared value by value)
+            eps = [np.fromfile(os.path.join(tmp, "eps_%s.f64" % c)) for c in "xyz"]
+            if eps[0].size <= 30 ** 3:
+                d["eps"] = np.stack(eps)
+                sig = sorted(f for f in os.listdir(tmp) if f.startswith("sigma_"))
+                if sig:
+                    d["sigma"] = np.stack([np.fromfile(os.path.join(tmp, f)) for f in sig])
+            path = os.path.join(ROOT, "tests", "golden", "ref_%s.npz" % name)
+            np.savez_compressed(path, **d)
+            print(name, d["time"].shape, "max |Ex| %.3e" % np.abs(d["time"]).max(), os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or [n for n in CASES if n != "run_slabs_smooth1"])

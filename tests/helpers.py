@@ -111,3 +111,60 @@ def early_pulse(scene, width_fs=0.08):
     src = scene.sources[0]
     src.start_time, src.width, src.end_time = 0.0, width_fs, 12.0 * width_fs
     return scene
+
+
+# ---- the reference's own driver (main.cpp + disp.cpp, compiled in place over oracle/shim) -------------------
+REF_SIM_GEOM = os.path.join(ROOT, "oracle", "_ref", "sim_geom_ref")
+
+
+def have_ref_sim_geom():
+    """oracle/_ref/sim_geom_ref exists, or can be built because /root/reference is mounted."""
+    if not os.path.exists(REF_SIM_GEOM) and os.path.isdir("/root/reference/src"):
+        import subprocess
+        subprocess.call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
+    return os.path.exists(REF_SIM_GEOM)
+
+
+def run_ref_sim_geom(conf, out_dir, extra=()):
+    """Run the reference binary from the repository root; returns (entries, blob, stdout).  entries: the recorded
+    HDF5 objects in creation order (oracle/shim/H5Cpp.h); dumps of eps / sigma land in out_dir."""
+    import json
+    import subprocess
+    os.makedirs(out_dir, exist_ok=True)
+    env = dict(os.environ, SJ_SHIM_DUMP=out_dir)
+    res = subprocess.run([REF_SIM_GEOM, "--conf-file", conf, "--out-dir", out_dir] + list(extra), cwd=ROOT, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
+    if res.returncode != 0:
+        raise RuntimeError("sim_geom_ref failed (%d):\n%s" % (res.returncode, res.stdout.decode()[-2000:]))
+    with open(os.path.join(out_dir, "field_samples.h5.manifest.json")) as fp:
+        entries = json.load(fp)["entries"]
+    with open(os.path.join(out_dir, "field_samples.h5.manifest.bin"), "rb") as fp:
+        blob = fp.read()
+    return entries, blob, res.stdout.decode()
+
+
+def ref_dataset(entries, blob, path):
+    """One recorded dataset as a numpy array: f64 / u64 scalars as they are, compounds as (n, n_members) float64."""
+    for e in entries:
+        if e["what"] == "dataset" and e["path"] == path:
+            raw = blob[e["offset"]:e["offset"] + e["nbytes"]]
+            t = e["type"]
+            if t["kind"] == "f64":
+                return np.frombuffer(raw, dtype="<f8").copy()
+            if t["kind"] == "u64":
+                return np.frombuffer(raw, dtype="<u8").copy()
+            dt = np.dtype({"names": [m["name"] for m in t["members"]], "formats": ["<f8"] * len(t["members"]),
+                           "offsets": [m["offset"] for m in t["members"]], "itemsize": t["size"]})
+            rec = np.frombuffer(raw, dtype=dt)
+            return np.stack([rec[m["name"]] for m in t["members"]], axis=1) if len(rec) else np.zeros((0, len(t["members"])))
+    raise KeyError(path)
+
+
+def ref_series(entries, blob):
+    """[n_saves][n_monitors] complex from the recorded cluster_*/point_*/time datasets, in monitor order."""
+    cols = []
+    for e in entries:
+        if e["what"] == "dataset" and e["path"].endswith("/time"):
+            a = ref_dataset(entries, blob, e["path"])
+            cols.append(a[:, 0] + 1j * a[:, 1])
+    return np.stack(cols, axis=1) if cols else np.zeros((0, 0), dtype=complex)
