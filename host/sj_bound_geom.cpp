@@ -1,5 +1,6 @@
 // sj_bound_geom.cpp -- `bound_geom` on the C ABI.  Construction order, unit conversions and the run
 // loop cadence are those of reference src/disp.cpp:482-749; every meep call is replaced by an sj_* call.
+#include <algorithm>
 #include "sj_host.hpp"
 #include "sj_hdf5.hpp"
 
@@ -341,7 +342,8 @@ int sj_bound_geom::save_field_times(const char *fname_prefix) {
                 if (field_times[i].size() < 2) break;
                 strcpy(pname, "point_"); write_number(pname + 6, sizeof pname - 6, (int)i, npd);
                 const std::string base = std::string(cname) + "/" + pname;
-                h.dataset(base + "/time", t_cplx, field_times[i].data(), field_times[i].size(), 16);
+                // sic: t_space holds n_t_pts / save_span samples (disp.cpp:771) although ceil(n_t_pts / save_span) were pushed
+                h.dataset(base + "/time", t_cplx, field_times[i].data(), std::min(field_times[i].size(), (size_t)(n_t_pts / save_span)), 16);
                 h.dataset(base + "/frequency", t_cplx, &spec[(size_t)i * n_freq * 2], n_freq, 16);
             }
         }
@@ -386,7 +388,7 @@ int sj_bound_geom::save_field_times(const char *fname_prefix) {
         for (; i < max_i; ++i) {
             if (field_times[i].size() < 2) { printf("Error: monitor location %zu has insufficient points\n", i); break; }
             strcpy(pname, "point_"); write_number(pname + 6, sizeof pname - 6, (int)i, npd);
-            w.add(std::string(cname) + "/" + pname + "/time", (const double *)field_times[i].data(), field_times[i].size(), 2);
+            w.add(std::string(cname) + "/" + pname + "/time", (const double *)field_times[i].data(), std::min(field_times[i].size(), (size_t)(n_t_pts / save_span)), 2);
         }
     }
     w.close();

@@ -134,3 +134,132 @@ void csg_raster_component(const csg_node *nodes, const int32_t *roots, int n_roo
                 out[((size_t)k * sy + j) * sx + i] = m;
             }
 }
+
+/* ---------------------------------------------------------------------------------------------------
+ * Stochastic boundary smoothing (reference src/disp.cpp:56-112, generate_smooth_pts) -- restated.
+ * The reference draws smooth_n offsets with libstdc++'s <random>:
+ *     std::seed_seq{seed & 0xffff, (seed & 0xffff0000) >> 32}   with seed = 0xd9a28bf3 -> {0x8bf3, 0}
+ *     std::mt19937 gen(seeder); std::normal_distribution<double>(0, rad); std::uniform_real_distribution<double>(0, 1)
+ * per point:  theta_inv = unif(gen); phi = 2 pi unif(gen); r = gaussian(gen);
+ *             x = r sin_theta cos(phi), y = r sin_theta cos(phi) (sic: cos, like x), z = r cos_theta
+ * and stores the 8 sign reflections, x sign slowest.  Below: the C++11 standard's seed_seq::generate and mt19937,
+ * and libstdc++'s generate_canonical<double, 53> (two 32-bit draws, low word first) and normal_distribution
+ * (Marsaglia polar method, the second variate saved for the next call) -- the published algorithms, not library code.
+ * Pinned by tests/test_oracle_csg.py against a program that calls <random> itself and against eps fields produced by
+ * the reference's own in_bound (tests/golden/ref_run_slabs_smooth*.npz).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct { uint32_t x[624]; int p; int saved_ok; double saved; } smooth_rng;
+
+static void rng_seed_seq(smooth_rng *g, const uint32_t *v, int s) {
+    enum { n = 624 };
+    uint32_t *b = g->x;
+    for (int i = 0; i < n; ++i) b[i] = 0x8b8b8b8bu;
+    const int t = 11, p = (n - t) / 2, q = p + t;
+    const int m = (s + 1 > n) ? s + 1 : n;
+    for (int k = 0; k < m; ++k) {
+        uint32_t a = b[k % n] ^ b[(k + p) % n] ^ b[(k + n - 1) % n];
+        uint32_t r1 = 1664525u * (a ^ (a >> 27));
+        uint32_t r2 = r1 + (k == 0 ? (uint32_t)s : (k <= s ? (uint32_t)(k % n) + v[k - 1] : (uint32_t)(k % n)));
+        b[(k + p) % n] += r1; b[(k + q) % n] += r2; b[k % n] = r2;
+    }
+    for (int k = m; k < m + n; ++k) {
+        uint32_t a = b[k % n] + b[(k + p) % n] + b[(k + n - 1) % n];
+        uint32_t r3 = 1566083941u * (a ^ (a >> 27));
+        uint32_t r4 = r3 - (uint32_t)(k % n);
+        b[(k + p) % n] ^= r3; b[(k + q) % n] ^= r4; b[k % n] = r4;
+    }
+    /* mersenne_twister_engine::seed(Sseq&): an all-zero state (top bit of x[0], every other word) becomes 2^31 */
+    int zero = (b[0] & 0x80000000u) == 0;
+    for (int i = 1; i < n && zero; ++i) if (b[i] != 0) zero = 0;
+    if (zero) b[0] = 0x80000000u;
+    g->p = n; g->saved_ok = 0; g->saved = 0;
+}
+static uint32_t rng_next(smooth_rng *g) {
+    enum { n = 624, m = 397 };
+    if (g->p >= n) {
+        uint32_t *x = g->x;
+        for (int k = 0; k < n; ++k) {
+            uint32_t y = (x[k] & 0x80000000u) | (x[(k + 1) % n] & 0x7fffffffu);
+            x[k] = x[(k + m) % n] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->p = 0;
+    }
+    uint32_t z = g->x[g->p++];
+    z ^= (z >> 11);
+    z ^= (z << 7) & 0x9d2c5680u;
+    z ^= (z << 15) & 0xefc60000u;
+    z ^= (z >> 18);
+    return z;
+}
+static double rng_canonical(smooth_rng *g) {      /* generate_canonical<double, 53>: k = 2 draws of 32 bits */
+    double sum = 0.0, tmp = 1.0;
+    for (int k = 0; k < 2; ++k) { sum += (double)rng_next(g) * tmp; tmp *= 4294967296.0; }
+    double ret = sum / tmp;
+    if (ret >= 1.0) ret = nextafter(1.0, 0.0);
+    return ret;
+}
+static double rng_normal(smooth_rng *g, double mean, double stddev) {
+    double ret;
+    if (g->saved_ok) { g->saved_ok = 0; ret = g->saved; }
+    else {
+        double x, y, r2;
+        do {
+            x = 2.0 * rng_canonical(g) - 1.0;
+            y = 2.0 * rng_canonical(g) - 1.0;
+            r2 = x * x + y * y;
+        } while (r2 > 1.0 || r2 == 0.0);
+        const double mult = sqrt(-2 * log(r2) / r2);
+        g->saved = x * mult; g->saved_ok = 1;
+        ret = y * mult;
+    }
+    return ret * stddev + mean;
+}
+
+/* out: 24 * smooth_n doubles = 8 * smooth_n offset vectors; returns 8 * smooth_n (the reference's final smooth_n) */
+int csg_smooth_points(int smooth_n, double smooth_rad, double *out) {
+    const uint32_t seed_words[2] = {0x8bf3u, 0u};        /* DEF_SEED = 0xd9a28bf3 through disp.cpp:58 */
+    smooth_rng g;
+    rng_seed_seq(&g, seed_words, 2);
+    for (int i = 0; i < smooth_n; ++i) {
+        int j = 0;
+        double theta_inv = rng_canonical(&g) * (1.0 - 0.0) + 0.0;
+        double cos_theta = 1 - 2 * theta_inv;
+        double sin_theta = 2 * sqrt(theta_inv * (1 - theta_inv));
+        double phi = 2 * M_PI * (rng_canonical(&g) * (1.0 - 0.0) + 0.0);
+        double r = rng_normal(&g, 0.0, smooth_rad);
+        double x = r * sin_theta * cos(phi);
+        double y = r * sin_theta * cos(phi);             /* sic, disp.cpp:92 */
+        double z = r * cos_theta;
+        for (int xf = -1; xf < 2; xf += 2)
+            for (int yf = -1; yf < 2; yf += 2)
+                for (int zf = -1; zf < 2; zf += 2) {
+                    out[24 * i + 3 * j] = x * xf; out[24 * i + 3 * j + 1] = y * yf; out[24 * i + 3 * j + 2] = z * zf;
+                    ++j;
+                }
+    }
+    return 8 * smooth_n;
+}
+
+/* in_bound's inner sums (disp.cpp:271-279): counts[r][point] = in_r(p) + sum_j in_r(p + delta_j), at the Yee points
+ * of E component comp.  counts: n_roots arrays of (nx+1)(ny+1)(nz+1) bytes, region-major. */
+void csg_raster_counts(const csg_node *nodes, const int32_t *roots, int n_roots, int nx, int ny, int nz, double a,
+                       int comp, const double *pts, int n_pts, uint8_t *counts) {
+    const size_t sx = (size_t)nx + 1, sy = (size_t)ny + 1, ntot = sx * sy * ((size_t)nz + 1);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k <= nz; ++k)
+        for (int j = 0; j <= ny; ++j)
+            for (int i = 0; i <= nx; ++i) {
+                const double r_x = csg_yee_coord(2 * i + (comp == 0), a, 0);
+                const double r_y = csg_yee_coord(2 * j + (comp == 1), a, 0);
+                const double r_z = csg_yee_coord(2 * k + (comp == 2), a, 0);
+                for (int q = 0; q < n_roots; ++q) {
+                    double r[3] = {r_x, r_y, r_z};
+                    int c = node_in(nodes, roots[q], r, 0);
+                    for (int s = 0; s < n_pts; ++s) {
+                        double rs[3] = {r_x + pts[3 * s], r_y + pts[3 * s + 1], r_z + pts[3 * s + 2]};
+                        c += node_in(nodes, roots[q], rs, 0);
+                    }
+                    counts[(size_t)q * ntot + ((size_t)k * sy + j) * sx + i] = (uint8_t)c;
+                }
+            }
+}

@@ -219,6 +219,48 @@ int orc_set_regions(orc_sim *s, double ambient_eps, int n_regions, const double 
     return 0;
 }
 
+/* Materials with stochastic smoothing (smooth_n > 0, disp.cpp:264-283): cnt_c[r * ntot + idx] = in_r(p) + sum_j in_r(p + delta_j)
+ * from csg_raster_counts, smooth_total = 8 * smooth_n offsets.  eps_inf = sum_r def + (s_r - def) * cnt / (smooth_total + 1);
+ * each (region, pole) susceptibility has sigma(p) = 0 + (sigma_rp - 0) * cnt / (smooth_total + 1) (its material function is
+ * built with def_ret = 0, disp.cpp:545). */
+int orc_set_regions_counts(orc_sim *s, double ambient_eps, int n_regions, const double *region_eps,
+                           const int *region_npoles, const double *poles, unsigned smooth_total, const uint8_t *cx,
+                           const uint8_t *cy, const uint8_t *cz) {
+    const uint8_t *cn[3] = {cx, cy, cz};
+    for (int c = 0; c < 3; ++c) {
+        free(s->maskc[c]);
+        s->maskc[c] = (uint8_t *)calloc(s->ntot, 1);
+        for (size_t i = 0; i < s->ntot; ++i) {
+            double ret = 0;
+            if (n_regions == 0) ret = ambient_eps;
+            for (int r = 0; r < n_regions; ++r) {
+                double this_ret = cn[c][(size_t)r * s->ntot + i];
+                ret += ambient_eps + (region_eps[r] - ambient_eps) * this_ret / (smooth_total + 1);
+            }
+            s->chi1inv[c][i] = 1 / ret;
+        }
+    }
+    int pidx = 0;
+    for (int r = 0; r < n_regions; ++r)
+        for (int p = 0; p < region_npoles[r]; ++p, ++pidx) {
+            if (s->n_sus >= ORC_MAX_SUS) return -2;
+            orc_sus *u = &s->sus[s->n_sus++];
+            u->omega0 = poles[4 * pidx + 0]; u->gamma = poles[4 * pidx + 1];
+            u->sigma = poles[4 * pidx + 2]; u->drude = poles[4 * pidx + 3] != 0.0;
+            u->region = r;
+            for (int c = 0; c < 3; ++c) {
+                u->sigarr[c] = zalloc(s->ntot);
+                for (size_t i = 0; i < s->ntot; ++i) {
+                    double this_ret = cn[c][(size_t)r * s->ntot + i];
+                    u->sigarr[c][i] = 0.0 + (u->sigma - 0.0) * this_ret / (smooth_total + 1);
+                }
+                for (int q = 0; q < s->nsets; ++q) { u->P[q][c] = zalloc(s->ntot); u->Pp[q][c] = zalloc(s->ntot); }
+            }
+            s->have_disp = 1;
+        }
+    return 0;
+}
+
 /* ---- source waveform: gaussian_src_time_phase (src/disp.cpp:378-400) ---- */
 static double _Complex src_dipole(const orc_src *g, double time) {
     if (g->kind == 2) { double o[2]; g->fn(g->ctx, time, o); return o[0] + I * o[1]; }

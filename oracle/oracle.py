@@ -36,6 +36,10 @@ def lib():
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_regions.argtypes = [C.c_void_p, C.c_double, C.c_int, dp, ip, dp, u8p, u8p, u8p]
+        L.orc_set_regions_counts.argtypes = [C.c_void_p, C.c_double, C.c_int, dp, ip, dp, C.c_uint, u8p, u8p, u8p]
+        L.csg_smooth_points.argtypes = [C.c_int, C.c_double, dp]
+        L.csg_raster_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.c_int, dp, C.c_int, u8p]
         L.orc_add_gaussian_source.argtypes = [C.c_void_p, C.c_int, dp, dp] + [C.c_double] * 7 + [C.c_int]
         L.orc_add_cw_source.argtypes = [C.c_void_p, C.c_int, dp, dp] + [C.c_double] * 7 + [C.c_int]
         L.orc_add_monitors.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
@@ -65,6 +69,14 @@ def lib():
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def smooth_points(smooth_n, smooth_rad):
+    """generate_smooth_pts (disp.cpp:56-112): (8 * smooth_n, 3) offsets, restated in csg_oracle.c."""
+    out = np.zeros(24 * max(int(smooth_n), 0))
+    if smooth_n > 0:
+        lib().csg_smooth_points(int(smooth_n), float(smooth_rad), _dp(out))
+    return out.reshape(-1, 3)
 
 
 class OracleSim:
@@ -106,6 +118,22 @@ class OracleSim:
             ms[0].ctypes.data_as(u8p), ms[1].ctypes.data_as(u8p), ms[2].ctypes.data_as(u8p))
         if rc:
             raise RuntimeError("orc_set_regions failed: %d" % rc)
+
+    def set_regions_counts(self, ambient_eps, region_eps, region_poles, smooth_total, counts):
+        """counts: per E component an array [n_regions, nz+1, ny+1, nx+1] of in_bound's inner sums (smooth_n > 0)."""
+        nreg = len(region_eps)
+        eps = np.ascontiguousarray(region_eps, dtype=np.float64)
+        npoles = np.ascontiguousarray([len(p) for p in region_poles], dtype=np.int32)
+        flat = np.ascontiguousarray([x for p in region_poles for pole in p for x in pole], dtype=np.float64)
+        if flat.size == 0:
+            flat = np.zeros(4)
+        cs = [np.ascontiguousarray(c, dtype=np.uint8).reshape((nreg,) + self.shape) for c in counts]
+        u8p = C.POINTER(C.c_uint8)
+        rc = self.L.orc_set_regions_counts(
+            self.h, float(ambient_eps), nreg, _dp(eps), npoles.ctypes.data_as(C.POINTER(C.c_int)), _dp(flat),
+            int(smooth_total), cs[0].ctypes.data_as(u8p), cs[1].ctypes.data_as(u8p), cs[2].ctypes.data_as(u8p))
+        if rc:
+            raise RuntimeError("orc_set_regions_counts failed: %d" % rc)
 
     def add_gaussian_source(self, comp, lo, hi, amp, freq, width, phase, t_start, t_end, integrated=True):
         lo = np.ascontiguousarray(lo, dtype=np.float64)

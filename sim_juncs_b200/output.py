@@ -69,7 +69,10 @@ def field_samples_dict(bg, with_frequency=True):
             if len(series) < 2:
                 break
             pn = cn + "/" + point_name(i, n_locs)
-            d[pn + "/time"] = np.stack([series.real, series.imag], axis=1)
+            # sic: the dataspace of `time` holds n_t_pts / save_span samples (disp.cpp:771) although the run loop pushed
+            # ceil(n_t_pts / save_span); `frequency` below is the transform of everything pushed (disp.cpp:800-806)
+            kept = series[:bg.n_t_pts // bg.save_span]
+            d[pn + "/time"] = np.stack([kept.real, kept.imag], axis=1)
             if with_frequency:
                 f = spectra[i] if spectra is not None else reference_fft(series)
                 d[pn + "/frequency"] = np.stack([f.real, f.imag], axis=1)

@@ -50,6 +50,25 @@ def oracle_raster(scene, settings, comp, coord_kind=0):
     return out
 
 
+def oracle_raster_counts(scene, settings, comp):
+    """in_bound's inner sums with smooth_n > 0: [n_regions, nz+1, ny+1, nx+1] counts and 8 * smooth_n."""
+    L = orc.lib()
+    nodes = scene.node_array()
+    for reg in scene.regions:
+        if reg.make_2d:
+            thick = THICK_SCALE / settings.resolution
+            for i in range(3):
+                nodes[reg.root].M[3 * i + 2] = nodes[reg.root].M[3 * i + 2] * thick
+    nreg = len(scene.regions)
+    roots = (C.c_int32 * max(nreg, 1))(*[r.root for r in scene.regions])
+    pts = np.ascontiguousarray(orc.smooth_points(settings.smooth_n, settings.smooth_rad))
+    n = settings.grid_cells()
+    out = np.zeros((max(nreg, 1), n + 1, n + 1, n + 1), dtype=np.uint8)
+    L.csg_raster_counts(C.cast(nodes, C.c_void_p), roots, nreg, n, n, n, settings.resolution, comp,
+                        pts.ctypes.data_as(C.POINTER(C.c_double)), len(pts), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out[:nreg], len(pts)
+
+
 def oracle_points(scene, pts):
     L = orc.lib()
     L.csg_eval_points.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_double), C.c_size_t,
@@ -79,7 +98,11 @@ def oracle_bound_geom(scene, settings, masks, nsets=2, integrated=True, mon_comp
     n = settings.grid_cells()
     o = orc.OracleSim((n, n, n), settings.resolution, pml=settings.pml_thickness, nsets=nsets)
     amb, reps, rpoles = region_tables(scene, settings)
-    o.set_regions(amb, reps, rpoles, masks)
+    if settings.smooth_n > 0:       # masks are ignored: in_bound averages over the smoothing offsets
+        counts = [oracle_raster_counts(scene, settings, c) for c in range(3)]
+        o.set_regions_counts(amb, reps, rpoles, counts[0][1], [c[0] for c in counts])
+    else:
+        o.set_regions(amb, reps, rpoles, masks)
     c_by_a = LIGHT_SPEED * settings.um_scale
     ttot = 0.0
     for info, (p1, p2) in zip(scene.sources, scene.source_boxes):

@@ -73,14 +73,14 @@ def test_reference_driver_equals_python_host(conf, extra, tmp_path):
     assert np.array_equal(ref, series[:ref.shape[0]])
 
 
-def test_reference_field_samples_layout_equals_own_writer(tmp_path):
+@pytest.mark.parametrize("conf,extra", [("scenes/tests/run.conf", ()), ("scenes/tests/graphene_short.conf", ("--grid-res", "2.5"))])
+def test_reference_field_samples_layout_equals_own_writer(conf, extra, tmp_path):
     """Every group, dataset, shape, compound member (name, offset, size) and value the reference's save_field_times
     hands to HDF5, against sim_juncs_b200/output.py + hdf5.py."""
     from sim_juncs_b200 import hdf5
     from sim_juncs_b200.output import save_field_samples
-    conf = "scenes/tests/run.conf"
-    entries, blob, out = helpers.run_ref_sim_geom(conf, str(tmp_path / "ref"))
-    st, scene, o, n_t_pts, series = _python_host_on_oracle(conf)
+    entries, blob, out = helpers.run_ref_sim_geom(conf, str(tmp_path / "ref"), extra)
+    st, scene, o, n_t_pts, series = _python_host_on_oracle(conf, extra)
 
     class Bg:        # the attributes save_field_samples reads from a BoundGeom
         pass
