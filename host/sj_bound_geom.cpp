@@ -110,7 +110,6 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
     um_scale = s.um_scale; post_source_t = s.post_source_t; save_span = s.save_span; n_sets = p_n_sets;
     ttot = 0; n_t_pts = 0; raster_ms = run_s = 0;
     if (s.n_dims != 3) { fprintf(stderr, "only dimensions = 3 is supported\n"); exit(1); }
-    if (s.smooth_n != 0) { fprintf(stderr, "smooth_n > 0 is not implemented\n"); exit(1); }
     printf("using simulation side length %f, resolution %f\n", s.len, s.resolution);
 
     const double z_center = s.len / 2 + s.pml_thickness;
@@ -147,8 +146,9 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
         }
     }
     auto t0 = std::chrono::steady_clock::now();
-    if (sj_rasterize(sim, s.ambient_eps, (int)nodes.size(), nodes.data(), (int)regions.size(), regions.data())) {
-        fprintf(stderr, "sj_rasterize: %s\n", sj_last_error(sim)); exit(1);
+    if (sj_rasterize_smooth(sim, s.ambient_eps, (int)nodes.size(), nodes.data(), (int)regions.size(), regions.data(),
+                            (int)s.smooth_n, s.smooth_rad)) {
+        fprintf(stderr, "sj_rasterize_smooth: %s\n", sj_last_error(sim)); exit(1);
     }
     raster_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 

@@ -105,6 +105,15 @@ int sj_set_materials(sj_sim *sim, int32_t n_mat, const sj_material *mats, const 
  * summed exactly like in_bound(); the material table is built from the distinct region masks.  */
 int sj_rasterize(sj_sim *sim, double ambient_eps, int32_t n_nodes, const sj_csg_node *nodes,
                  int32_t n_regions, const sj_region *regions);
+/* The same with the reference's stochastic boundary smoothing (params.conf smooth_n / smooth_rad; cgs_material_function::
+ * generate_smooth_pts + in_bound, src/disp.cpp:56-112, 264-283): every inside test becomes the sum over the point and
+ * 8 * smooth_n fixed offsets drawn from mt19937(seed_seq{0x8bf3, 0}); eps_inf and every pole's sigma take one of
+ * 8 * smooth_n + 2 levels per region.  A material is then one distinct tuple of per-region sums (at most 256 tuples,
+ * 4 regions, smooth_n <= 31; SJ_ERR_UNSUPPORTED beyond).  smooth_n = 0 is sj_rasterize.                              */
+int sj_rasterize_smooth(sj_sim *sim, double ambient_eps, int32_t n_nodes, const sj_csg_node *nodes,
+                        int32_t n_regions, const sj_region *regions, int32_t smooth_n, double smooth_rad);
+/* Material id (index into sj_get_material_table) of every owned Yee point of E component comp. */
+int sj_get_material_ids(sj_sim *sim, int comp, uint8_t *out);
 /* Read back what sj_rasterize produced (tests, eps-*.h5 dump):  region bit masks per E component
  * over the owned slab planes [kz0,kz1) and the material table. */
 int sj_get_region_masks(sj_sim *sim, int comp, uint8_t *out);

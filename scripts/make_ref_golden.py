@@ -27,7 +27,8 @@ CASES = {
     "cw_slab": ("scenes/tests/cw_slab.conf", []),
     "graphene_res2p5": ("scenes/tests/graphene_short.conf", ["--grid-res", "2.5"]),
     "graphene_short": ("scenes/tests/graphene_short.conf", []),
-    "run_slabs_smooth1": ("scenes/tests/run_smooth.conf", []),
+    "run_slabs_smooth1": ("scenes/tests/run_smooth.conf", []),          # stochastic boundary smoothing, dielectric
+    "graphene_smooth2": ("scenes/tests/graphene_smooth.conf", []),      # smoothing of eps and of every pole's sigma
 }
 
 
@@ -66,4 +67,4 @@ def main(names):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or [n for n in CASES if n != "run_slabs_smooth1"])
+    main(sys.argv[1:] or list(CASES))

@@ -49,6 +49,9 @@ SYMBOLS = {
     "sj_version": (C.c_int, []),
     "sj_set_materials": (C.c_int, [_vp, C.c_int32, C.POINTER(SjMaterial), _u8p, _u8p, _u8p]),
     "sj_rasterize": (C.c_int, [_vp, C.c_double, C.c_int32, C.POINTER(SjCsgNode), C.c_int32, C.POINTER(SjRegion)]),
+    "sj_rasterize_smooth": (C.c_int, [_vp, C.c_double, C.c_int32, C.POINTER(SjCsgNode), C.c_int32, C.POINTER(SjRegion),
+                                      C.c_int32, C.c_double]),
+    "sj_get_material_ids": (C.c_int, [_vp, C.c_int, _u8p]),
     "sj_get_region_masks": (C.c_int, [_vp, C.c_int, _u8p]),
     "sj_get_material_table": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(SjMaterial), C.c_int32]),
     "sj_add_gaussian_source": (C.c_int, [_vp, C.c_int, _dp, _dp] + [C.c_double] * 7 + [C.c_int, _dp]),

@@ -40,8 +40,6 @@ class BoundGeom:
         self.n_sets = n_sets
         if settings.n_dims != 3:
             raise NotImplementedError("only dimensions = 3 is supported (all shipped junction confs)")
-        if settings.smooth_n != 0:
-            raise NotImplementedError("smooth_n > 0 (stochastic supersampling, disp.cpp:56-112) is not implemented")
 
         # ---- structure_from_settings (disp.cpp:482-550) ----
         n = settings.grid_cells()
@@ -66,7 +64,7 @@ class BoundGeom:
                      for (w0, g, sg, use_denom) in reg.poles_raw]               # disp.cpp:539-541
             regions.append((reg.root, eps, poles))
         t0 = time.time()
-        self.sim.rasterize(settings.ambient_eps, nodes, regions)
+        self.sim.rasterize(settings.ambient_eps, nodes, regions, settings.smooth_n, settings.smooth_rad)
         self.t_raster = time.time() - t0
 
         # ---- sources and monitors (disp.cpp:584-639) ----

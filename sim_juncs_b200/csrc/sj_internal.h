@@ -119,6 +119,7 @@ struct sj_sim {
     void *E[3], *H[3];        // device, [set][local plane][row][pitch]
     uint8_t *mat[3];
     uint8_t *masks[3];        // region masks from the rasterizer (same layout)
+    bool smoothed = false;    // materials come from the smooth_n > 0 rasterizer (ids are not region masks)
     void *Pall;
     int n_slots;
     int np_thr[SJ_MAX_POLES];
@@ -193,4 +194,4 @@ int sj_profile_f64(sj_sim *s, int reps, double out[4]);
 int sj_profile_f32(sj_sim *s, int reps, double out[4]);
 // sj_raster.cu
 int sj_raster_launch(sj_sim *s, double ambient_eps, int n_nodes, const sj_csg_node *nodes, int n_regions,
-                     const sj_region *regions);
+                     const sj_region *regions, int smooth_n, double smooth_rad);

@@ -80,8 +80,9 @@ class Sim:
                 ptrs[c] = a.ctypes.data_as(C.POINTER(C.c_uint8))
         self._ck(self.L.sj_set_materials(self.h, len(mats), arr, ptrs[0], ptrs[1], ptrs[2]))
 
-    def rasterize(self, ambient_eps, nodes, regions):
-        """nodes: ctypes array of SjCsgNode; regions: list of (root, eps, poles)."""
+    def rasterize(self, ambient_eps, nodes, regions, smooth_n=0, smooth_rad=0.0):
+        """nodes: ctypes array of SjCsgNode; regions: list of (root, eps, poles); smooth_n / smooth_rad: the reference's
+        stochastic boundary smoothing (params.conf, disp.cpp:56-112)."""
         reg = (SjRegion * max(len(regions), 1))()
         for r, (root, eps, poles) in enumerate(regions):
             reg[r].root = int(root)
@@ -89,7 +90,14 @@ class Sim:
             reg[r].n_poles = len(poles)
             for q, p in enumerate(poles):
                 reg[r].poles[q] = make_pole(*p)
-        self._ck(self.L.sj_rasterize(self.h, float(ambient_eps), len(nodes), nodes, len(regions), reg))
+        self._ck(self.L.sj_rasterize_smooth(self.h, float(ambient_eps), len(nodes), nodes, len(regions), reg,
+                                            int(smooth_n), float(smooth_rad)))
+
+    def material_ids(self, comp):
+        """index into material_table() at every owned Yee point of E component comp"""
+        out = np.zeros(self.shape, dtype=np.uint8)
+        self._ck(self.L.sj_get_material_ids(self.h, comp, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
 
     def region_masks(self, comp):
         out = np.zeros(self.shape, dtype=np.uint8)

@@ -170,7 +170,7 @@ def write_eps_h5(bg, out_dir):
     table = np.array([m[0] for m in bg.sim.material_table()])
     tr = 0.0
     for c in range(3):
-        tr = tr + centred(1.0 / table[bg.sim.region_masks(c)], c)
+        tr = tr + centred(1.0 / table[bg.sim.material_ids(c)], c)
     os.makedirs(out_dir, exist_ok=True)
     path = os.path.join(out_dir, "eps-000000.00.h5")
     with H5Writer(path) as w:

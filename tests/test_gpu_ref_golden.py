@@ -12,7 +12,7 @@ from sim_juncs_b200.bound_geom import BoundGeom
 from sim_juncs_b200.settings import settings_from
 
 pytestmark = pytest.mark.gpu
-CASES = ["run_slabs", "cw_slab", "graphene_res2p5", "graphene_short"]
+CASES = ["run_slabs", "cw_slab", "graphene_res2p5", "graphene_short", "run_slabs_smooth1", "graphene_smooth2"]
 
 
 def _launch(name, golden, precision):
@@ -60,3 +60,41 @@ def test_fp32_series_match_reference_driver(name, golden):
     ref = g["time"]
     got = np.stack(bg.get_field_times(), axis=1)[:ref.shape[0]]
     assert rel_l2(got, ref) <= 1e-4, rel_l2(got, ref)
+
+
+def test_smoothed_rasterizer_equals_reference_in_bound(golden):
+    """smooth_n = 1: eps_inf at every Yee point from the CUDA rasterizer (counts over the point and its 8 offsets, material
+    table from the distinct count tuples) against what the reference's own in_bound returned -- exact."""
+    g = np.load(os.path.join(golden, "ref_run_slabs_smooth1.npz"))
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        st = settings_from(str(g["conf"]), [str(a) for a in g["argv"]])
+        bg = BoundGeom(st, None, n_sets=1)
+    finally:
+        os.chdir(cwd)
+    n = st.grid_cells()
+    table = np.array([m[0] for m in bg.sim.material_table()])
+    assert 2 < len(table) <= 10
+    for c in range(3):
+        eps = table[bg.sim.material_ids(c)]
+        assert np.array_equal(eps, g["eps"][c].reshape(n + 1, n + 1, n + 1))
+    # the plain inside bits are still reported
+    assert set(np.unique(bg.sim.region_masks(0)).tolist()) == {0, 1}
+
+
+def test_smoothed_slab_equals_global(golden):
+    """z-slab rasterization with smoothing: material ids may be numbered differently per slab, eps may not differ."""
+    g = np.load(os.path.join(golden, "ref_graphene_smooth2.npz"))
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        st = settings_from(str(g["conf"]), [str(a) for a in g["argv"]])
+        whole = BoundGeom(st, None, n_sets=1)
+        part = BoundGeom(st, None, n_sets=1, kz=(17, 33))
+    finally:
+        os.chdir(cwd)
+    tw = np.array([m[0] for m in whole.sim.material_table()])
+    tp = np.array([m[0] for m in part.sim.material_table()])
+    for c in range(3):
+        assert np.array_equal(tw[whole.sim.material_ids(c)][17:33], tp[part.sim.material_ids(c)])

@@ -30,7 +30,7 @@ def _python_host_on_oracle(conf, extra=()):
         st = _settings(conf, extra)
         scene = Scene.from_geom(st.geom_fname, st)
         masks = [helpers.oracle_raster(scene, st, c) for c in range(3)]
-        o, n_t_pts = helpers.oracle_bound_geom(scene, st, masks)
+        o, n_t_pts = helpers.oracle_bound_geom(scene, st, masks)       # smooth_n > 0: counts instead of the masks
         o.run(n_t_pts, st.save_span or 1)
     finally:
         os.chdir(cwd)
@@ -39,10 +39,11 @@ def _python_host_on_oracle(conf, extra=()):
 
 
 @pytest.mark.parametrize("conf,extra", [("scenes/tests/run.conf", ()), ("scenes/tests/cw_slab.conf", ()),
-                                        ("scenes/tests/graphene_short.conf", ("--grid-res", "2.5"))])
+                                        ("scenes/tests/graphene_short.conf", ("--grid-res", "2.5")),
+                                        ("scenes/tests/run_smooth.conf", ()), ("scenes/tests/graphene_smooth.conf", ())])
 def test_reference_driver_equals_python_host(conf, extra, tmp_path):
     """Vacuum + dielectric slabs with a Gaussian pulse; a CW source; the Au / graphene / SiO2 junction (Drude + Lorentz
-    poles, make_2d sheet) on a coarse grid."""
+    poles, make_2d sheet) on a coarse grid; the last two with stochastic boundary smoothing (smooth_n = 1 and 2)."""
     entries, blob, out = helpers.run_ref_sim_geom(conf, str(tmp_path), extra)
     st, scene, o, n_t_pts, series = _python_host_on_oracle(conf, extra)
     # eps_inf at every Yee point: the reference's in_bound() vs region masks + material table
@@ -53,14 +54,21 @@ def test_reference_driver_equals_python_host(conf, extra, tmp_path):
     # sigma of every susceptibility (one per region and pole, disp.cpp:529-548) vs sigma_rp * inside bit
     amb, reps, rpoles = helpers.region_tables(scene, st)
     isus = 0
+    most_levels = 0
     for r, poles in enumerate(rpoles):
         for (w0, g, sg, drude) in poles:
             for c, nm in enumerate("xyz"):
                 sig_ref = np.fromfile(os.path.join(str(tmp_path), "sigma_%d_%s.f64" % (isus, nm))).reshape(n + 1, n + 1, n + 1)
-                bit = (helpers.oracle_raster(scene, st, c) >> r) & 1
-                assert np.array_equal(sig_ref, sg * bit)
+                if st.smooth_n > 0:
+                    cnt, tot = helpers.oracle_raster_counts(scene, st, c)
+                    assert np.array_equal(sig_ref, 0.0 + (sg - 0.0) * cnt[r].astype(np.float64) / (tot + 1))
+                    most_levels = max(most_levels, len(np.unique(sig_ref)))
+                else:
+                    bit = (helpers.oracle_raster(scene, st, c) >> r) & 1
+                    assert np.array_equal(sig_ref, sg * bit)
             isus += 1
     assert not os.path.exists(os.path.join(str(tmp_path), "sigma_%d_x.f64" % isus))
+    assert most_levels > 2 or st.smooth_n == 0 or isus == 0        # smoothing really produced intermediate sigma levels
     # the run loop: number of steps and saves, then the monitor series -- same engine underneath, so the only
     # differences could come from the host logic (waveform, placement box, amplitude, units, cadence)
     ref = helpers.ref_series(entries, blob)
