@@ -134,10 +134,21 @@ int sj_add_gaussian_source(sj_sim *sim, int comp, const double lo[3], const doub
 int sj_add_cw_source(sj_sim *sim, int comp, const double lo[3], const double hi[3],
                      double amp_re, double amp_im, double freq, double width,
                      double t_start, double t_end, double slowness, int integrated, const double *set_phase);
+/* fields.add_volume_source(c, src, volume, amp) for ANY meep::src_time subclass: `fn` is its dipole(time) (called on
+ * the host, from the calling thread, while the drive table of the next steps is built; it must stay valid until
+ * sj_destroy), last_time its last_time(), integrated its is_integrated.                                          */
+typedef void (*sj_dipole_fn)(void *ctx, double time, double out_re_im[2]);
+int sj_add_custom_source(sj_sim *sim, int comp, const double lo[3], const double hi[3],
+                         double amp_re, double amp_im, sj_dipole_fn fn, void *ctx, double last_time,
+                         int integrated, const double *set_phase);
 double sj_last_source_time(const sj_sim *sim);     /* fields.last_source_time(), disp.cpp:625 */
 
 /* ---- monitors: fields.get_field(component, loc) at fixed points (src/disp.cpp:724) ------- */
 int sj_add_monitors(sj_sim *sim, int comp, int32_t n, const double *xyz);
+
+/* fields.get_field(component, loc) at arbitrary points, at the current step (one small kernel + one copy; the monitor
+ * list above is the fast path).  out: [n][n_sets] doubles, same interpolation and ownership rule as the monitors. */
+int sj_sample_at(sj_sim *sim, int comp, int32_t n, const double *xyz, double *out);
 
 /* ---- stepping --------------------------------------------------------------------------
  * sj_run = the body of bound_geom::run (src/disp.cpp:719-741): for i in [0,n_steps): if

@@ -42,6 +42,7 @@ class SjRegion(C.Structure):
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 _vp = C.c_void_p
+DIPOLE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.POINTER(C.c_double))
 SYMBOLS = {
     "sj_create": (C.c_int, [C.POINTER(SjGrid), C.POINTER(_vp)]),
     "sj_destroy": (None, [_vp]),
@@ -56,6 +57,8 @@ SYMBOLS = {
     "sj_get_material_table": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(SjMaterial), C.c_int32]),
     "sj_add_gaussian_source": (C.c_int, [_vp, C.c_int, _dp, _dp] + [C.c_double] * 7 + [C.c_int, _dp]),
     "sj_add_cw_source": (C.c_int, [_vp, C.c_int, _dp, _dp] + [C.c_double] * 7 + [C.c_int, _dp]),
+    "sj_add_custom_source": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_double, C.c_double, DIPOLE_FN, _vp, C.c_double, C.c_int, _dp]),
+    "sj_sample_at": (C.c_int, [_vp, C.c_int, C.c_int32, _dp, _dp]),
     "sj_last_source_time": (C.c_double, [_vp]),
     "sj_add_monitors": (C.c_int, [_vp, C.c_int, C.c_int32, _dp]),
     "sj_run": (C.c_int, [_vp, C.c_int64, C.c_int32]),

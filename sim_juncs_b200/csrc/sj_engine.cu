@@ -527,6 +527,7 @@ extern "C" int sj_get_region_masks(sj_sim *s, int comp, uint8_t *out) {
 // ---- sources -------------------------------------------------------------------------------
 // gaussian_src_time_phase (reference src/disp.cpp:378-400) evaluated on the host in fp64
 static std::complex<double> src_dipole(const HostSource &g, double time) {
+    if (g.kind == 2) { double o[2] = {0, 0}; g.fn(g.fn_ctx, time, o); return std::complex<double>(o[0], o[1]); }
     if (g.kind == 1) {
         // meep::continuous_src_time::dipole (what the reference instantiates for CW_source, src/disp.cpp:618):
         // zero outside [start, end] (float compare), exp(-i w t)/(-i w), tanh turn-on/off when width != 0
@@ -545,7 +546,7 @@ static std::complex<double> src_dipole(const HostSource &g, double time) {
 
 extern "C" double sj_last_source_time(const sj_sim *s) {
     double t = 0;
-    for (const auto &g : s->srcs) t = std::max(t, g.kind == 1 ? g.t_end : (double)float(g.peak + g.cutoff));
+    for (const auto &g : s->srcs) t = std::max(t, g.kind == 2 ? g.last_time : g.kind == 1 ? g.t_end : (double)float(g.peak + g.cutoff));
     return t;
 }
 
@@ -645,6 +646,17 @@ extern "C" int sj_add_cw_source(sj_sim *s, int comp, const double lo[3], const d
     return place_source(s, g, lo, hi, amp_re, amp_im, set_phase);
 }
 
+// fields.add_volume_source(c, src, volume, amp) for an arbitrary meep::src_time subclass: fn is its dipole(time)
+extern "C" int sj_add_custom_source(sj_sim *s, int comp, const double lo[3], const double hi[3], double amp_re, double amp_im,
+                                    sj_dipole_fn fn, void *ctx, double last_time, int integrated, const double *set_phase) {
+    if (!s || comp < 0 || comp > 2 || !lo || !hi || !fn) return fail(s, SJ_ERR_ARG, "bad source arguments (E components only)");
+    if ((int)s->srcs.size() >= SJ_MAX_SRC) return fail(s, SJ_ERR_ARG, "too many sources");
+    HostSource g;
+    g.comp = comp; g.integrated = integrated; g.kind = 2; g.fn = fn; g.fn_ctx = ctx; g.last_time = last_time;
+    g.omega = g.width = g.phi = g.peak = g.cutoff = g.t_start = g.t_end = g.slowness = g.amp_t_re = g.amp_t_im = 0;
+    return place_source(s, g, lo, hi, amp_re, amp_im, set_phase);
+}
+
 // drive table [step][src][set][2]: {S_n, dt*J_n}; S_n = Re/Im(amp * dipole(n dt)) for integrated
 // sources (meep update_eh), dt*J_n = Re/Im(amp * dt * current(n dt + dt/2)) otherwise (step_source)
 static int ensure_drive(sj_sim *s, long long upto) {
@@ -683,7 +695,44 @@ static int ensure_drive(sj_sim *s, long long upto) {
 }
 
 // ---- monitors --------------------------------------------------------------------------------
-// meep grid_volume::interpolate: linear weights between the two bracketing Yee points per direction
+// meep grid_volume::interpolate: linear weights between the two bracketing Yee points per direction.
+// Returns whether this slab owns the point (idx8 stays -1 otherwise).
+static bool interp_stencil(const sj_sim *s, int comp, const double *xyz, long long *idx8, double *w8) {
+    const int cdir = comp % 3; const bool isH = comp >= 3;
+    int mid[3], sh[3]; double dv[3];
+    for (int d = 0; d < 3; ++d) {
+        sh[d] = isH ? (d != cdir) : (d == cdir);
+        const double pc = xyz[d];
+        const double p = (pc - sh[d] * (0.5 * s->inva)) * s->g.a;
+        mid[d] = ((int)floor(p)) * 2 + 1 + sh[d];
+        const double midv = mid[d] * (0.5 * s->inva);
+        dv[d] = (pc - midv) * (2 * s->g.a);
+    }
+    // the rank owning the lower bracketing z plane evaluates the whole stencil (upper plane may be its halo)
+    const int klow = (mid[2] - 1 - sh[2]) / 2;
+    const int kown = std::min(std::max(klow, 0), s->g.n[2]);
+    const bool mine = (kown >= s->kz0 && kown < s->kz1);
+    for (int q = 0; q < 8; ++q) { idx8[q] = -1; w8[q] = 0.0; }
+    if (!mine) return false;
+    for (int q = 0; q < 8; ++q) {
+        double wt = 1.0; long long lin = 0; bool ok = true;
+        for (int d = 0; d < 3; ++d) {
+            const int up = (q >> d) & 1;
+            const int h = mid[d] + (up ? 1 : -1);
+            wt *= up ? 0.5 * (1.0 + dv[d]) : 0.5 * (1.0 - dv[d]);
+            const int i = (h - sh[d]) / 2;
+            if (h - sh[d] < 0 || i > s->g.n[d]) { ok = false; continue; }
+            if (d == 0) lin += i; else if (d == 1) lin += (long long)i * s->pitch;
+            else { const int kl = i - s->kz0 + 1; if (kl < 0 || kl >= s->nzl) ok = false; else lin += (long long)kl * s->plane; }
+        }
+        if (wt < 0.0) wt = 0.0;
+        if (!ok) wt = 0.0;
+        idx8[q] = ok ? lin : 0;   // >= 0 marks "owned"; weight 0 drops the point
+        w8[q] = wt;
+    }
+    return true;
+}
+
 extern "C" int sj_add_monitors(sj_sim *s, int comp, int32_t n, const double *xyz) {
     if (s) cudaSetDevice(s->g.device);
     if (!s || comp < 0 || comp > 5 || n < 0 || (n && !xyz)) return fail(s, SJ_ERR_ARG, "bad monitor arguments");
@@ -693,40 +742,7 @@ extern "C" int sj_add_monitors(sj_sim *s, int comp, int32_t n, const double *xyz
     std::vector<long long> idx((size_t)n * 8, -1);
     std::vector<double> w((size_t)n * 8, 0.0);
     s->mon_owned.assign(n, 0);
-    const int cdir = comp % 3; const bool isH = comp >= 3;
-    for (int m = 0; m < n; ++m) {
-        int mid[3], sh[3]; double dv[3];
-        for (int d = 0; d < 3; ++d) {
-            sh[d] = isH ? (d != cdir) : (d == cdir);
-            const double pc = xyz[3 * m + d];
-            const double p = (pc - sh[d] * (0.5 * s->inva)) * s->g.a;
-            mid[d] = ((int)floor(p)) * 2 + 1 + sh[d];
-            const double midv = mid[d] * (0.5 * s->inva);
-            dv[d] = (pc - midv) * (2 * s->g.a);
-        }
-        // the rank owning the lower bracketing z plane evaluates the whole stencil (upper plane may be its halo)
-        const int klow = (mid[2] - 1 - sh[2]) / 2;
-        const int kown = std::min(std::max(klow, 0), s->g.n[2]);
-        const bool mine = (kown >= s->kz0 && kown < s->kz1);
-        s->mon_owned[m] = mine;
-        if (!mine) continue;
-        for (int q = 0; q < 8; ++q) {
-            double wt = 1.0; long long lin = 0; bool ok = true;
-            for (int d = 0; d < 3; ++d) {
-                const int up = (q >> d) & 1;
-                const int h = mid[d] + (up ? 1 : -1);
-                wt *= up ? 0.5 * (1.0 + dv[d]) : 0.5 * (1.0 - dv[d]);
-                const int i = (h - sh[d]) / 2;
-                if (h - sh[d] < 0 || i > s->g.n[d]) { ok = false; continue; }
-                if (d == 0) lin += i; else if (d == 1) lin += (long long)i * s->pitch;
-                else { const int kl = i - s->kz0 + 1; if (kl < 0 || kl >= s->nzl) ok = false; else lin += (long long)kl * s->plane; }
-            }
-            if (wt < 0.0) wt = 0.0;
-            if (!ok) wt = 0.0;
-            idx[(size_t)m * 8 + q] = ok ? lin : 0;   // >= 0 marks "owned"; weight 0 drops the point
-            w[(size_t)m * 8 + q] = wt;
-        }
-    }
+    for (int m = 0; m < n; ++m) s->mon_owned[m] = interp_stencil(s, comp, xyz + 3 * m, &idx[(size_t)m * 8], &w[(size_t)m * 8]);
     CK(cudaMalloc((void **)&s->mon_idx, std::max<size_t>(idx.size(), 1) * sizeof(long long)));
     CK(cudaMalloc((void **)&s->mon_w, std::max<size_t>(w.size(), 1) * sizeof(double)));
     if (n) {
@@ -764,6 +780,35 @@ static int do_sample(sj_sim *s, cudaStream_t st, long long base_step, int base_c
     s->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+// fields.get_field(c, loc) at arbitrary points, now: the monitors' interpolation kernel on a temporary point list
+extern "C" int sj_sample_at(sj_sim *s, int comp, int32_t n, const double *xyz, double *out) {
+    if (s) cudaSetDevice(s->g.device);
+    if (!s || comp < 0 || comp > 5 || n < 0 || (n && (!xyz || !out))) return fail(s, SJ_ERR_ARG, "bad sample arguments");
+    if (n == 0) return SJ_OK;
+    std::vector<long long> idx((size_t)n * 8, -1);
+    std::vector<double> w((size_t)n * 8, 0.0);
+    for (int m = 0; m < n; ++m) interp_stencil(s, comp, xyz + 3 * m, &idx[(size_t)m * 8], &w[(size_t)m * 8]);
+    const size_t nt = (size_t)n * s->g.n_sets;
+    long long *didx = NULL; double *dw = NULL, *dout = NULL; int *dflag = NULL;
+    CK(cudaMalloc((void **)&didx, idx.size() * sizeof(long long)));
+    CK(cudaMalloc((void **)&dw, w.size() * sizeof(double)));
+    CK(cudaMalloc((void **)&dout, nt * sizeof(double)));
+    CK(cudaMalloc((void **)&dflag, sizeof(int)));
+    CK(cudaMemcpyAsync(didx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(dw, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemsetAsync(dflag, 0, sizeof(int), s->stream));
+    MonDev m; m.n_mon = n; m.comp = comp; m.idx = didx; m.w = dw; m.series = dout; m.flags = dflag;
+    // cursor = 0: base_step is the current step and the span is never reached
+    if (s->prec == SJ_F64) { KParams<double> p; fill_params(s, p); sample_monitors<double><<<(unsigned)((nt + 127) / 128), 128, 0, s->stream>>>(p, m, s->steps_done, 0, 1 << 30); }
+    else { KParams<float> p; fill_params(s, p); sample_monitors<float><<<(unsigned)((nt + 127) / 128), 128, 0, s->stream>>>(p, m, s->steps_done, 0, 1 << 30); }
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, nt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(didx); cudaFree(dw); cudaFree(dout); cudaFree(dflag);
+    return SJ_OK;
 }
 
 extern "C" int sj_pass(sj_sim *s, int which, int32_t k0, int32_t k1, void *stream) {

@@ -94,7 +94,10 @@ struct MonDev {
 // ---- host-side state -------------------------------------------------------------------
 struct HostSource {
     int comp, integrated;
-    int kind;                     // 0: gaussian_src_time_phase, 1: meep::continuous_src_time
+    int kind;                     // 0: gaussian_src_time_phase, 1: meep::continuous_src_time, 2: caller's waveform
+    void (*fn)(void *, double, double *) = nullptr;   // kind 2: dipole(ctx, time, {re, im}), called on the host
+    void *fn_ctx = nullptr;
+    double last_time = 0;         // kind 2
     double t_start, t_end, slowness;   // kind 1
     double omega, width, phi, peak, cutoff;
     double amp_t_re, amp_t_im;    // 1/(-i omega)

@@ -138,6 +138,30 @@ class Sim:
         self._ck(self.L.sj_add_cw_source(self.h, comp, _dp(lo), _dp(hi), amp.real, amp.imag, freq, width, t_start, t_end,
                                          float(slowness), int(integrated), sp))
 
+    def add_custom_source(self, comp, lo, hi, amp, dipole, last_time, integrated=True, set_phase=None):
+        """dipole: callable t -> complex, the waveform of any meep::src_time subclass (sj_add_custom_source)."""
+        from ._lib import DIPOLE_FN
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        amp = complex(amp)
+
+        def tramp(ctx, t, out):
+            v = complex(dipole(t))
+            out[0] = v.real
+            out[1] = v.imag
+        cb = DIPOLE_FN(tramp)
+        self._callbacks = getattr(self, "_callbacks", []) + [cb]      # must outlive the simulation
+        ph = None if set_phase is None else np.ascontiguousarray(set_phase, dtype=np.float64)
+        self._ck(self.L.sj_add_custom_source(self.h, comp, _dp(lo), _dp(hi), amp.real, amp.imag, cb, None, float(last_time),
+                                             int(integrated), None if ph is None else _dp(ph)))
+
+    def sample_at(self, xyz, comp=0):
+        """fields.get_field at arbitrary points, now: [n, n_sets]"""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((len(xyz), self.n_sets))
+        self._ck(self.L.sj_sample_at(self.h, comp, len(xyz), _dp(xyz), _dp(out)))
+        return out
+
     def last_source_time(self):
         return self.L.sj_last_source_time(self.h)
 

@@ -82,3 +82,86 @@ def test_python_cli_with_own_parser_matches_reference_parser_path(tmp_path, scen
         worst = max(worst, float(np.abs(got - series[:len(got)]).max()))
     assert worst == 0.0
     assert max(np.abs(s_).max() for s_ in bg.get_field_times()) > 1e-6
+
+
+# ---- the reference's OWN sim_geom on the B200 engine (host/meep_compat) -----------------------------------------
+MEEP_EXE = os.path.join(ROOT, "host", "_ref", "sim_geom_meep")
+
+
+@pytest.mark.skipif(not os.path.exists(MEEP_EXE), reason="host/_ref/sim_geom_meep is built where /root/reference exists")
+@pytest.mark.parametrize("name", ["run_slabs", "cw_slab", "graphene_res2p5", "graphene_smooth2"])
+def test_unmodified_reference_main_on_the_cuda_engine(name, tmp_path, golden):
+    """main.cpp + disp.cpp + cgs*.cpp + data_utils.cpp of the reference, unmodified, linked against host/meep_compat
+    (meep API slice on the C ABI) instead of libmeep: same command line, the series it writes to field_samples.h5 must be
+    the ones the same sources produce over the CPU oracle (tests/golden/ref_*.npz) to <= 1e-9."""
+    from helpers import rel_l2
+    from sim_juncs_b200 import hdf5
+    g = np.load(os.path.join(golden, "ref_%s.npz" % name))
+    argv = [MEEP_EXE, "--conf-file", str(g["conf"]), "--out-dir", str(tmp_path)] + [str(a) for a in g["argv"]]
+    out = subprocess.check_output(argv, cwd=ROOT, timeout=900).decode()
+    assert "finished writing hdf5 file!" in out
+    f = hdf5.File(os.path.join(str(tmp_path), "field_samples.h5"))
+    ref = g["time"]
+    cols, fcols, locs = [], [], []
+    for cn in sorted(k for k in f.keys() if k.startswith("cluster_")):
+        cl = f[cn]
+        loc = cl["locations"].read()
+        if len(loc):
+            locs.append(np.stack([loc["x"], loc["y"], loc["z"]], axis=1))
+        for pn in sorted(k for k in cl.keys() if k.startswith("point_")):
+            t = cl[pn]["time"].read()
+            cols.append(t["Re"] + 1j * t["Im"])
+            fr = cl[pn]["frequency"].read()
+            fcols.append(fr["Re"] + 1j * fr["Im"])
+    got = np.stack(cols, axis=1)
+    assert got.shape == ref.shape
+    assert np.abs(ref).max() > 1e-7
+    assert rel_l2(got, ref) <= 1e-9, rel_l2(got, ref)
+    assert rel_l2(np.stack(fcols, axis=1), g["frequency"]) <= 1e-9
+    assert np.array_equal(np.concatenate(locs), g["locations"])
+    assert np.array_equal(f["info"]["time_bounds"].read(), g["time_bounds"])
+    assert int(f["info"]["n_time_points"].read()[0]) == int(g["n_time_points"][0])
+    src = f["info"]["sources"].read()
+    assert np.array_equal(np.stack([src[k] for k in ("wavelen", "width", "phase", "start_time", "end_time", "amplitude")], axis=1), g["sources"])
+    assert sorted(f["info"]["cgs_params"].keys()) == sorted(str(x) for x in g["cgs_names"])
+
+
+def test_custom_source_and_sample_at_equal_builtin_paths():
+    """sj_add_custom_source with the Gaussian waveform evaluated in Python == sj_add_gaussian_source; sj_sample_at ==
+    the monitor list, bit for bit."""
+    import cmath
+    import math
+    from sim_juncs_b200 import Sim
+    n, a = (24, 20, 28), 6.0
+    lo, hi = [0, 0, 1.0], [n[0] / a, n[1] / a, 1.0]
+    f0, w, ph, t0, t1 = 0.4, 1.5, 0.3, 1.0, 19.0
+    omega, peak, cutoff = 2 * math.pi * f0, 0.5 * (t0 + t1), float(np.float32((t1 - t0) * 0.5))
+
+    def dipole(t):                       # disp.cpp:395-400
+        tt = t - peak
+        if float(np.float32(abs(tt))) > cutoff:
+            return 0.0
+        return math.exp(-tt * tt / (2 * w * w)) * cmath.rect(1.0, -omega * tt - (ph + math.pi)) * (1.0 / complex(0, -omega))
+    pts = np.array([[2.0, 1.6, 2.3], [1.0, 2.0, 3.0], [3.3, 0.2, 0.9]])
+    sims = []
+    for custom in (False, True):
+        g = Sim(n, a, pml=1.0, n_sets=2)
+        g.set_materials([(1.0, []), (2.25, [(1.1, 0.05, 1.3, 0)])], [(np.arange(29)[:, None, None] > 16).astype(np.uint8) * np.ones((29, 21, 25), dtype=np.uint8)] * 3)
+        if custom:
+            g.add_custom_source(0, lo, hi, 1.0, dipole, float(np.float32(peak + cutoff)), True)
+        else:
+            g.add_gaussian_source(0, lo, hi, 1.0, f0, w, ph, t0, t1, True)
+        g.add_monitors(pts, 0)
+        g.run(120, 1 << 30)
+        sims.append(g)
+    assert sims[0].last_source_time() == sims[1].last_source_time()
+    a0, a1 = sims[0].sample_at(pts), sims[1].sample_at(pts)
+    assert np.abs(a0).max() > 1e-6
+    assert rel_l2_(a1, a0) < 1e-13              # libm exp / polar in C++ vs Python: last-bit differences of the waveform
+    for g in sims:                              # the run loop samples BEFORE it steps (disp.cpp:719-741): this sample is of
+        g.run(1, 1)                             # the state sample_at saw
+    assert np.array_equal(sims[0].monitors()[-1], a0) and np.array_equal(sims[1].monitors()[-1], a1)
+
+
+def rel_l2_(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
