@@ -29,6 +29,7 @@ CASES = {
     "graphene_short": ("scenes/tests/graphene_short.conf", []),
     "run_slabs_smooth1": ("scenes/tests/run_smooth.conf", []),          # stochastic boundary smoothing, dielectric
     "graphene_smooth2": ("scenes/tests/graphene_smooth.conf", []),      # smoothing of eps and of every pole's sigma
+    "graphene_long": ("scenes/tests/graphene_long.conf", []),           # 5965 steps: late-time ringing, long after the pulse
 }
 
 

@@ -98,3 +98,19 @@ def test_smoothed_slab_equals_global(golden):
     tp = np.array([m[0] for m in part.sim.material_table()])
     for c in range(3):
         assert np.array_equal(tw[whole.sim.material_ids(c)][17:33], tp[part.sim.material_ids(c)])
+
+
+def test_late_time_tail_matches_reference_driver(golden):
+    """5965 steps at res 5 (the pulse is over after ~1100): the weak ringing that remains -- six orders of magnitude below
+    the pulse -- must still be the reference driver's, window by window (absolute error against the pulse's scale, since
+    round-off of the pulse is what limits the tail)."""
+    g, st, bg = _launch("graphene_long", golden, "f64")
+    ref = g["time"]
+    got = np.stack(bg.get_field_times(), axis=1)[:ref.shape[0]]
+    peak = np.abs(ref).max()
+    assert rel_l2(got, ref) <= 1e-9
+    for lo in range(0, ref.shape[0], 100):
+        w = slice(lo, min(lo + 100, ref.shape[0]))
+        assert np.abs(got[w] - ref[w]).max() <= 1e-12 * peak, (lo, np.abs(got[w] - ref[w]).max())
+        assert rel_l2(got[w], ref[w]) <= 1e-6, (lo, rel_l2(got[w], ref[w]))
+    assert np.abs(ref[300:]).max() < 1e-4 * peak            # no late-time growth at this resolution
