@@ -370,7 +370,7 @@ void sj_interior_geom(const sj_sim *s, int k_begin, int k_end, IntGeom &g, dim3 
     const int V = s->prec == SJ_F64 ? 2 : 4;
     g.i_lo = s->lo[0]; g.i_hi = s->hi[0]; g.j_lo = s->lo[1]; g.j_hi = s->hi[1];
     g.k_lo = std::max(s->lo[2], s->kz0); g.k_hi = std::min(s->hi[2], s->kz1);
-    g.zchunk = s->int_zchunk; g.flags = s->flags_int;
+    g.zchunk = s->int_zchunk; g.flags = NULL;
     const int ni = std::max(g.i_hi - g.i_lo, 0), nj = std::max(g.j_hi - g.j_lo, 0);
     const int tw = s->int_lx * V, th = (32 / s->int_lx) * 8;
     const int kb = std::max(k_begin, g.k_lo), ke = std::min(k_end, g.k_hi);
@@ -419,24 +419,14 @@ int sj_finish_materials(sj_sim *s) {
     {
         const int V = s->prec == SJ_F64 ? 2 : 4;
         IntGeom g; dim3 grd; sj_interior_geom(s, s->kz0, s->kz1, g, grd);
-        cudaFree(s->flags_int); s->flags_int = NULL;
-        const size_t nfl = (size_t)grd.x * grd.y * std::max(g.nzc, 1);
-        CK(cudaMalloc((void **)&s->flags_int, std::max<size_t>(nfl, 1) * sizeof(unsigned)));
-        if (g.nzc > 0 && grd.x && grd.y) {
-            tile_flags_kernel<<<dim3(grd.x, grd.y, g.nzc), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], g, s->int_lx * V,
-                (32 / s->int_lx) * 8, s->pitch, s->plane, s->kz0, s->first_disp, s->flags_int);
-        }
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(s->stream));
-        // split the E-pass work into "uniform material" and "general" lists (block-uniform fast path)
         auto upload = [&](ItemList &L, const std::vector<WorkItem> &v) -> int {
             cudaFree(L.dev); L.dev = NULL; L.n = (int)v.size();
             CK(cudaMalloc((void **)&L.dev, std::max<size_t>(v.size(), 1) * sizeof(WorkItem)));
             if (!v.empty()) CK(cudaMemcpy(L.dev, v.data(), v.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
             return 0;
         };
-        // class of a tile from its flag word (tile_flags_kernel / item_flags_kernel): mixed -> 1; one material without
-        // poles -> 0; one material with 1 or 2 poles -> 2 / 3 (SJ_NO_UNI=1 sends those through the general path too)
+        // class of a tile plane from its flag word (plane_flags_kernel): mixed -> 1; one material without poles -> 0; one
+        // material with 1 or 2 poles -> 2 / 3 (SJ_NO_UNI=1 sends those through the general path too)
         static const bool uni_on = getenv("SJ_NO_UNI") == NULL;
         auto tile_class = [&](unsigned f) -> int {
             if (f & 1u) return 1;
@@ -444,35 +434,86 @@ int sj_finish_materials(sj_sim *s) {
             const int np = s->mats_sorted[f >> 8].n_poles;
             return (uni_on && np >= 1 && np <= 2 && s->n_slots <= 2) ? 1 + np : 1;
         };
-        std::vector<WorkItem> lst[4];
-        std::vector<unsigned> fl(std::max<size_t>(nfl, 1));
-        if (nfl) CK(cudaMemcpy(fl.data(), s->flags_int, nfl * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        const int tw = s->int_lx * V, th = (32 / s->int_lx) * 8;
-        for (int q = 0; q < s->g.n_sets; ++q)
+        // Split every (tile, z-chunk) item along z into runs of planes that hold one material (fast paths: no material
+        // bytes, coefficients in registers) and runs that do not (general path).  Material interfaces in these scenes are
+        // mostly horizontal, so a chunk that straddles one is uniform above and below it.  Uniform runs shorter than
+        // `min_run` planes are not worth a block of their own and join the neighbouring general run.  The arithmetic of
+        // the paths is identical, so the split changes nothing but speed.  SJ_ZSPLIT=0: classify whole items.
+        static const int min_run = getenv("SJ_ZSPLIT") ? atoi(getenv("SJ_ZSPLIT")) : 3;
+        const int ZMAX = 64;
+        auto classify = [&](const std::vector<WorkItem> &items, int tile_w, int tile_h, std::vector<WorkItem> (&out)[4]) -> int {
+            if (items.empty()) return 0;
+            WorkItem *ditems; unsigned *df;
+            CK(cudaMalloc((void **)&ditems, items.size() * sizeof(WorkItem)));
+            CK(cudaMalloc((void **)&df, items.size() * ZMAX * sizeof(unsigned)));
+            CK(cudaMemcpyAsync(ditems, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s->stream));
+            plane_flags_kernel<<<(unsigned)items.size(), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], ditems, tile_w, tile_h,
+                s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df, ZMAX);
+            std::vector<unsigned> fl(items.size() * ZMAX);
+            CK(cudaMemcpyAsync(fl.data(), df, fl.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            CK(cudaGetLastError());
+            cudaFree(ditems); cudaFree(df);
+            struct Seg { int kb, ke; unsigned key; };       // key 1 = general, else the flag word of a uniform run
+            for (size_t n = 0; n < items.size(); ++n) {
+                const WorkItem &it = items[n];
+                const int nz = it.ke - it.kb;
+                std::vector<Seg> seg;
+                if (nz > ZMAX || min_run <= 0) {            // whole item: uniform only if every plane agrees
+                    unsigned key = nz > 0 && nz <= ZMAX ? fl[n * ZMAX] : 1u;
+                    if (tile_class(key) == 1) key = 1u;
+                    for (int kk = 1; kk < nz && nz <= ZMAX && key != 1u; ++kk) if (fl[n * ZMAX + kk] != key) key = 1u;
+                    seg.push_back(Seg{it.kb, it.ke, key});
+                } else {
+                    for (int kk = 0; kk < nz; ++kk) {
+                        unsigned key = fl[n * ZMAX + kk];
+                        if (tile_class(key) == 1) key = 1u;
+                        if (!seg.empty() && seg.back().key == key) seg.back().ke = it.kb + kk + 1;
+                        else seg.push_back(Seg{it.kb + kk, it.kb + kk + 1, key});
+                    }
+                    if (seg.size() > 1) {
+                        for (size_t q = 0; q < seg.size(); ++q) if (seg[q].key != 1u && seg[q].ke - seg[q].kb < min_run) seg[q].key = 1u;
+                        std::vector<Seg> merged;
+                        for (size_t q = 0; q < seg.size(); ++q) {
+                            if (!merged.empty() && merged.back().key == seg[q].key) merged.back().ke = seg[q].ke;
+                            else merged.push_back(seg[q]);
+                        }
+                        seg.swap(merged);
+                    }
+                }
+                for (size_t q = 0; q < seg.size(); ++q) {
+                    WorkItem w = it;
+                    w.kb = seg[q].kb; w.ke = seg[q].ke;
+                    w.mat = seg[q].key == 1u ? 0 : (int)(seg[q].key >> 8);
+                    out[seg[q].key == 1u ? 1 : tile_class(seg[q].key)].push_back(w);
+                }
+            }
+            return 0;
+        };
+        // interior: one item per (tile, chunk); the field sets share the materials, so classify once and replicate
+        {
+            const int tw = s->int_lx * V, th = (32 / s->int_lx) * 8;
+            std::vector<WorkItem> items;
             for (int kc = 0; kc < g.nzc; ++kc)
                 for (unsigned ty = 0; ty < grd.y; ++ty)
                     for (unsigned tx = 0; tx < grd.x; ++tx) {
-                        const unsigned f = fl[((size_t)kc * grd.y + ty) * grd.x + tx];
-                        WorkItem w = {-1, q, g.i_lo + (int)tx * tw, g.j_lo + (int)ty * th, g.k_lo + kc * g.zchunk,
-                                      std::min(g.k_lo + (kc + 1) * g.zchunk, g.k_hi), (int)(f >> 8), 0};
-                        lst[tile_class(f)].push_back(w);
+                        const int i0 = g.i_lo + (int)tx * tw, j0 = g.j_lo + (int)ty * th;
+                        WorkItem w = {-1, 0, i0, j0, g.k_lo + kc * g.zchunk, std::min(g.k_lo + (kc + 1) * g.zchunk, g.k_hi), 0, 0,
+                                      std::min(i0 + tw, g.i_hi), std::min(j0 + th, g.j_hi)};
+                        if (w.kb < w.ke) items.push_back(w);
                     }
-        for (int a = 0; a < 4; ++a) { rc = upload(s->il_int[a], lst[a]); if (rc) return rc; }
+            std::vector<WorkItem> one[4], lst[4];
+            rc = classify(items, tw, th, one); if (rc) return rc;
+            for (int a = 0; a < 4; ++a)
+                for (int q = 0; q < s->g.n_sets; ++q)
+                    for (size_t n = 0; n < one[a].size(); ++n) { WorkItem w = one[a][n]; w.set = q; lst[a].push_back(w); }
+            for (int a = 0; a < 4; ++a) { rc = upload(s->il_int[a], lst[a]); if (rc) return rc; }
+        }
         for (int f = 0; f < 2; ++f)
             for (int wn = 0; wn < 2; ++wn) {
-                const std::vector<WorkItem> &src = s->h_items[f][wn];
-                std::vector<unsigned> f2(std::max<size_t>(src.size(), 1), 0u);
-                if (!src.empty()) {
-                    unsigned *df; CK(cudaMalloc((void **)&df, src.size() * sizeof(unsigned)));
-                    const int lxw = wn ? s->pml_lx_n : s->pml_lx;
-                    item_flags_kernel<<<(unsigned)src.size(), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->il_h[f][wn].dev,
-                        lxw * s->pml_v, (32 / lxw) * 8, s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df);
-                    CK(cudaMemcpyAsync(f2.data(), df, src.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
-                    CK(cudaStreamSynchronize(s->stream));
-                    cudaFree(df);
-                }
+                const int lxw = wn ? s->pml_lx_n : s->pml_lx;
                 std::vector<WorkItem> l2[4];
-                for (size_t i = 0; i < src.size(); ++i) { WorkItem w = src[i]; w.mat = (int)(f2[i] >> 8); l2[tile_class(f2[i])].push_back(w); }
+                rc = classify(s->h_items[f][wn], lxw * s->pml_v, (32 / lxw) * 8, l2); if (rc) return rc;
                 for (int a2 = 0; a2 < 4; ++a2) { rc = upload(s->il_pml[f][wn][a2], l2[a2]); if (rc) return rc; }
             }
     }

@@ -620,32 +620,6 @@ __global__ void __launch_bounds__(256, 1) e_interior_stg(KParams<T> p, IntGeom g
     else e_interior_stg_body<T, V, LX, NS, false, UNI>(p, g, it, kb, ke, sj_smem);
 }
 
-// flags for e_interior: one thread block per (tile, chunk); "general" when the material differs
-// from the first one anywhere in the tile or has poles
-static __global__ void tile_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, IntGeom g, int tile_w, int tile_h,
-                                  int pitch, long long plane, int kz0, int first_disp, unsigned *flags) {
-    const int kc = blockIdx.z;
-    const int kb = g.k_lo + kc * g.zchunk, ke = min(kb + g.zchunk, g.k_hi);
-    const int i_lo = g.i_lo + blockIdx.x * tile_w, j_lo = g.j_lo + blockIdx.y * tile_h;
-    const int i_hi = min(i_lo + tile_w, g.i_hi), j_hi = min(j_lo + tile_h, g.j_hi);
-    __shared__ int s_gen;
-    if (threadIdx.x == 0) s_gen = 0;
-    __syncthreads();
-    const int nx = max(i_hi - i_lo, 0), ny = max(j_hi - j_lo, 0), nz = max(ke - kb, 0);
-    const int ref = (nx && ny && nz) ? m0[(long long)(kb - kz0 + 1) * plane + (long long)j_lo * pitch + i_lo] : 0;
-    int gen = 0;
-    for (int t = threadIdx.x; t < nx * ny * nz && !gen; t += blockDim.x) {
-        const int i = i_lo + t % nx, j = j_lo + (t / nx) % ny, k = kb + t / (nx * ny);
-        const long long x = (long long)(k - kz0 + 1) * plane + (long long)j * pitch + i;
-        if (m0[x] != ref || m1[x] != ref || m2[x] != ref) gen = 1;
-    }
-    if (gen) s_gen = 1;
-    __syncthreads();
-    // bit 0: mixed materials; bit 1: one material, with poles; bits 8..: that material
-    if (threadIdx.x == 0) flags[((long long)kc * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] =
-        s_gen ? 1u : (((unsigned)ref << 8) | (ref >= first_disp ? 2u : 0u));
-}
-
 // ------------------------------------------------------------------------------------------
 // PML shell, tiled.  PD = 0: general cell (any combination of sigmas; D/B for all components, U
 // where two sigmas overlap).  PD = 1,2,3: "face" tile whose cells have a single non-zero sigma,
@@ -982,26 +956,25 @@ __global__ void __launch_bounds__(256, (V * sizeof(T) == 8) ? (NS == 0 ? (FACE ?
     else e_pml_body<T, V, LX, NS, 3, false, UNI>(p, b, it, k_lo, k_hi, chi_u, eps_u);
 }
 
-// material flags of the PML work items (one block per item)
-static __global__ void item_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, const WorkItem *items, int tile_w,
-                                  int tile_h, int n0, int n1, int pitch, long long plane, int kz0, int first_disp,
-                                  unsigned *flags) {
+// per-plane material flags of work items (one block per item): flags[item * zmax + (k - kb)] = 1 if the tile's plane k
+// holds more than one material id (over the three E components), else (id << 8) | (2 if the material has poles)
+static __global__ void plane_flags_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, const WorkItem *items, int tile_w,
+                                          int tile_h, int n0, int n1, int pitch, long long plane, int kz0, int first_disp,
+                                          unsigned *flags, int zmax) {
     const WorkItem it = items[blockIdx.x];
     const int i_hi = min(min(it.i0 + tile_w, it.i_hi), n0 + 1), j_hi = min(min(it.j0 + tile_h, it.j_hi), n1 + 1);
-    __shared__ int s_gen;
-    if (threadIdx.x == 0) s_gen = 0;
-    __syncthreads();
-    const int nx = max(i_hi - it.i0, 0), ny = max(j_hi - it.j0, 0), nz = max(it.ke - it.kb, 0);
-    const int ref = (nx && ny && nz) ? m0[(long long)(it.kb - kz0 + 1) * plane + (long long)it.j0 * pitch + it.i0] : 0;
-    int gen = 0;
-    for (int t = threadIdx.x; t < nx * ny * nz && !gen; t += blockDim.x) {
-        const int i = it.i0 + t % nx, j = it.j0 + (t / nx) % ny, k = it.kb + t / (nx * ny);
-        const long long x = (long long)(k - kz0 + 1) * plane + (long long)j * pitch + i;
-        if (m0[x] != ref || m1[x] != ref || m2[x] != ref) gen = 1;
+    const int nx = max(i_hi - it.i0, 0), ny = max(j_hi - it.j0, 0), nz = min(max(it.ke - it.kb, 0), zmax);
+    for (int kk = 0; kk < nz; ++kk) {
+        const long long base = (long long)(it.kb + kk - kz0 + 1) * plane;
+        const int ref = (nx && ny) ? m0[base + (long long)it.j0 * pitch + it.i0] : 0;
+        int gen = 0;
+        for (int t = threadIdx.x; t < nx * ny && !gen; t += blockDim.x) {
+            const long long x = base + (long long)(it.j0 + t / nx) * pitch + it.i0 + t % nx;
+            if (m0[x] != ref || m1[x] != ref || m2[x] != ref) gen = 1;
+        }
+        gen = __syncthreads_or(gen);
+        if (threadIdx.x == 0) flags[(long long)blockIdx.x * zmax + kk] = gen ? 1u : (((unsigned)ref << 8) | (ref >= first_disp ? 2u : 0u));
     }
-    if (gen) s_gen = 1;
-    __syncthreads();
-    if (threadIdx.x == 0) flags[blockIdx.x] = s_gen ? 1u : (((unsigned)ref << 8) | (ref >= first_disp ? 2u : 0u));
 }
 
 // ------------------------------------------------------------------------------------------
