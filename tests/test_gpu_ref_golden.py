@@ -114,3 +114,32 @@ def test_late_time_tail_matches_reference_driver(golden):
         assert np.abs(got[w] - ref[w]).max() <= 1e-12 * peak, (lo, np.abs(got[w] - ref[w]).max())
         assert rel_l2(got[w], ref[w]) <= 1e-6, (lo, rel_l2(got[w], ref[w]))
     assert np.abs(ref[300:]).max() < 1e-4 * peak            # no late-time growth at this resolution
+
+
+def test_production_launch_of_the_shipped_Au_SiO2_box_scene(scene_json, golden):
+    """SURVEY case P: the reference's own junctions/Au_SiO2_box scene as scripts/run.sh launches it (--grid-res 12 ->
+    217^3 cells, 3506 steps, 1600 monitors, save_span 20).  Golden: the reference's driver over the CPU oracle (every
+    20th monitor kept).  The GPU run enters through the scene fixture the reference parser produced for that launch."""
+    from helpers import settings_from_doc
+    if not os.path.exists(os.path.join(golden, "ref_Au_SiO2_box_P.npz")):
+        pytest.skip("tests/golden/ref_Au_SiO2_box_P.npz not generated (scripts/make_ref_golden.py Au_SiO2_box_P, 20 min of CPU)")
+    g = np.load(os.path.join(golden, "ref_Au_SiO2_box_P.npz"))
+    st = settings_from_doc(scene_json("Au_SiO2_box"))
+    bg = BoundGeom(st, scene_json("Au_SiO2_box"))
+    bg.run()
+    assert bg.sim.n[0] == 217 and bg.n_t_pts == 3506
+    ref = g["time"]
+    n_saves = int(g["n_time_points"][0])
+    assert bg.n_t_pts // bg.save_span == n_saves == ref.shape[0] == 175
+    got = np.stack(bg.get_field_times(), axis=1)
+    assert got.shape[1] == 1600 and len(bg.monitor_clusters) == int(g["n_clusters"][0]) == 40
+    got = got[:n_saves, ::int(g["monitor_stride"])]
+    assert np.abs(ref).max() > 1e-3
+    assert rel_l2(got, ref) <= 1e-9, rel_l2(got, ref)
+    assert np.array_equal(np.array(bg.time_bounds()), g["time_bounds"])
+    assert np.array_equal(np.array(bg.get_monitor_locs()), g["locations"])
+    from sim_juncs_b200.output import field_samples_dict
+    d = field_samples_dict(bg)
+    fr = np.stack([d[k][:, 0] + 1j * d[k][:, 1] for k in d if k.endswith("/frequency")], axis=1)[:, ::int(g["monitor_stride"])]
+    assert fr.shape == g["frequency"].shape == (128, ref.shape[1])
+    assert rel_l2(fr, g["frequency"]) <= 1e-9
