@@ -42,6 +42,7 @@ struct Node {
     bool is_group;
     std::map<std::string, Node> children;      // std::map iterates in byte order of the names, the B-tree's order
     bytes dtype, raw; uint64_t count;
+    std::vector<uint64_t> dims;                // empty: rank 1 with `count` elements
     Node() : is_group(true), count(0) {}
 };
 
@@ -64,6 +65,15 @@ public:
         d.is_group = false; d.dtype = dtype; d.count = count; d.raw.assign((const char *)data, count * item);
     }
     void dataset_f64(const std::string &path, const double *p, uint64_t n) { dataset(path, f64_type(), p, n, 8); }
+    // rank-N array of doubles, C order (the whole-grid dumps eps-*.h5 / ex-*.h5)
+    void dataset_f64_nd(const std::string &path, const double *p, const std::vector<uint64_t> &dims) {
+        uint64_t n = 1;
+        for (size_t i = 0; i < dims.size(); ++i) n *= dims[i];
+        dataset(path, f64_type(), p, n, 8);
+        const size_t cut = path.rfind('/');
+        Node &g = cut == std::string::npos ? root : group(path.substr(0, cut));
+        g.children[cut == std::string::npos ? path : path.substr(cut + 1)].dims = dims;
+    }
     void dataset_u64(const std::string &path, const uint64_t *p, uint64_t n) { dataset(path, u64_type(), p, n, 8); }
 
     int save(const char *path) {
@@ -103,7 +113,9 @@ private:
     }
     uint64_t emit_dataset(const Node &d) {
         const uint64_t addr = d.raw.empty() ? UNDEF : alloc(d.raw);
-        bytes space; put(space, 1, 1); put(space, 1, 1); put(space, 0, 6); put(space, d.count, 8);
+        bytes space; put(space, 1, 1); put(space, d.dims.empty() ? 1 : d.dims.size(), 1); put(space, 0, 6);
+        if (d.dims.empty()) put(space, d.count, 8);
+        else for (size_t i = 0; i < d.dims.size(); ++i) put(space, d.dims[i], 8);
         bytes fill; put(fill, 1, 1); put(fill, 2, 1); put(fill, 2, 1); put(fill, 1, 1); put(fill, 0, 4);
         bytes lay; put(lay, 3, 1); put(lay, 1, 1); put(lay, addr, 8); put(lay, d.raw.size(), 8);
         return object_header(message(1, space, 0) + message(3, d.dtype, 1) + message(5, fill, 1) + message(8, lay, 0), 4);

@@ -165,3 +165,37 @@ def test_custom_source_and_sample_at_equal_builtin_paths():
 
 def rel_l2_(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+@pytest.mark.skipif(not os.path.exists(MEEP_EXE), reason="host/_ref/sim_geom_meep is built where /root/reference exists")
+def test_reference_main_on_the_cuda_engine_writes_the_whole_grid_dumps(tmp_path):
+    """fields.output_hdf5 through host/meep_compat: eps-000000.00.h5 at the start of run() and, with dump_raw = 1, one
+    ex-<time>.h5 per save (disp.cpp:696, 732-737), against the same launch through the Python host (output.py)."""
+    from sim_juncs_b200 import hdf5
+    from sim_juncs_b200.settings import settings_from
+    conf = "scenes/tests/run_dump.conf"
+    a, b = str(tmp_path / "ref_main"), str(tmp_path / "py")
+    os.makedirs(a)
+    subprocess.check_output([MEEP_EXE, "--conf-file", conf, "--out-dir", a], cwd=ROOT, timeout=600)
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        st = settings_from(conf, ["--out-dir", b])
+        bg = BoundGeom(st, None)
+        bg.run(b)
+    finally:
+        os.chdir(cwd)
+    fa = sorted(f for f in os.listdir(a) if f.endswith(".h5") and f != "field_samples.h5")
+    fb = sorted(f for f in os.listdir(b) if f.endswith(".h5") and f != "field_samples.h5")
+    assert fa == fb and "eps-000000.00.h5" in fa and len(fa) == 1 + (bg.n_t_pts + 39) // 40
+    eps_a, eps_b = hdf5.File(os.path.join(a, "eps-000000.00.h5"))["eps"].read(), hdf5.File(os.path.join(b, "eps-000000.00.h5"))["eps"].read()
+    n = st.grid_cells()
+    assert eps_a.shape == (n, n, n) and np.array_equal(eps_a, eps_b) and eps_a.min() == 1.0 and eps_a.max() == 3.5
+    seen = 0.0
+    for f in fa[1:]:
+        for ds in ("ex.r", "ex.i"):
+            x, y = hdf5.File(os.path.join(a, f))[ds].read(), hdf5.File(os.path.join(b, f))[ds].read()
+            assert x.shape == (n, n, n)
+            assert np.abs(x - y).max() <= 1e-12 * max(np.abs(y).max(), 1e-30), (f, ds)
+            seen = max(seen, np.abs(y).max())
+    assert seen > 1e-9
