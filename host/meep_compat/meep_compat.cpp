@@ -10,7 +10,7 @@
 
 #include "meep.hpp"
 #include "sim_juncs_b200.h"
-#include "../sj_hdf5.hpp"
+#include "../sj_dumps.hpp"
 
 namespace meep {
 
@@ -160,57 +160,19 @@ double fields::last_source_time() {
 }
 void fields::set_output_directory(const char *dir) { outdir = dir ? dir : ""; }
 volume fields::total_volume() const { return strct->gv.surroundings(); }
-// An E-component Yee array [k][j][i] of (n+1)^3 points -> n^3 values at the pixel centres, x slowest (meep's output grid and
-// axis order): the mean of the four Yee points of that component around each centre (same expression order as
-// sim_juncs_b200/output.py centred(); meep's own interpolation is recalled, not pinned).
-static std::vector<double> centred(const std::vector<double> &a, const int n[3], int comp) {
-    const size_t sx = n[0] + 1, sy = n[1] + 1;
-    std::vector<double> out((size_t)n[0] * n[1] * n[2]);
-    auto at = [&](int k, int j, int i) { return a[((size_t)k * sy + j) * sx + i]; };
-    for (int i = 0; i < n[0]; ++i)
-        for (int j = 0; j < n[1]; ++j)
-            for (int k = 0; k < n[2]; ++k) {
-                double v;
-                if (comp == 0) v = 0.25 * (((at(k, j, i) + at(k + 1, j, i)) + at(k, j + 1, i)) + at(k + 1, j + 1, i));
-                else if (comp == 1) v = 0.25 * (((at(k, j, i) + at(k + 1, j, i)) + at(k, j, i + 1)) + at(k + 1, j, i + 1));
-                else v = 0.25 * (((at(k, j, i) + at(k, j + 1, i)) + at(k, j, i + 1)) + at(k, j + 1, i + 1));
-                out[((size_t)i * n[1] + j) * n[2] + k] = v;
-            }
-    return out;
-}
-
-// fields.output_hdf5(meep::Dielectric, total_volume) (disp.cpp:696) -> <outdir>/eps-000000.00.h5, dataset "eps" =
-// 3 / sum_c <1 / eps_c> at the pixel centres; fields.output_hdf5(meep::Ex, vol.surroundings(), file) (disp.cpp:735) ->
-// <outdir>/<file>.h5 with "ex.r" and "ex.i".  File and dataset names as meep writes them (recalled).
+// fields.output_hdf5(meep::Dielectric, total_volume) (disp.cpp:696) -> <outdir>/eps-000000.00.h5; fields.output_hdf5(meep::Ex,
+// vol.surroundings(), file) (disp.cpp:735) -> <outdir>/<file>.h5 with "ex.r" and "ex.i" (host/sj_dumps.hpp)
 void fields::output_hdf5(component c, const volume &, h5file *file) {
     const int *n = strct->gv.n;
-    const std::vector<uint64_t> dims = {(uint64_t)n[0], (uint64_t)n[1], (uint64_t)n[2]};
     const std::string dir = outdir.empty() ? std::string(".") : outdir;
-    sj_h5::Writer w;
     if (c == Dielectric) {
-        std::vector<double> tr((size_t)n[0] * n[1] * n[2], 0.0);
-        for (int q = 0; q < 3; ++q) {
-            std::vector<double> inv(strct->eps[q].size());
-            for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / strct->eps[q][i];
-            const std::vector<double> cq = centred(inv, n, q);
-            for (size_t i = 0; i < tr.size(); ++i) tr[i] = tr[i] + cq[i];
-        }
-        for (size_t i = 0; i < tr.size(); ++i) tr[i] = 3.0 / tr[i];
-        w.dataset_f64_nd("eps", tr.data(), dims);
-        if (w.save((dir + "/eps-000000.00.h5").c_str())) throw std::runtime_error("meep_compat: cannot write eps-000000.00.h5");
+        if (sj_dump::write_eps(dir, strct->eps, n)) throw std::runtime_error("meep_compat: cannot write eps-000000.00.h5");
         return;
     }
     if (!is_electric(c)) throw std::runtime_error("meep_compat: output_hdf5 of Dielectric and E components only");
-    const int comp = component_index(c);
     static const char *nm[3] = {"ex", "ey", "ez"};
-    std::vector<double> raw((size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1));
-    for (int set = 0; set < 2; ++set) {
-        ck(sj_get_field(sim, comp, set, raw.data()), sim, "sj_get_field");
-        const std::vector<double> cq = centred(raw, n, comp);
-        w.dataset_f64_nd(std::string(nm[comp]) + (set ? ".i" : ".r"), cq.data(), dims);
-    }
-    const std::string name = file ? file->name : std::string(nm[comp]);
-    if (w.save((dir + "/" + name + ".h5").c_str())) throw std::runtime_error("meep_compat: cannot write " + name + ".h5");
+    const std::string name = file ? file->name : std::string(nm[component_index(c)]);
+    if (sj_dump::write_field(dir + "/" + name + ".h5", sim, component_index(c), 2, n)) throw std::runtime_error("meep_compat: cannot write " + name + ".h5");
 }
 h5file *fields::open_h5file(const char *name) { return new h5file(name ? name : ""); }
 

@@ -2,9 +2,10 @@
 // loop cadence are those of reference src/disp.cpp:482-749; every meep call is replaced by an sj_* call.
 #include <algorithm>
 #include "sj_host.hpp"
-#include "sj_hdf5.hpp"
+#include "sj_dumps.hpp"
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,7 +109,7 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
     : problem(s.geom_fname, sj_context_from_settings(s), ercode), sim(NULL) {
     if (ercode && *ercode != E_SUCCESS) { printf("Scene parsing failed, exiting.\n"); exit(1); }
     um_scale = s.um_scale; post_source_t = s.post_source_t; save_span = s.save_span; n_sets = p_n_sets;
-    ttot = 0; n_t_pts = 0; raster_ms = run_s = 0;
+    ttot = 0; n_t_pts = 0; raster_ms = run_s = 0; dump_raw = s.dump_raw;
     if (s.n_dims != 3) { fprintf(stderr, "only dimensions = 3 is supported\n"); exit(1); }
     printf("using simulation side length %f, resolution %f\n", s.len, s.resolution);
 
@@ -116,7 +117,7 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
     sj_grid g;
     memset(&g, 0, sizeof g);
     const int n = (int)(2 * z_center * s.resolution + 0.5);          // meep::vol3d
-    g.n[0] = g.n[1] = g.n[2] = n; g.a = s.resolution; g.courant = 0.5; g.pml_thickness = s.pml_thickness; g.pml_R = 1e-15;
+    g.n[0] = g.n[1] = g.n[2] = n; n_cells[0] = n_cells[1] = n_cells[2] = n; g.a = s.resolution; g.courant = 0.5; g.pml_thickness = s.pml_thickness; g.pml_R = 1e-15;
     g.precision = precision; g.n_sets = n_sets; g.device = -1;
     if (sj_create(&g, &sim)) { fprintf(stderr, "sj_create: %s\n", sj_last_error(sim)); exit(1); }
 
@@ -218,7 +219,23 @@ int sj_bound_geom::run(const char *fname_prefix) {
     n_t_pts = (unsigned)((ttot + dt / 2) / dt);
     printf("starting simulations\n");
     auto t0 = std::chrono::steady_clock::now();
-    int rc = sj_run(sim, n_t_pts, save_span);
+    int rc = 0;
+    if (fname_prefix && sj_dump::write_eps_from_sim(fname_prefix, sim, n_cells))      // fields.output_hdf5(Dielectric), disp.cpp:696
+        printf("warning: could not write %s/eps-000000.00.h5\n", fname_prefix);
+    if (dump_raw && fname_prefix) {
+        // disp.cpp:709-737: at every save point the whole Ex field goes to ex-<time>.h5 before the step
+        const int n_digits_a = (int)(ceil(log(ttot) / log(10)));
+        const int n_digits_b = (int)ceil(-log((double)dt) / log(10.0)) + 1;
+        char h5_fname[BUF_SIZE];
+        strcpy(h5_fname, "ex-");
+        for (unsigned done = 0; done < n_t_pts && !rc; done += save_span) {
+            make_dec_str(h5_fname + 3, BUF_SIZE - 3, done * dt, n_digits_a, n_digits_b);
+            if (sj_dump::write_field(std::string(fname_prefix) + "/" + h5_fname + ".h5", sim, SJ_EX, n_sets, n_cells))
+                printf("warning: could not write %s\n", h5_fname);
+            rc = sj_run(sim, std::min(save_span, n_t_pts - done), save_span);
+            if (rc == SJ_ERR_DIVERGED) rc = 0;
+        }
+    } else rc = sj_run(sim, n_t_pts, save_span);
     if (!rc) rc = sj_sync(sim);
     if (rc == SJ_ERR_DIVERGED) printf("divergence in run (%s)\n", sj_last_error(sim));
     else if (rc) { printf("error in run: %s\n", sj_last_error(sim)); return rc; }

@@ -59,6 +59,8 @@ private:
     double um_scale, post_source_t;
     unsigned save_span;
     int n_sets;
+    bool dump_raw;
+    int n_cells[3];
 };
 
 context sj_context_from_settings(const parse_settings &args);

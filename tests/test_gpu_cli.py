@@ -168,15 +168,17 @@ def rel_l2_(a, b):
 
 
 @pytest.mark.skipif(not os.path.exists(MEEP_EXE), reason="host/_ref/sim_geom_meep is built where /root/reference exists")
-def test_reference_main_on_the_cuda_engine_writes_the_whole_grid_dumps(tmp_path):
-    """fields.output_hdf5 through host/meep_compat: eps-000000.00.h5 at the start of run() and, with dump_raw = 1, one
-    ex-<time>.h5 per save (disp.cpp:696, 732-737), against the same launch through the Python host (output.py)."""
+@pytest.mark.parametrize("exe", [MEEP_EXE, EXE])
+def test_cpp_hosts_write_the_whole_grid_dumps(exe, tmp_path):
+    """fields.output_hdf5 through host/meep_compat (the reference's main.cpp) and in the own C++ host: eps-000000.00.h5 at
+    the start of run() and, with dump_raw = 1, one ex-<time>.h5 per save (disp.cpp:696, 732-737), against the same launch
+    through the Python host (output.py)."""
     from sim_juncs_b200 import hdf5
     from sim_juncs_b200.settings import settings_from
     conf = "scenes/tests/run_dump.conf"
     a, b = str(tmp_path / "ref_main"), str(tmp_path / "py")
     os.makedirs(a)
-    subprocess.check_output([MEEP_EXE, "--conf-file", conf, "--out-dir", a], cwd=ROOT, timeout=600)
+    subprocess.check_output([exe, "--conf-file", conf, "--out-dir", a], cwd=ROOT, timeout=600)
     cwd = os.getcwd()
     os.chdir(ROOT)
     try:
