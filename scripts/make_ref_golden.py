@@ -32,13 +32,17 @@ CASES = {
     "graphene_long": ("scenes/tests/graphene_long.conf", []),           # 5965 steps: late-time ringing, long after the pulse
     # the reference's own production launch (scripts/run.sh:78): its shipped Au_SiO2_box scene at --grid-res 12, 217^3 cells,
     # 3506 steps, 1600 monitors (about 20 minutes of CPU); the GPU test enters through scenes/json/Au_SiO2_box.json
+    # the reference's shipped bowtie scene (BASELINE config 3) on a coarse grid, 73^3
+    "bowtie_res4": ("/root/reference/junctions/Au_SiO2_bowtie/params.conf",
+                    ["--geom-file", "/root/reference/junctions/Au_SiO2_bowtie/junc.geom", "--grid-res", "4.0",
+                     "--opts", "width=0.05;thick=0.2;inf_thick=0;wavelen=0.76;n_cycles=0.5"]),
     "Au_SiO2_box_P": ("/root/reference/junctions/Au_SiO2_box/params.conf",
                       ["--geom-file", "/root/reference/junctions/Au_SiO2_box/junc.geom", "--grid-res", "12.0",
                        "--opts", "width=0.05;thick=0.2;inf_thick=0;wavelen=0.76;n_cycles=0.5"]),
 }
 
 
-MONITOR_STRIDE = {"graphene_long": 5, "Au_SiO2_box_P": 20}
+MONITOR_STRIDE = {"graphene_long": 5, "Au_SiO2_box_P": 20, "bowtie_res4": 20}
 
 
 def load_existing(out_dir):

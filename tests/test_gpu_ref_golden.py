@@ -143,3 +143,26 @@ def test_production_launch_of_the_shipped_Au_SiO2_box_scene(scene_json, golden):
     fr = np.stack([d[k][:, 0] + 1j * d[k][:, 1] for k in d if k.endswith("/frequency")], axis=1)[:, ::int(g["monitor_stride"])]
     assert fr.shape == g["frequency"].shape == (128, ref.shape[1])
     assert rel_l2(fr, g["frequency"]) <= 1e-9
+
+
+def test_shipped_bowtie_scene_on_a_coarse_grid(scene_json, golden):
+    """BASELINE config 3: the reference's junctions/Au_SiO2_bowtie scene (rotated boxes, cylinders, 1600 monitors) as
+    `--grid-res 4 --opts "width=0.05;..."` launches it (73^3 cells).  Golden: the reference's driver over the CPU oracle,
+    every 20th monitor; the GPU run enters through the reference parser's fixture with the same grid."""
+    from helpers import settings_from_doc
+    g = np.load(os.path.join(golden, "ref_bowtie_res4.npz"))
+    st = settings_from_doc(scene_json("Au_SiO2_bowtie"))
+    st.grid_num = 73
+    st.resolution = 73 / 18.0          # argparse.h:171-191 for --grid-res 4.0: odd grid number over the total length
+    bg = BoundGeom(st, scene_json("Au_SiO2_bowtie"))
+    bg.run()
+    ref = g["time"]
+    n_saves = int(g["n_time_points"][0])
+    assert bg.sim.n[0] == 73 and bg.n_t_pts // bg.save_span == n_saves == ref.shape[0]
+    got = np.stack(bg.get_field_times(), axis=1)
+    assert got.shape[1] == 1600
+    got = got[:n_saves, ::int(g["monitor_stride"])]
+    assert np.abs(ref).max() > 1e-3
+    assert rel_l2(got, ref) <= 1e-9, rel_l2(got, ref)
+    assert np.array_equal(np.array(bg.time_bounds()), g["time_bounds"])
+    assert np.array_equal(np.array(bg.get_monitor_locs()), g["locations"])

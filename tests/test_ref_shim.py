@@ -38,6 +38,20 @@ def _python_host_on_oracle(conf, extra=()):
     return st, scene, o, n_t_pts, ser[:, :, 0] + 1j * ser[:, :, 1]
 
 
+RUN_SH_OPTS = "width=0.05;thick=0.2;inf_thick=0;wavelen=0.76;n_cycles=0.5"       # reference scripts/run.sh:76-78
+BOWTIE = ("/root/reference/junctions/Au_SiO2_bowtie/params.conf",
+          ("--geom-file", "/root/reference/junctions/Au_SiO2_bowtie/junc.geom", "--grid-res", "4.0", "--opts", RUN_SH_OPTS))
+
+
+def test_shipped_bowtie_scene_reference_driver_equals_python_host(tmp_path):
+    """BASELINE config 3: the reference's own junctions/Au_SiO2_bowtie scene (rotated boxes, cylinders, --opts overrides,
+    1600 monitors) on a coarse grid (--grid-res 4 -> 73^3): the reference's driver against settings.py + cgs.py + scene.py
+    over the same engine, eps, sigma and series bit for bit."""
+    if not os.path.exists(BOWTIE[0]):
+        pytest.skip("needs /root/reference")
+    test_reference_driver_equals_python_host(BOWTIE[0], BOWTIE[1], tmp_path)
+
+
 @pytest.mark.parametrize("conf,extra", [("scenes/tests/run.conf", ()), ("scenes/tests/cw_slab.conf", ()),
                                         ("scenes/tests/graphene_short.conf", ("--grid-res", "2.5")),
                                         ("scenes/tests/run_smooth.conf", ()), ("scenes/tests/graphene_smooth.conf", ())])
