@@ -172,7 +172,7 @@ def test_phase_batch_against_reference_driver(golden):
     """BASELINE config 5: quartz_box run as a CEP phase batch (one real field set per phase, shared materials).  The sets
     for phase 0 and pi/2 are the real and imaginary parts of the complex run -- here checked against the series the
     reference's own driver produced for that scene (complex fields, as meep runs them)."""
-    g = np.load(os.path.join(golden, "ref_quartz_res3.npz"))
+    g = np.load(os.path.join(golden, "ref_quartz_res6.npz"))
     cwd = os.getcwd()
     os.chdir(ROOT)
     try:
