@@ -92,12 +92,25 @@ MEEP_EXE = os.path.join(ROOT, "host", "_ref", "sim_geom_meep")
 @pytest.mark.parametrize("name", ["run_slabs", "cw_slab", "graphene_res2p5", "graphene_smooth2"])
 def test_unmodified_reference_main_on_the_cuda_engine(name, tmp_path, golden):
     """main.cpp + disp.cpp + cgs*.cpp + data_utils.cpp of the reference, unmodified, linked against host/meep_compat
-    (meep API slice on the C ABI) instead of libmeep: same command line, the series it writes to field_samples.h5 must be
-    the ones the same sources produce over the CPU oracle (tests/golden/ref_*.npz) to <= 1e-9."""
+    (meep API slice on the C ABI) instead of libmeep."""
+    _cli_against_reference_golden(MEEP_EXE, name, tmp_path, golden)
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="host/_ref/sim_geom is built where /root/reference exists")
+@pytest.mark.parametrize("name", ["cw_slab", "graphene_smooth2"])
+def test_own_cpp_host_against_reference_driver(name, tmp_path, golden):
+    """host/sim_geom (reference front end + GPU rasterizer, incl. smooth_n > 0) on the same launch lines."""
+    _cli_against_reference_golden(EXE, name, tmp_path, golden)
+
+
+def _cli_against_reference_golden(exe, name, tmp_path, golden):
+    """A C++ binary on the engine, launched with the reference's command line: the series, spectra, locations, time bounds
+    and source records it writes to field_samples.h5 must be the ones the reference's own sources produce over the CPU
+    oracle (tests/golden/ref_*.npz), series and spectra to <= 1e-9."""
     from helpers import rel_l2
     from sim_juncs_b200 import hdf5
     g = np.load(os.path.join(golden, "ref_%s.npz" % name))
-    argv = [MEEP_EXE, "--conf-file", str(g["conf"]), "--out-dir", str(tmp_path)] + [str(a) for a in g["argv"]]
+    argv = [exe, "--conf-file", str(g["conf"]), "--out-dir", str(tmp_path)] + [str(a) for a in g["argv"]]
     out = subprocess.check_output(argv, cwd=ROOT, timeout=900).decode()
     assert "finished writing hdf5 file!" in out
     f = hdf5.File(os.path.join(str(tmp_path), "field_samples.h5"))
