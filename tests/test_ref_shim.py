@@ -52,6 +52,16 @@ def test_shipped_bowtie_scene_reference_driver_equals_python_host(tmp_path):
     test_reference_driver_equals_python_host(BOWTIE[0], BOWTIE[1], tmp_path)
 
 
+def test_reference_own_test_scene_c1(tmp_path):
+    """BASELINE config 0 literally: the reference's tests/run.conf + tests/run.geom (brace-form geometry = a root without
+    children = vacuum) with the sizes its unit test uses (main_test.cpp:1884-1899: length 2, resolution 5)."""
+    conf = "/root/reference/tests/run.conf"
+    if not os.path.exists(conf):
+        pytest.skip("needs /root/reference")
+    test_reference_driver_equals_python_host(conf, ("--geom-file", "/root/reference/tests/run.geom", "--length", "2.0",
+                                                    "--grid-res", "5.0"), tmp_path)
+
+
 @pytest.mark.parametrize("conf,extra", [("scenes/tests/run.conf", ()), ("scenes/tests/cw_slab.conf", ()),
                                         ("scenes/tests/graphene_short.conf", ("--grid-res", "2.5")),
                                         ("scenes/tests/run_smooth.conf", ()), ("scenes/tests/graphene_smooth.conf", ())])
