@@ -246,6 +246,10 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
                 if (!v.empty()) CK(cudaMemcpy(s->il_h[f][w].dev, v.data(), v.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
             }
     }
+    {   // TMA-staged kernels (sj_tma.cuh): SJ_TMA bit 0 = H-pass, bit 1 = E-pass
+        s->tma.mode = getenv("SJ_TMA") ? atoi(getenv("SJ_TMA")) : 3;
+        int rc = sj_tma_build_geometry(s); if (rc) return rc;
+    }
     // default material table: vacuum
     {
         sj_material vac; memset(&vac, 0, sizeof vac); vac.eps_inf = 1.0;
@@ -267,6 +271,7 @@ extern "C" void sj_destroy(sj_sim *s) {
     for (int a = 0; a < 4; ++a) cudaFree(s->il_int[a].dev);
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { cudaFree(s->il_h[a][b].dev); for (int c = 0; c < 4; ++c) cudaFree(s->il_pml[a][b][c].dev); }
     cudaFree(s->Pall); cudaFree(s->src_dev);
+    sj_tma_free(s);
     for (auto &B : s->boxes) cudaFree(B.base);
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
     cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
@@ -379,6 +384,73 @@ void sj_interior_geom(const sj_sim *s, int k_begin, int k_end, IntGeom &g, dim3 
     grd = dim3((ni + tw - 1) / tw, (nj + th - 1) / th, std::max(g.nzc, 0) * s->g.n_sets);
 }
 
+// Material class of every work item, split along z (used by the register kernels' lists and by the TMA schedules).
+// class of a tile plane from its flag word (plane_flags_kernel): mixed -> 1; one material without poles -> 0; one
+// material with 1 or 2 poles -> 2 / 3 (SJ_NO_UNI=1 sends those through the general path too).
+// Every (tile, z-chunk) item is cut along z into runs of planes that hold one material (fast paths: no material
+// bytes, coefficients in registers) and runs that do not (general path).  Material interfaces in these scenes are
+// mostly horizontal, so a chunk that straddles one is uniform above and below it.  Uniform runs shorter than
+// `min_run` planes are not worth a block of their own and join the neighbouring general run.  The arithmetic of
+// the paths is identical, so the split changes nothing but speed.  SJ_ZSPLIT=0: classify whole items.
+int sj_classify_items(sj_sim *s, const std::vector<WorkItem> &items, int tile_w, int tile_h, std::vector<WorkItem> (&out)[4]) {
+    static const bool uni_on = getenv("SJ_NO_UNI") == NULL;
+    auto tile_class = [&](unsigned f) -> int {
+        if (f & 1u) return 1;
+        if (!(f & 2u)) return 0;
+        const int np = s->mats_sorted[f >> 8].n_poles;
+        return (uni_on && np >= 1 && np <= 2 && s->n_slots <= 2) ? 1 + np : 1;
+    };
+    static const int min_run = getenv("SJ_ZSPLIT") ? atoi(getenv("SJ_ZSPLIT")) : 3;
+    const int ZMAX = 64;
+    if (items.empty()) return 0;
+    WorkItem *ditems; unsigned *df;
+    CK(cudaMalloc((void **)&ditems, items.size() * sizeof(WorkItem)));
+    CK(cudaMalloc((void **)&df, items.size() * ZMAX * sizeof(unsigned)));
+    CK(cudaMemcpyAsync(ditems, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s->stream));
+    plane_flags_kernel<<<(unsigned)items.size(), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], ditems, tile_w, tile_h,
+        s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df, ZMAX);
+    std::vector<unsigned> fl(items.size() * ZMAX);
+    CK(cudaMemcpyAsync(fl.data(), df, fl.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaGetLastError());
+    cudaFree(ditems); cudaFree(df);
+    struct Seg { int kb, ke; unsigned key; };       // key 1 = general, else the flag word of a uniform run
+    for (size_t n = 0; n < items.size(); ++n) {
+        const WorkItem &it = items[n];
+        const int nz = it.ke - it.kb;
+        std::vector<Seg> seg;
+        if (nz > ZMAX || min_run <= 0) {            // whole item: uniform only if every plane agrees
+            unsigned key = nz > 0 && nz <= ZMAX ? fl[n * ZMAX] : 1u;
+            if (tile_class(key) == 1) key = 1u;
+            for (int kk = 1; kk < nz && nz <= ZMAX && key != 1u; ++kk) if (fl[n * ZMAX + kk] != key) key = 1u;
+            seg.push_back(Seg{it.kb, it.ke, key});
+        } else {
+            for (int kk = 0; kk < nz; ++kk) {
+                unsigned key = fl[n * ZMAX + kk];
+                if (tile_class(key) == 1) key = 1u;
+                if (!seg.empty() && seg.back().key == key) seg.back().ke = it.kb + kk + 1;
+                else seg.push_back(Seg{it.kb + kk, it.kb + kk + 1, key});
+            }
+            if (seg.size() > 1) {
+                for (size_t q = 0; q < seg.size(); ++q) if (seg[q].key != 1u && seg[q].ke - seg[q].kb < min_run) seg[q].key = 1u;
+                std::vector<Seg> merged;
+                for (size_t q = 0; q < seg.size(); ++q) {
+                    if (!merged.empty() && merged.back().key == seg[q].key) merged.back().ke = seg[q].ke;
+                    else merged.push_back(seg[q]);
+                }
+                seg.swap(merged);
+            }
+        }
+        for (size_t q = 0; q < seg.size(); ++q) {
+            WorkItem w = it;
+            w.kb = seg[q].kb; w.ke = seg[q].ke;
+            w.mat = seg[q].key == 1u ? 0 : (int)(seg[q].key >> 8);
+            out[seg[q].key == 1u ? 1 : tile_class(seg[q].key)].push_back(w);
+        }
+    }
+    return 0;
+}
+
 int sj_finish_materials(sj_sim *s) {
     graph_drop(s);                      // work lists and material tables are rebuilt below
     // sort the table: non-dispersive materials first, so "has poles" is a compare, not a load
@@ -425,70 +497,8 @@ int sj_finish_materials(sj_sim *s) {
             if (!v.empty()) CK(cudaMemcpy(L.dev, v.data(), v.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
             return 0;
         };
-        // class of a tile plane from its flag word (plane_flags_kernel): mixed -> 1; one material without poles -> 0; one
-        // material with 1 or 2 poles -> 2 / 3 (SJ_NO_UNI=1 sends those through the general path too)
-        static const bool uni_on = getenv("SJ_NO_UNI") == NULL;
-        auto tile_class = [&](unsigned f) -> int {
-            if (f & 1u) return 1;
-            if (!(f & 2u)) return 0;
-            const int np = s->mats_sorted[f >> 8].n_poles;
-            return (uni_on && np >= 1 && np <= 2 && s->n_slots <= 2) ? 1 + np : 1;
-        };
-        // Split every (tile, z-chunk) item along z into runs of planes that hold one material (fast paths: no material
-        // bytes, coefficients in registers) and runs that do not (general path).  Material interfaces in these scenes are
-        // mostly horizontal, so a chunk that straddles one is uniform above and below it.  Uniform runs shorter than
-        // `min_run` planes are not worth a block of their own and join the neighbouring general run.  The arithmetic of
-        // the paths is identical, so the split changes nothing but speed.  SJ_ZSPLIT=0: classify whole items.
-        static const int min_run = getenv("SJ_ZSPLIT") ? atoi(getenv("SJ_ZSPLIT")) : 3;
-        const int ZMAX = 64;
         auto classify = [&](const std::vector<WorkItem> &items, int tile_w, int tile_h, std::vector<WorkItem> (&out)[4]) -> int {
-            if (items.empty()) return 0;
-            WorkItem *ditems; unsigned *df;
-            CK(cudaMalloc((void **)&ditems, items.size() * sizeof(WorkItem)));
-            CK(cudaMalloc((void **)&df, items.size() * ZMAX * sizeof(unsigned)));
-            CK(cudaMemcpyAsync(ditems, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s->stream));
-            plane_flags_kernel<<<(unsigned)items.size(), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], ditems, tile_w, tile_h,
-                s->g.n[0], s->g.n[1], s->pitch, s->plane, s->kz0, s->first_disp, df, ZMAX);
-            std::vector<unsigned> fl(items.size() * ZMAX);
-            CK(cudaMemcpyAsync(fl.data(), df, fl.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
-            CK(cudaStreamSynchronize(s->stream));
-            CK(cudaGetLastError());
-            cudaFree(ditems); cudaFree(df);
-            struct Seg { int kb, ke; unsigned key; };       // key 1 = general, else the flag word of a uniform run
-            for (size_t n = 0; n < items.size(); ++n) {
-                const WorkItem &it = items[n];
-                const int nz = it.ke - it.kb;
-                std::vector<Seg> seg;
-                if (nz > ZMAX || min_run <= 0) {            // whole item: uniform only if every plane agrees
-                    unsigned key = nz > 0 && nz <= ZMAX ? fl[n * ZMAX] : 1u;
-                    if (tile_class(key) == 1) key = 1u;
-                    for (int kk = 1; kk < nz && nz <= ZMAX && key != 1u; ++kk) if (fl[n * ZMAX + kk] != key) key = 1u;
-                    seg.push_back(Seg{it.kb, it.ke, key});
-                } else {
-                    for (int kk = 0; kk < nz; ++kk) {
-                        unsigned key = fl[n * ZMAX + kk];
-                        if (tile_class(key) == 1) key = 1u;
-                        if (!seg.empty() && seg.back().key == key) seg.back().ke = it.kb + kk + 1;
-                        else seg.push_back(Seg{it.kb + kk, it.kb + kk + 1, key});
-                    }
-                    if (seg.size() > 1) {
-                        for (size_t q = 0; q < seg.size(); ++q) if (seg[q].key != 1u && seg[q].ke - seg[q].kb < min_run) seg[q].key = 1u;
-                        std::vector<Seg> merged;
-                        for (size_t q = 0; q < seg.size(); ++q) {
-                            if (!merged.empty() && merged.back().key == seg[q].key) merged.back().ke = seg[q].ke;
-                            else merged.push_back(seg[q]);
-                        }
-                        seg.swap(merged);
-                    }
-                }
-                for (size_t q = 0; q < seg.size(); ++q) {
-                    WorkItem w = it;
-                    w.kb = seg[q].kb; w.ke = seg[q].ke;
-                    w.mat = seg[q].key == 1u ? 0 : (int)(seg[q].key >> 8);
-                    out[seg[q].key == 1u ? 1 : tile_class(seg[q].key)].push_back(w);
-                }
-            }
-            return 0;
+            return sj_classify_items(s, items, tile_w, tile_h, out);
         };
         // interior: one item per (tile, chunk); the field sets share the materials, so classify once and replicate
         {
@@ -517,6 +527,7 @@ int sj_finish_materials(sj_sim *s) {
                 for (int a2 = 0; a2 < 4; ++a2) { rc = upload(s->il_pml[f][wn][a2], l2[a2]); if (rc) return rc; }
             }
     }
+    rc = sj_tma_build_materials(s); if (rc) return rc;
     s->materials_set = true;
     return 0;
 }
@@ -809,6 +820,10 @@ static int ensure_series(sj_sim *s, int need) {
 
 // ---- kernel parameter assembly + launches ------------------------------------------------------
 static int do_pass(sj_sim *s, int which, int k0, int k1, cudaStream_t st) {
+    // whole-slab passes go through the TMA-staged column kernels (sj_tma.cuh); plane-restricted ones and scenes with more
+    // than two pole slots through the register kernels
+    if (((s->tma.mode >> which) & 1) && k0 <= s->kz0 && k1 >= s->kz1 && (which == 0 || s->n_slots <= 2) && !s->trace_reg)
+        return s->prec == SJ_F64 ? sj_tma_pass_f64(s, which, st) : sj_tma_pass_f32(s, which, st);
     return s->prec == SJ_F64 ? sj_launch_pass_f64(s, which, k0, k1, st) : sj_launch_pass_f32(s, which, k0, k1, st);
 }
 

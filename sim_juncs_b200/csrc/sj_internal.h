@@ -79,8 +79,25 @@ struct PmlBoxSet { PmlBox<T> b[SJ_N_PML_BOX]; };
 // one thread block of a PML tile kernel: a (tile_w x tile_h) column of box `box`, planes [kb,ke)
 // box: PML box (-1 interior); [i0,i_hi) x [j0,j_hi): the tile clipped to its rectangle; mat: uniform material id
 // (fast-path lists); kind: 0 general PML cell, 1/2/3 face tile with normal x/y/z
-struct WorkItem { int box, set, i0, j0, kb, ke, mat, kind, i_hi, j_hi; };
+// shape: tile shape index of the TMA-staged kernels (sj_tma.cuh)
+struct WorkItem { int box, set, i0, j0, kb, ke, mat, kind, i_hi, j_hi, shape, pad; };
 struct ItemList { WorkItem *dev; int n; };
+
+// ---- TMA-staged column kernels (sj_tma.cuh): tile shapes, tensor maps, per-block item schedules ----------------
+#define SJ_TMA_MAX_SHAPES 12
+struct TShape { int nvx, th, tw, hp; };   // vectors per tile row, tile rows, tile width and halo-box row pitch in elements
+struct TmaList { WorkItem *items; int *first; int n_items, grid; double bytes; };   // first: [grid + 1] CSR over blocks
+struct TmaState {
+    int mode = 0;                 // bit 0: H-pass through the TMA kernels, bit 1: E-pass
+    int nt = 224;                 // consumer threads per block the shapes were sized for
+    int n_shapes = 0;
+    TShape shapes[SJ_TMA_MAX_SHAPES];
+    void *maps = nullptr;         // CUtensorMap[n_shapes][SJ_TMAP_PER_SHAPE] in device memory
+    std::vector<WorkItem> geo[2]; // geometry items of one field set before material classification: [class A | general]
+    TmaList h[2] = {};            // H-pass: [class A (interior + faces) | general (edges, corners)]
+    TmaList e[2][4] = {};         // E-pass: same split x material class (0: one non-dispersive material, 1: mixed,
+                                  //         2 / 3: one material with 1 / 2 poles)
+};
 
 struct MonDev {
     int n_mon;
@@ -174,6 +191,8 @@ struct sj_sim {
     double pole_points;       // sum over E component points of n_poles (owned slab)
     double pole_points_int;   // same, restricted to the interior-kernel box
     double pml_cells;
+    TmaState tma;
+    bool trace_reg = false;   // force the register kernels (profiling the old path)
     std::string err;
 };
 
@@ -195,6 +214,13 @@ int sj_launch_pass_f64(sj_sim *s, int which, int k0, int k1, cudaStream_t st);
 int sj_launch_pass_f32(sj_sim *s, int which, int k0, int k1, cudaStream_t st);
 int sj_profile_f64(sj_sim *s, int reps, double out[4]);
 int sj_profile_f32(sj_sim *s, int reps, double out[4]);
+// sj_tma_host.cu / sj_tma_f64.cu / sj_tma_f32.cu
+int sj_classify_items(sj_sim *s, const std::vector<WorkItem> &items, int tile_w, int tile_h, std::vector<WorkItem> (&out)[4]);
+int sj_tma_build_geometry(sj_sim *s);          // shapes + geometry items + H-pass schedules (once, at create)
+int sj_tma_build_materials(sj_sim *s);         // tensor maps + E-pass schedules (after every material upload)
+void sj_tma_free(sj_sim *s);
+int sj_tma_pass_f64(sj_sim *s, int which, cudaStream_t st);
+int sj_tma_pass_f32(sj_sim *s, int which, cudaStream_t st);
 // sj_raster.cu
 int sj_raster_launch(sj_sim *s, double ambient_eps, int n_nodes, const sj_csg_node *nodes, int n_regions,
                      const sj_region *regions, int smooth_n, double smooth_rad);

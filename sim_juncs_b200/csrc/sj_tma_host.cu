@@ -1,0 +1,237 @@
+// sj_tma_host.cu -- host side of the TMA-staged column kernels (sj_tma.cuh): tile shapes per region, CUtensorMap
+// descriptors of the field / polarisation / PML-box allocations, work items and the static per-block schedules.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <queue>
+
+#include "sj_tma.cuh"
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = NULL;
+    if (!fn) {
+        void *p = NULL;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// rank-3 map over an allocation stored [unit][row][x]: dim0 = pitch elements, dim1 = rows, dim2 = units (planes of all
+// arrays and sets back to back); box = (bw, bh, 1).  Out-of-range elements are filled with zeros.
+static int make_map(sj_sim *s, CUtensorMap *m, void *base, int pitch, int rows, long long units, long long unit_stride, int bw, int bh) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { s->err = "cuTensorMapEncodeTiled not available from this driver"; return SJ_ERR_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)std::max<long long>(units, 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * s->esz, (cuuint64_t)unit_stride * s->esz};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    // L2 promotion off: tiles start on 32-byte sectors, not on 128- or 256-byte lines, and a promoted fetch would pull the
+    // rest of every line it touches from DRAM (measured: +46 % read traffic with L2_256B)
+    static const int promo = getenv("SJ_TMA_L2PROMO") ? atoi(getenv("SJ_TMA_L2PROMO")) : 0;
+    const CUtensorMapL2promotion pr = promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    const CUresult r = fn(m, s->prec == SJ_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[256];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d): pitch %d rows %d units %lld box %d x %d", (int)r, pitch, rows, units, bw, bh);
+        s->err = b;
+        return SJ_ERR_CUDA;
+    }
+    return 0;
+}
+
+// tile shape for a w x h rectangle: nvx vectors per row, th rows, with nvx * th <= NT threads and the halo box
+// (nvx + 1) * (th + 1) vectors inside its slot (1.25 NT vectors).  Minimises the vectors a plane of the region makes the
+// TMA engine read (three curl inputs with halo + three own arrays, tile overhang past the region included) per useful
+// vector; ties go to the fuller thread block.
+static void pick_shape(int w, int h, int V, int NT, int &nvx_out, int &th_out) {
+    const int nv = (w + V - 1) / V;
+    double best = 1e30;
+    nvx_out = 1; th_out = 1;
+    for (int nvx = 1; nvx <= std::min(nv, 63); ++nvx) {
+        const int tiles_x = (nv + nvx - 1) / nvx;
+        if ((nv + tiles_x - 1) / tiles_x != nvx) continue;          // only balanced splits
+        if (nvx < std::min(nv, 6)) continue;                         // rows of at least 96 bytes where the region allows
+        if ((nvx & 1) && nvx != nv) continue;                        // tile rows are whole 32-byte sectors (DRAM granularity)
+        for (int th = 1; th <= std::min(h, 255); ++th) {
+            if (nvx * th > NT || (nvx + 1) * (th + 1) * 4 > NT * 5) continue;
+            const int tiles_y = (h + th - 1) / th;
+            if ((h + tiles_y - 1) / tiles_y != th) continue;
+            const double read = (double)tiles_x * tiles_y * (3.0 * (nvx + 1) * (th + 1) + 3.0 * nvx * th) / ((double)nv * h);
+            const double fill = (double)nvx * th / NT;
+            const double score = read + 0.6 * (1.0 - fill);
+            if (score < best) { best = score; nvx_out = nvx; th_out = th; }
+        }
+    }
+}
+
+static int shape_index(sj_sim *s, int nvx, int th, int V) {
+    TmaState &t = s->tma;
+    for (int i = 0; i < t.n_shapes; ++i) if (t.shapes[i].nvx == nvx && t.shapes[i].th == th) return i;
+    if (t.n_shapes >= SJ_TMA_MAX_SHAPES) return -1;
+    t.shapes[t.n_shapes] = TShape{nvx, th, nvx * V, (nvx + 1) * V};
+    return t.n_shapes++;
+}
+
+static void free_list(TmaList &l) { cudaFree(l.items); cudaFree(l.first); l.items = NULL; l.first = NULL; l.n_items = 0; l.grid = 0; }
+
+void sj_tma_free(sj_sim *s) {
+    TmaState &t = s->tma;
+    cudaFree(t.maps); t.maps = NULL;
+    for (int g = 0; g < 2; ++g) { free_list(t.h[g]); for (int c = 0; c < 4; ++c) free_list(t.e[g][c]); }
+}
+
+// Static schedule: items sorted by cost, each given to the least-loaded block (LPT); a block then walks its items in
+// that order.  cost = planes loaded (run + 1 partial plane).
+static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int grid_cap, TmaList &out) {
+    free_list(out);
+    if (items.empty()) return 0;
+    std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return (a.ke - a.kb) > (b.ke - b.kb); });
+    {   // the last quarter of the work is cut into runs of at most `fine` planes: fine grains even out the end of the kernel
+        static const int fine = getenv("SJ_TMA_FINE") ? atoi(getenv("SJ_TMA_FINE")) : 6;
+        const size_t keep = items.size() - items.size() / 4;
+        std::vector<WorkItem> cut(items.begin(), items.begin() + keep);
+        for (size_t n = keep; n < items.size() && fine > 0; ++n) {
+            const WorkItem &w = items[n];
+            const int nz = w.ke - w.kb, parts = std::max(1, (nz + fine - 1) / fine), len = (nz + parts - 1) / parts;
+            for (int kb = w.kb; kb < w.ke; kb += len) { WorkItem c = w; c.kb = kb; c.ke = std::min(kb + len, w.ke); cut.push_back(c); }
+        }
+        if (fine > 0) items.swap(cut);
+        std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return (a.ke - a.kb) > (b.ke - b.kb); });
+    }
+    const int grid = std::max(1, std::min(grid_cap, (int)items.size()));
+    typedef std::pair<long long, int> LB;     // (load, block)
+    std::priority_queue<LB, std::vector<LB>, std::greater<LB>> pq;
+    for (int b = 0; b < grid; ++b) pq.push(LB(0, b));
+    std::vector<std::vector<WorkItem>> per(grid);
+    for (const WorkItem &w : items) {
+        LB lb = pq.top(); pq.pop();
+        per[lb.second].push_back(w);
+        lb.first += (w.ke - w.kb) + 1;
+        pq.push(lb);
+    }
+    std::vector<WorkItem> flat; std::vector<int> first(grid + 1, 0);
+    for (int b = 0; b < grid; ++b) { first[b] = (int)flat.size(); flat.insert(flat.end(), per[b].begin(), per[b].end()); }
+    first[grid] = (int)flat.size();
+    CK(cudaMalloc((void **)&out.items, flat.size() * sizeof(WorkItem)));
+    CK(cudaMalloc((void **)&out.first, first.size() * sizeof(int)));
+    CK(cudaMemcpy(out.items, flat.data(), flat.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(out.first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    out.n_items = (int)flat.size(); out.grid = grid;
+    return 0;
+}
+
+static std::vector<WorkItem> replicate_sets(const std::vector<WorkItem> &one, int n_sets) {
+    std::vector<WorkItem> all;
+    for (int q = 0; q < n_sets; ++q)
+        for (WorkItem w : one) { w.set = q; all.push_back(w); }
+    return all;
+}
+
+static int env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
+
+int sj_tma_build_geometry(sj_sim *s) {
+    TmaState &t = s->tma;
+    t.n_shapes = 0; t.geo[0].clear(); t.geo[1].clear();
+    if (!t.mode) return 0;
+    int dev = 0, cc = 0;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev);
+    if (cc < 9 || !encode_fn()) { t.mode = 0; return 0; }          // no TMA on this device / driver: register kernels only
+    const int V = s->prec == SJ_F64 ? 2 : 4;
+    t.nt = 224;
+    const int nt_gen = 96;             // edge / corner tiles: thin strips, heavy stages -> small blocks
+    const int zc_int = env_int("SJ_TMA_ZC", s->int_zchunk);
+    const int zc_gen = env_int("SJ_TMA_ZCG", 6);       // edge / corner tiles are bound by instruction latency: many short items
+    struct Reg { int box, kind, i0, i1, j0, j1, k0, k1; };
+    std::vector<Reg> regs;
+    const int N1x = s->g.n[0] + 1, N1y = s->g.n[1] + 1;
+    const int L[3] = {s->lo[0], s->lo[1], s->lo[2]}, Hh[3] = {s->hi[0], s->hi[1], s->hi[2]};
+    regs.push_back(Reg{-1, 0, L[0], Hh[0], L[1], Hh[1], std::max(L[2], s->kz0), std::min(Hh[2], s->kz1)});
+    for (size_t bi = 0; bi < s->boxes.size(); ++bi) {
+        const sj_sim::Box &B = s->boxes[bi];
+        const bool zbox = (B.lo[0] == 0 && B.hi[0] == N1x && B.lo[1] == 0 && B.hi[1] == N1y);
+        const bool ybox = !zbox && (B.lo[0] == 0 && B.hi[0] == N1x);
+        auto add = [&](int i0, int i1, int j0, int j1, int kind) { regs.push_back(Reg{(int)bi, kind, i0, i1, j0, j1, B.lo[2], B.hi[2]}); };
+        if (zbox) {
+            add(L[0], Hh[0], L[1], Hh[1], 3);
+            add(0, N1x, 0, L[1], 0); add(0, N1x, Hh[1], N1y, 0); add(0, L[0], L[1], Hh[1], 0); add(Hh[0], N1x, L[1], Hh[1], 0);
+        } else if (ybox) {
+            add(L[0], Hh[0], B.lo[1], B.hi[1], 2);
+            add(0, L[0], B.lo[1], B.hi[1], 0); add(Hh[0], N1x, B.lo[1], B.hi[1], 0);
+        } else add(B.lo[0], B.hi[0], B.lo[1], B.hi[1], 1);
+    }
+    for (const Reg &R : regs) {
+        const int w = R.i1 - R.i0, h = R.j1 - R.j0, nz = R.k1 - R.k0;
+        if (w <= 0 || h <= 0 || nz <= 0) continue;
+        int nvx, th;
+        pick_shape(w, h, V, (R.box >= 0 && R.kind == 0) ? nt_gen : t.nt, nvx, th);
+        const int sh = shape_index(s, nvx, th, V);
+        if (sh < 0) { t.mode = 0; return 0; }
+        // planes per item: runs of about zc_int planes, evened out; thin regions (the z boxes) in one run
+        const int zc_t = (R.box >= 0 && R.kind == 0) ? zc_gen : zc_int;
+        const int nchunk = std::max(1, (nz + zc_t - 1) / zc_t), zc = (nz + nchunk - 1) / nchunk;
+        const int tw = nvx * V;
+        for (int kb = R.k0; kb < R.k1; kb += zc)
+            for (int j0 = R.j0; j0 < R.j1; j0 += th)
+                for (int i0 = R.i0; i0 < R.i1; i0 += tw) {
+                    WorkItem wi = {R.box, 0, i0, j0, kb, std::min(kb + zc, R.k1), 0, R.kind, std::min(i0 + tw, R.i1), std::min(j0 + th, R.j1), sh, 0};
+                    t.geo[(R.box >= 0 && R.kind == 0) ? 1 : 0].push_back(wi);
+                }
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int rc = upload_schedule(s, replicate_sets(t.geo[0], s->g.n_sets), n_sm * env_int("SJ_TMA_HBLK", 2), t.h[0]); if (rc) return rc;
+    rc = upload_schedule(s, replicate_sets(t.geo[1], s->g.n_sets), n_sm * env_int("SJ_TMA_HGBLK", 2), t.h[1]); if (rc) return rc;
+    return 0;
+}
+
+int sj_tma_build_materials(sj_sim *s) {
+    TmaState &t = s->tma;
+    if (!t.mode) return 0;
+    // ---- tensor maps (F and the boxes never move; P is re-allocated when the slot count changes) ----
+    std::vector<CUtensorMap> maps((size_t)t.n_shapes * SJ_TMAP_PER_SHAPE);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    const long long f_units = 6LL * s->g.n_sets * s->nzl, p_units = 2LL * std::max(s->n_slots, 1) * 3 * s->g.n_sets * s->nzl;
+    for (int i = 0; i < t.n_shapes; ++i) {
+        const TShape &sh = t.shapes[i];
+        CUtensorMap *m = &maps[(size_t)i * SJ_TMAP_PER_SHAPE];
+        int rc = make_map(s, m + SJ_TMAP_F_HALO, s->F, s->pitch, s->rows, f_units, s->plane, sh.hp, sh.th + 1); if (rc) return rc;
+        rc = make_map(s, m + SJ_TMAP_F_OWN, s->F, s->pitch, s->rows, f_units, s->plane, sh.tw, sh.th); if (rc) return rc;
+        rc = make_map(s, m + SJ_TMAP_P_OWN, s->Pall, s->pitch, s->rows, p_units, s->plane, sh.tw, sh.th); if (rc) return rc;
+        for (size_t b = 0; b < s->boxes.size(); ++b) {
+            const sj_sim::Box &B = s->boxes[b];
+            rc = make_map(s, m + SJ_TMAP_BOX0 + b, B.base, B.bpitch, B.by, 12LL * s->g.n_sets * B.bz, B.bplane, sh.tw, sh.th); if (rc) return rc;
+        }
+    }
+    cudaFree(t.maps); t.maps = NULL;
+    CK(cudaMalloc(&t.maps, std::max<size_t>(maps.size(), 1) * sizeof(CUtensorMap)));
+    CK(cudaMemcpy(t.maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    // ---- E-pass schedules: classify the geometry items by material, per tile shape ----
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    static const char *knob[2][4] = {{"SJ_TMA_E0BLK", "SJ_TMA_E1BLK", "SJ_TMA_E2BLK", "SJ_TMA_E3BLK"},
+                                     {"SJ_TMA_G0BLK", "SJ_TMA_G1BLK", "SJ_TMA_G2BLK", "SJ_TMA_G3BLK"}};
+    static const int dflt[2][4] = {{2, 1, 2, 1}, {2, 1, 2, 1}};
+    for (int g = 0; g < 2; ++g) {
+        std::vector<WorkItem> cls[4];
+        for (int sh = 0; sh < t.n_shapes; ++sh) {
+            std::vector<WorkItem> sub;
+            for (const WorkItem &w : t.geo[g]) if (w.shape == sh) sub.push_back(w);
+            int rc = sj_classify_items(s, sub, t.shapes[sh].tw, t.shapes[sh].th, cls); if (rc) return rc;
+        }
+        for (int c = 0; c < 4; ++c) {
+            int rc = upload_schedule(s, replicate_sets(cls[c], s->g.n_sets), n_sm * env_int(knob[g][c], dflt[g][c]), t.e[g][c]); if (rc) return rc;
+        }
+    }
+    return 0;
+}
