@@ -98,5 +98,8 @@ if __name__ == "__main__":
         print("bench %s: %s (%.1f s)" % (prec, "BITWISE EQUAL" if ok else "DIFFERENT", time.time() - t0))
         sys.exit(0 if ok else 1)
     if what == "time":
-        modes = tuple(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else (0, 1, 2, 3)
+        if len(sys.argv) > 3 and sys.argv[3] == "env":
+            modes = (int(os.environ.get("SJ_TMA", "3")),)
+        else:
+            modes = tuple(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else (0, 1, 2, 3)
         run_time(prec, modes)

@@ -86,7 +86,7 @@ struct ItemList { WorkItem *dev; int n; };
 // ---- TMA-staged column kernels (sj_tma.cuh): tile shapes, tensor maps, per-block item schedules ----------------
 #define SJ_TMA_MAX_SHAPES 12
 struct TShape { int nvx, th, tw, hp; };   // vectors per tile row, tile rows, tile width and halo-box row pitch in elements
-struct TmaList { WorkItem *items; int *first; int n_items, grid; double bytes; };   // first: [grid + 1] CSR over blocks
+struct TmaList { WorkItem *items; int *first; int n_items, grid; double bytes; };   // first: the queue counters {next item, drained producers}
 struct TmaState {
     int mode = 0;                 // bit 0: H-pass through the TMA kernels, bit 1: E-pass
     int nt = 224;                 // consumer threads per block the shapes were sized for

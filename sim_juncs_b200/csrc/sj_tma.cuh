@@ -8,7 +8,7 @@
 // boxes (the curl inputs are loaded with a one-vector / one-row halo, so there are no shuffles, no tile-edge loads and
 // no boundary predicates: TMA zero-fills outside the grid), do the arithmetic of sj_kernels.cuh and store with 128-bit
 // st.global.  The ring is released stage by stage through a second set of mbarriers (one arrival per consumer warp), so
-// the producer runs NST-1 planes ahead -- also across the boundary between two items -- whatever the occupancy.
+// the producer runs as many planes ahead as the ring holds -- also across the boundary between two items -- whatever the occupancy.
 //
 // The arithmetic (curl order, UPML forms, ADE) is expression for expression that of the register kernels in
 // sj_kernels.cuh, so both paths give bit-identical fields (tests/test_gpu_tma.py).
@@ -27,9 +27,11 @@
 struct TmaPlan {
     const CUtensorMap *maps;              // [shape][SJ_TMAP_PER_SHAPE], device memory
     TShape shape[SJ_TMA_MAX_SHAPES];
-    const WorkItem *items;
-    const int *blk_first;                 // [gridDim.x + 1]: block b owns items [blk_first[b], blk_first[b+1])
+    const WorkItem *items;                // sorted: heaviest first, fine-grained ones last
+    int n_items;
+    int *queue;                           // [0] next item to hand out, [1] producers that have drained the queue
 };
+#define SJ_ITEM_END (-99)                 // WorkItem::box of the end-of-queue message
 
 // ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,37 +57,71 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
-template <typename T, int V>
-__device__ __forceinline__ void lds_vec(Vec<T, V> &v, const T *p) { v.load(p); }
-
-// ring bookkeeping shared by producer and consumers: load number q -> stage q % NST, phase (q / NST) & 1
-template <int NST>
+// ---- the staging ring ------------------------------------------------------------------------------------
+// One ring of `cap` bytes per block holds the plane loads of every item class back to back: load number q (counted per
+// block, in the order both sides derive from the item list) takes `len` contiguous bytes at the head, or at offset 0 if
+// it does not fit before the end.  Barrier pair q % NB belongs to load q: `full` completes when the TMA bytes have
+// landed (one producer arrival + expect_tx), `empty` when every consumer warp has read them.  A light class (7 tiles per
+// plane) therefore gets many planes in flight and a heavy one (19 tiles) two or three, from the same shared memory.
+template <int NB>
 struct Ring {
-    uint32_t full0, empty0, data0;      // shared-space addresses (barriers, stage 0)
-    unsigned char *data_gen;            // generic address of stage 0
-    int stage_bytes;
-    __device__ __forceinline__ uint32_t full(int q) const { return full0 + 8u * (unsigned)(q % NST); }
-    __device__ __forceinline__ uint32_t empty(int q) const { return empty0 + 8u * (unsigned)(q % NST); }
-    __device__ __forceinline__ uint32_t phase(int q) const { return (unsigned)(q / NST) & 1u; }
-    __device__ __forceinline__ uint32_t data(int q) const { return data0 + (unsigned)(q % NST) * (unsigned)stage_bytes; }
-    __device__ __forceinline__ const unsigned char *gen(int q) const { return data_gen + (q % NST) * stage_bytes; }
+    uint32_t full0, empty0, data0;      // shared-space addresses (barriers, byte 0 of the ring)
+    unsigned char *data_gen;            // generic address of byte 0
+    WorkItem *mail;                     // [NB] the item that starts with load q (written by the producer before it arms full(q))
+    int2 *meta;                         // [NB] (position, length) of the loads in flight -- producer's bookkeeping, in shared
+                                        // memory: with the ring taking the whole SM there is no L1 left for a local array
+    int cap;
+    __device__ __forceinline__ uint32_t full(int q) const { return full0 + 8u * (unsigned)(q % NB); }
+    __device__ __forceinline__ uint32_t empty(int q) const { return empty0 + 8u * (unsigned)(q % NB); }
+    __device__ __forceinline__ uint32_t phase(int q) const { return (unsigned)(q / NB) & 1u; }
 };
 
-// Stage layout (byte offsets inside one stage), NT = consumer threads:
-//   3 curl-input boxes with halo (HALO bytes each), 3 own-field tiles, NAUX auxiliary tiles, NPOL polarisation tiles
+// position of the next load: the same arithmetic on the producer and on every consumer thread
+struct Cursor {
+    int q, head;
+    __device__ __forceinline__ int place(int len, int cap) { const int pos = (head + len > cap) ? 0 : head; head = pos + len; return pos; }
+};
+
 template <int NT> struct Slots { static constexpr int OWN = NT * 16, HALO = NT * 20; };
 
-template <int NST>
-__device__ __forceinline__ void ring_setup(Ring<NST> &r, unsigned char *smem, int stage_bytes, int n_consumer_warps) {
+template <int NB>
+__device__ __forceinline__ void ring_setup(Ring<NB> &r, unsigned char *smem, int cap, int n_consumer_warps) {
     const uint32_t base = (smem_u32(smem) + 127u) & ~127u;
-    r.full0 = base; r.empty0 = base + 8u * NST; r.data0 = base + 128u; r.stage_bytes = stage_bytes;
-    r.data_gen = smem + (base + 128u - smem_u32(smem));
+    static_assert(16 * NB <= 256 && 8 * NB <= 128 && sizeof(WorkItem) * NB <= 640, "ring header layout");
+    r.full0 = base; r.empty0 = base + 8u * NB; r.data0 = base + 1024u; r.cap = cap;
+    r.data_gen = smem + (base + 1024u - smem_u32(smem));
+    r.meta = reinterpret_cast<int2 *>(smem + (base + 256u - smem_u32(smem)));
+    r.mail = reinterpret_cast<WorkItem *>(smem + (base + 384u - smem_u32(smem)));
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(r.full0 + 8u * s, 1u); mbar_init(r.empty0 + 8u * s, (unsigned)n_consumer_warps); }
+        for (int s = 0; s < NB; ++s) { mbar_init(r.full0 + 8u * s, 1u); mbar_init(r.empty0 + 8u * s, (unsigned)n_consumer_warps); }
         mbar_fence_init();
     }
     __syncthreads();
 }
+
+// producer side: where load q goes and which earlier loads must have been released first
+template <int NB>
+struct Producer {
+    Cursor c;
+    int oldest;
+    __device__ __forceinline__ void init() { c.q = 0; c.head = 0; oldest = 0; }
+    __device__ __forceinline__ void wait_released(const Ring<NB> &r, int upto) {
+        while (oldest <= upto) { mbar_wait(r.empty(oldest), r.phase(oldest)); ++oldest; }
+    }
+    // returns the shared-space address of the load's bytes; the caller arms r.full(c.q), issues the copies, then ++c.q
+    __device__ __forceinline__ uint32_t acquire(const Ring<NB> &r, int len) {
+        wait_released(r, c.q - NB);                         // barrier pair q % NB is free again
+        const int pos = c.place(len, r.cap);
+        int need = oldest - 1;
+        for (int i = oldest; i < c.q; ++i) {
+            const int2 m = r.meta[i % NB];
+            if (m.x < pos + len && pos < m.x + m.y) need = i;
+        }
+        wait_released(r, need);                             // every in-flight load under [pos, pos + len) has been read
+        r.meta[c.q % NB] = make_int2(pos, len);
+        return r.data0 + (unsigned)pos;
+    }
+};
 
 // z coordinate (dimension 2 of the tensor maps) of plane kl of (array a, set) for arrays stored [a][set][plane]
 __device__ __forceinline__ int zcoord(int a, int n_sets, int set, int planes, int kl) { return (a * n_sets + set) * planes + kl; }
@@ -95,20 +131,24 @@ __device__ __forceinline__ int zcoord(int a, int n_sets, int set, int planes, in
 // =====================================================================================================
 // aux slots: class A (GENERAL = false): 1 (the normal B of a face tile; unused by interior tiles);
 //            GENERAL: 6 (Bx, By, Bz, Ux, Uy, Uz)
-template <typename T, int NT, int NST, bool GENERAL>
-__device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const Ring<NST> &r,
+template <typename T, int NT, int NB>
+__device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const Ring<NB> &r,
                                               int k_lo, int k_hi) {
     typedef Slots<NT> SL;
-    int q = 0;
-    const int n0 = plan.blk_first[blockIdx.x], n1 = plan.blk_first[blockIdx.x + 1];
-    for (int n = n0; n < n1; ++n) {
+    Producer<NB> pr; pr.init();
+    for (;;) {
+        const int n = atomicAdd(plan.queue, 1);
+        if (n >= plan.n_items) break;
         const WorkItem it = plan.items[n];
+        bool first = true;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
-        if (kb >= ke) continue;
+        if (kb >= ke) continue;                           // (never in a whole-slab pass)
         const TShape sh = plan.shape[it.shape];
         const CUtensorMap *mp = plan.maps + it.shape * SJ_TMAP_PER_SHAPE;
         const uint32_t hb = (uint32_t)(sh.hp * (sh.th + 1)) * sizeof(T), ob = (uint32_t)(sh.tw * sh.th) * sizeof(T);
-        const int naux = GENERAL ? 6 : (it.kind != 0 && it.box >= 0 ? 1 : 0);
+        const bool general = it.box >= 0 && it.kind == 0;
+        const int naux = general ? 6 : (it.box >= 0 ? 1 : 0);
+        const int len_full = 3 * SL::HALO + (3 + (general ? 6 : 1)) * SL::OWN;
         int bi = 0, bj = 0, bz = 1, bk0 = 0;
         const CUtensorMap *mb = mp;
         if (it.box >= 0) {
@@ -116,11 +156,13 @@ __device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxS
             bi = it.i0 - b.lo[0]; bj = it.j0 - b.lo[1]; bz = b.hi[2] - b.lo[2]; bk0 = b.lo[2];
             mb = mp + SJ_TMAP_BOX0 + it.box;
         }
-        for (int k = kb; k <= ke; ++k, ++q) {
-            mbar_wait(r.empty(q), r.phase(q) ^ 1u);
-            const uint32_t bar = r.full(q), d = r.data(q);
+        for (int k = ke; k >= kb; --k) {                  // top down: plane k + 1 is then always the previous load
+            const bool partial = (k == ke);               // the plane above the run: Ex, Ey only
+            const uint32_t d = pr.acquire(r, partial ? 2 * SL::HALO : len_full), bar = r.full(pr.c.q);
+            if (first) { r.mail[pr.c.q % NB] = it; first = false; }     // ordered before the barrier arrival below (release)
+            ++pr.c.q;
             const int kl = k - p.kz0 + 1;
-            if (k == ke) {               // the plane above the run: Ex, Ey only
+            if (partial) {
                 mbar_expect_tx(bar, 2 * hb);
                 tma_load_3d(d, mp + SJ_TMAP_F_HALO, it.i0, it.j0, zcoord(0, p.n_sets, it.set, p.nzl, kl), bar);
                 tma_load_3d(d + SL::HALO, mp + SJ_TMAP_F_HALO, it.i0, it.j0, zcoord(1, p.n_sets, it.set, p.nzl, kl), bar);
@@ -133,7 +175,7 @@ __device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxS
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 tma_load_3d(d + 3 * SL::HALO + c * SL::OWN, mp + SJ_TMAP_F_OWN, it.i0, it.j0, zcoord(3 + c, p.n_sets, it.set, p.nzl, kl), bar);
-            if (GENERAL) {
+            if (general) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {     // B = array group 1, UB = array group 3 of the box allocation
                     tma_load_3d(d + 3 * SL::HALO + (3 + c) * SL::OWN, mb, bi, bj, zcoord(3 + c, p.n_sets, it.set, bz, k - bk0), bar);
@@ -144,13 +186,23 @@ __device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxS
             }
         }
     }
+    {   // end of queue: an empty load whose mailbox says so
+        pr.acquire(r, 0);
+        WorkItem e; e.box = SJ_ITEM_END;
+        r.mail[pr.c.q % NB] = e;
+        mbar_arrive(r.full(pr.c.q));
+        if (atomicAdd(plan.queue + 1, 1) == (int)gridDim.x - 1) { plan.queue[0] = 0; plan.queue[1] = 0; }   // ready for the next launch
+    }
 }
 
 // PD: 4 interior, 1/2/3 face with normal x/y/z, 0 general
-template <typename T, int NT, int NST, int PD>
+// LATE: the load is released after the arithmetic instead of right after the shared-memory reads (fewer live registers:
+// the reads can be interleaved with the arithmetic; used by the two-blocks-per-SM build)
+template <typename T, int NT, int NB, int PD, bool LATE>
 __device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const WorkItem &it, const TShape &sh,
-                                           const Ring<NST> &r, int kb, int ke, int &q) {
+                                           const Ring<NB> &r, int kb, int ke, Cursor &cu) {
     typedef Slots<NT> SL;
+    constexpr int LEN_FULL = 3 * SL::HALO + (3 + (PD == 0 ? 6 : 1)) * SL::OWN, LEN_PART = 2 * SL::HALO;
     constexpr int V = 16 / (int)sizeof(T);
     const int t = threadIdx.x, lane = t & 31;
     const int row = t / sh.nvx, vx = t - row * sh.nvx;
@@ -190,18 +242,26 @@ __device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<
 
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz, ux, uy, uz;
     bx.zero(); by.zero(); bz.zero(); ux.zero(); uy.zero(); uz.zero();
-    mbar_wait(r.full(q), r.phase(q));
+    // the run is marched from its top plane down, so Ex, Ey of plane k + 1 are carried in registers and only one load
+    // is resident at a time; first the plane above the run (Ex, Ey only)
     {
-        const unsigned char *d = r.gen(q);
-        ex0.load(reinterpret_cast<const T *>(d) + hc); ey0.load(reinterpret_cast<const T *>(d + SL::HALO) + hc);
+        const int pos = cu.place(LEN_PART, r.cap);
+        mbar_wait(r.full(cu.q), r.phase(cu.q));
+        const unsigned char *d = r.data_gen + pos;
+        ex1.load(reinterpret_cast<const T *>(d) + hc); ey1.load(reinterpret_cast<const T *>(d + SL::HALO) + hc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.empty(cu.q));
+        ++cu.q;
     }
-    for (int k = kb; k < ke; ++k, ++q) {
-        mbar_wait(r.full(q + 1), r.phase(q + 1));
-        const unsigned char *d0 = r.gen(q), *d1 = r.gen(q + 1);
+    pH += (long long)(ke - 1 - kb) * plane; pB += (long long)(ke - 1 - kb) * bplane; pU += (long long)(ke - 1 - kb) * bplane;
+    for (int k = ke - 1; k >= kb; --k, ++cu.q) {
+        const int pos = cu.place(LEN_FULL, r.cap);
+        mbar_wait(r.full(cu.q), r.phase(cu.q));
+        const unsigned char *d0 = r.data_gen + pos;
         const T *sEx = reinterpret_cast<const T *>(d0), *sEy = reinterpret_cast<const T *>(d0 + SL::HALO), *sEz = reinterpret_cast<const T *>(d0 + 2 * SL::HALO);
         const T *sH = reinterpret_cast<const T *>(d0 + 3 * SL::HALO);
         constexpr int OWN_E = SL::OWN / (int)sizeof(T);
-        ex1.load(reinterpret_cast<const T *>(d1) + hc); ey1.load(reinterpret_cast<const T *>(d1 + SL::HALO) + hc);
+        ex0.load(sEx + hc); ey0.load(sEy + hc);
         ez0.load(sEz + hc); ezj.load(sEz + hj); exj.load(sEx + hj);
         const T ez_n = sEz[hc + V], ey_n = sEy[hc + V];
         hx.load(sH + oc); hy.load(sH + OWN_E + oc); hz.load(sH + 2 * OWN_E + oc);
@@ -211,8 +271,7 @@ __device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<
         } else if (PD == 1) bx.load(sH + 3 * OWN_E + oc);
         else if (PD == 2) by.load(sH + 3 * OWN_E + oc);
         else if (PD == 3) bz.load(sH + 3 * OWN_E + oc);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(r.empty(q));           // stage of plane k is free (plane k+1 stays until the next iteration)
+        if (!LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
         if (act) {
             if (PD == 4) {
 #pragma unroll
@@ -281,37 +340,34 @@ __device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<
             if (PD == 0 || PD == 3) bz.store(pB + 2 * bcs);
             if (PD == 0) { ux.store(pU); uy.store(pU + bcs); uz.store(pU + 2 * bcs); }
         }
-        ex0 = ex1; ey0 = ey1;
-        pH += plane; pB += bplane; pU += bplane;
+        if (LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
+        ex1 = ex0; ey1 = ey0;
+        pH -= plane; pB -= bplane; pU -= bplane;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(r.empty(q));               // the Ex, Ey plane above the run
-    ++q;
 }
 
-template <typename T, int NT, int NST, bool GENERAL, int MINB>
-__global__ void __launch_bounds__(NT + 32, MINB) h_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan,
-                                                                  int k_lo, int k_hi) {
-    typedef Slots<NT> SL;
+template <typename T, int NT, int NB, int MINB>
+__global__ void __launch_bounds__(NT + 32, MINB) h_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, int cap,
+                                                         int k_lo, int k_hi) {
     extern __shared__ unsigned char sj_tma_smem[];
-    Ring<NST> r;
-    ring_setup<NST>(r, sj_tma_smem, 3 * SL::HALO + (3 + (GENERAL ? 6 : 1)) * SL::OWN, NT / 32);
+    Ring<NB> r;
+    ring_setup<NB>(r, sj_tma_smem, cap, NT / 32);
     if (threadIdx.x >= NT) {
-        if (threadIdx.x == NT) h_tma_produce<T, NT, NST, GENERAL>(p, bs, plan, r, k_lo, k_hi);
+        if (threadIdx.x == NT) h_tma_produce<T, NT, NB>(p, bs, plan, r, k_lo, k_hi);
         return;
     }
-    int q = 0;
-    const int n0 = plan.blk_first[blockIdx.x], n1 = plan.blk_first[blockIdx.x + 1];
-    for (int n = n0; n < n1; ++n) {
-        const WorkItem it = plan.items[n];
+    Cursor cu; cu.q = 0; cu.head = 0;
+    for (;;) {
+        mbar_wait(r.full(cu.q), r.phase(cu.q));           // the first load of the next item (or the end message) is there
+        const WorkItem it = r.mail[cu.q % NB];
+        if (it.box == SJ_ITEM_END) break;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
-        if (kb >= ke) continue;
         const TShape sh = plan.shape[it.shape];
-        if (GENERAL) h_tma_item<T, NT, NST, 0>(p, bs, it, sh, r, kb, ke, q);
-        else if (it.box < 0) h_tma_item<T, NT, NST, 4>(p, bs, it, sh, r, kb, ke, q);
-        else if (it.kind == 1) h_tma_item<T, NT, NST, 1>(p, bs, it, sh, r, kb, ke, q);
-        else if (it.kind == 2) h_tma_item<T, NT, NST, 2>(p, bs, it, sh, r, kb, ke, q);
-        else h_tma_item<T, NT, NST, 3>(p, bs, it, sh, r, kb, ke, q);
+        if (it.box < 0) h_tma_item<T, NT, NB, 4, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else if (it.kind == 0) h_tma_item<T, NT, NB, 0, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else if (it.kind == 1) h_tma_item<T, NT, NB, 1, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else if (it.kind == 2) h_tma_item<T, NT, NB, 2, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else h_tma_item<T, NT, NB, 3, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
     }
 }
 
@@ -329,23 +385,36 @@ template <int NT, int NS, bool GENERAL> struct EStage {
     static constexpr int BYTES = OFF_P + 6 * NS * SL::OWN;
 };
 
-template <typename T, int NT, int NST, int NS, bool GENERAL>
-__device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const Ring<NST> &r,
+// material class of an item (WorkItem::pad): 0 one non-dispersive material, 1 mixed (p.n_slots slots staged), 2 / 3 one
+// material with 1 / 2 poles
+template <typename T>
+__device__ __forceinline__ int item_slots(const KParams<T> &p, const WorkItem &it) {
+    return it.pad == 0 ? 0 : it.pad == 1 ? p.n_slots : it.pad - 1;
+}
+
+template <typename T, int NT, int NB>
+__device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const Ring<NB> &r,
                                               int k_lo, int k_hi) {
     typedef Slots<NT> SL;
-    typedef EStage<NT, NS, GENERAL> ES;
     constexpr int V = 16 / (int)sizeof(T);
-    int q = 0;
+    Producer<NB> pr; pr.init();
     const int parity = (int)(*p.step & 1);
-    const int n0 = plan.blk_first[blockIdx.x], n1 = plan.blk_first[blockIdx.x + 1];
-    for (int n = n0; n < n1; ++n) {
+    for (;;) {
+        const int n = atomicAdd(plan.queue, 1);
+        if (n >= plan.n_items) break;
         const WorkItem it = plan.items[n];
+        bool first = true;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
-        if (kb >= ke) continue;
+        if (kb >= ke) continue;                           // (never in a whole-slab pass)
         const TShape sh = plan.shape[it.shape];
         const CUtensorMap *mp = plan.maps + it.shape * SJ_TMAP_PER_SHAPE;
         const uint32_t hb = (uint32_t)(sh.hp * (sh.th + 1)) * sizeof(T), ob = (uint32_t)(sh.tw * sh.th) * sizeof(T);
-        const int naux = GENERAL ? 6 : (it.kind != 0 && it.box >= 0 ? 1 : 0);
+        const bool general = it.box >= 0 && it.kind == 0;
+        const int naux = general ? 6 : (it.box >= 0 ? 1 : 0);
+        const int ns = item_slots(p, it);
+        // same layout as EStage<NT, ns, general>
+        const int off_e = 3 * SL::HALO, off_aux = off_e + 3 * SL::OWN, off_p = off_aux + (general ? 6 : 1) * SL::OWN;
+        const int len_full = off_p + 6 * ns * SL::OWN;
         int bi = 0, bj = 0, bz = 1, bk0 = 0;
         const CUtensorMap *mb = mp;
         if (it.box >= 0) {
@@ -354,49 +423,56 @@ __device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxS
             mb = mp + SJ_TMAP_BOX0 + it.box;
         }
         const int hi0 = it.i0 - V, hj0 = it.j0 - 1;
-        for (int k = kb - 1; k < ke; ++k, ++q) {
-            mbar_wait(r.empty(q), r.phase(q) ^ 1u);
-            const uint32_t bar = r.full(q), d = r.data(q);
+        for (int k = kb - 1; k < ke; ++k) {
+            const bool partial = (k == kb - 1);           // the plane below the run: Hx, Hy only
+            const uint32_t d = pr.acquire(r, partial ? 2 * SL::HALO : len_full), bar = r.full(pr.c.q);
+            if (first) { r.mail[pr.c.q % NB] = it; first = false; }     // ordered before the barrier arrival below (release)
+            ++pr.c.q;
             const int kl = k - p.kz0 + 1;
-            if (k == kb - 1) {           // the plane below the run: Hx, Hy only
+            if (partial) {
                 mbar_expect_tx(bar, 2 * hb);
                 tma_load_3d(d, mp + SJ_TMAP_F_HALO, hi0, hj0, zcoord(3, p.n_sets, it.set, p.nzl, kl), bar);
                 tma_load_3d(d + SL::HALO, mp + SJ_TMAP_F_HALO, hi0, hj0, zcoord(4, p.n_sets, it.set, p.nzl, kl), bar);
                 continue;
             }
-            mbar_expect_tx(bar, 3 * hb + (3 + naux + 6 * NS) * ob);
+            mbar_expect_tx(bar, 3 * hb + (3 + naux + 6 * ns) * ob);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 tma_load_3d(d + c * SL::HALO, mp + SJ_TMAP_F_HALO, hi0, hj0, zcoord(3 + c, p.n_sets, it.set, p.nzl, kl), bar);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                tma_load_3d(d + ES::OFF_E + c * SL::OWN, mp + SJ_TMAP_F_OWN, it.i0, it.j0, zcoord(c, p.n_sets, it.set, p.nzl, kl), bar);
-            if (GENERAL) {
+                tma_load_3d(d + off_e + c * SL::OWN, mp + SJ_TMAP_F_OWN, it.i0, it.j0, zcoord(c, p.n_sets, it.set, p.nzl, kl), bar);
+            if (general) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {     // D = array group 0, UD = array group 2 of the box allocation
-                    tma_load_3d(d + ES::OFF_AUX + c * SL::OWN, mb, bi, bj, zcoord(c, p.n_sets, it.set, bz, k - bk0), bar);
-                    tma_load_3d(d + ES::OFF_AUX + (3 + c) * SL::OWN, mb, bi, bj, zcoord(6 + c, p.n_sets, it.set, bz, k - bk0), bar);
+                    tma_load_3d(d + off_aux + c * SL::OWN, mb, bi, bj, zcoord(c, p.n_sets, it.set, bz, k - bk0), bar);
+                    tma_load_3d(d + off_aux + (3 + c) * SL::OWN, mb, bi, bj, zcoord(6 + c, p.n_sets, it.set, bz, k - bk0), bar);
                 }
             } else if (naux) {
-                tma_load_3d(d + ES::OFF_AUX, mb, bi, bj, zcoord(it.kind - 1, p.n_sets, it.set, bz, k - bk0), bar);
+                tma_load_3d(d + off_aux, mb, bi, bj, zcoord(it.kind - 1, p.n_sets, it.set, bz, k - bk0), bar);
             }
-#pragma unroll
             for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
+                for (int s = 0; s < ns; ++s) {
                     const int ac = (parity * p.n_slots + s) * 3 + c, ap = ((parity ^ 1) * p.n_slots + s) * 3 + c;
-                    tma_load_3d(d + ES::OFF_P + ((c * NS + s) * 2) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ac, p.n_sets, it.set, p.nzl, kl), bar);
-                    tma_load_3d(d + ES::OFF_P + ((c * NS + s) * 2 + 1) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ap, p.n_sets, it.set, p.nzl, kl), bar);
+                    tma_load_3d(d + off_p + ((c * ns + s) * 2) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ac, p.n_sets, it.set, p.nzl, kl), bar);
+                    tma_load_3d(d + off_p + ((c * ns + s) * 2 + 1) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ap, p.n_sets, it.set, p.nzl, kl), bar);
                 }
         }
     }
+    {   // end of queue: an empty load whose mailbox says so
+        pr.acquire(r, 0);
+        WorkItem e; e.box = SJ_ITEM_END;
+        r.mail[pr.c.q % NB] = e;
+        mbar_arrive(r.full(pr.c.q));
+        if (atomicAdd(plan.queue + 1, 1) == (int)gridDim.x - 1) { plan.queue[0] = 0; plan.queue[1] = 0; }   // ready for the next launch
+    }
 }
 
-template <typename T, int NT, int NST, int NS, int PD, bool SRC, bool UNI, bool GENERAL>
+template <typename T, int NT, int NB, int NS, int PD, bool SRC, bool UNI, bool LATE>
 __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const WorkItem &it, const TShape &sh,
-                                           const Ring<NST> &r, int kb, int ke, int &q) {
+                                           const Ring<NB> &r, int kb, int ke, Cursor &cu) {
     typedef Slots<NT> SL;
-    typedef EStage<NT, NS, GENERAL> ES;
+    typedef EStage<NT, NS, PD == 0> ES;
     constexpr int V = 16 / (int)sizeof(T);
     constexpr bool POL = NS > 0;
     constexpr bool GEN = POL && !UNI;             // per-cell material bytes and table look-ups
@@ -462,18 +538,20 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
     if (GEN && act) { load_bytes<V>(pm, mx); load_bytes<V>(pm + mcs, my); load_bytes<V>(pm + mcs2, mz); }
     PolState<T, V, NS> pol;
 
-    mbar_wait(r.full(q), r.phase(q));
     {
-        const unsigned char *d = r.gen(q);
+        const int pos = cu.place(2 * SL::HALO, r.cap);
+        mbar_wait(r.full(cu.q), r.phase(cu.q));
+        const unsigned char *d = r.data_gen + pos;
         hxm.load(reinterpret_cast<const T *>(d) + hcen); hym.load(reinterpret_cast<const T *>(d + SL::HALO) + hcen);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(r.empty(q));
-    ++q;
-    for (int k = kb; k < ke; ++k, ++q) {
+    if (lane == 0) mbar_arrive(r.empty(cu.q));
+    ++cu.q;
+    for (int k = kb; k < ke; ++k, ++cu.q) {
         if (GEN && act) { load_bytes<V>(pm + plane, nx_); load_bytes<V>(pm + mcs + plane, ny_); load_bytes<V>(pm + mcs2 + plane, nz_); }
-        mbar_wait(r.full(q), r.phase(q));
-        const unsigned char *d0 = r.gen(q);
+        const int pos = cu.place(ES::BYTES, r.cap);
+        mbar_wait(r.full(cu.q), r.phase(cu.q));
+        const unsigned char *d0 = r.data_gen + pos;
         const T *sHx = reinterpret_cast<const T *>(d0), *sHy = reinterpret_cast<const T *>(d0 + SL::HALO), *sHz = reinterpret_cast<const T *>(d0 + 2 * SL::HALO);
         const T *sE = reinterpret_cast<const T *>(d0 + ES::OFF_E), *sA = reinterpret_cast<const T *>(d0 + ES::OFF_AUX);
         const T *sP = reinterpret_cast<const T *>(d0 + ES::OFF_P);
@@ -502,8 +580,7 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
                 pol.prv[c][s].load(sP + ((c * NS + s) * 2 + 1) * OWN_E + oc);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(r.empty(q));
+        if (!LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
         const unsigned smask = SRC ? src_plane_mask(p, k) : 0u;
         if (act) {
             if (PD == 4) {
@@ -587,6 +664,7 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
                 for (int c = 0; c < 3; ++c)
                     if (pol.need[c][s]) pol.prv[c][s].store(bprv + (3 * s + c) * pcs + xg);
         }
+        if (LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
         hxm = hx0; hym = hy0;
         if (GEN) {
 #pragma unroll
@@ -596,30 +674,41 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
     }
 }
 
-template <typename T, int NT, int NST, int NS, bool UNI, bool GENERAL, int MINB>
-__global__ void __launch_bounds__(NT + 32, MINB) e_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, int k_lo, int k_hi) {
-    typedef EStage<NT, NS, GENERAL> ES;
+template <typename T, int NT, int NB, int NS, bool UNI, bool LATE>
+__device__ __forceinline__ void e_tma_dispatch(const KParams<T> &p, const PmlBoxSet<T> &bs, const WorkItem &it, const TShape &sh,
+                                               const Ring<NB> &r, int kb, int ke, Cursor &cu) {
+    const bool src = src_in_chunk(p, kb, ke);
+#define SJ_E_ITEM(PD_, SRC_) e_tma_item<T, NT, NB, NS, PD_, SRC_, UNI, LATE>(p, bs, it, sh, r, kb, ke, cu)
+    if (it.box < 0) { if (src) SJ_E_ITEM(4, true); else SJ_E_ITEM(4, false); }
+    else if (it.kind == 0) { if (src) SJ_E_ITEM(0, true); else SJ_E_ITEM(0, false); }
+    else if (it.kind == 1) { if (src) SJ_E_ITEM(1, true); else SJ_E_ITEM(1, false); }
+    else if (it.kind == 2) { if (src) SJ_E_ITEM(2, true); else SJ_E_ITEM(2, false); }
+    else { if (src) SJ_E_ITEM(3, true); else SJ_E_ITEM(3, false); }
+#undef SJ_E_ITEM
+}
+
+// One launch per E-pass: every item class (interior / face / edge tiles x material class) through the same ring.
+template <typename T, int NT, int NB, int MINB>
+__global__ void __launch_bounds__(NT + 32, MINB) e_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, int cap,
+                                                         int k_lo, int k_hi) {
     extern __shared__ unsigned char sj_tma_smem[];
-    Ring<NST> r;
-    ring_setup<NST>(r, sj_tma_smem, ES::BYTES, NT / 32);
+    Ring<NB> r;
+    ring_setup<NB>(r, sj_tma_smem, cap, NT / 32);
     if (threadIdx.x >= NT) {
-        if (threadIdx.x == NT) e_tma_produce<T, NT, NST, NS, GENERAL>(p, bs, plan, r, k_lo, k_hi);
+        if (threadIdx.x == NT) e_tma_produce<T, NT, NB>(p, bs, plan, r, k_lo, k_hi);
         return;
     }
-    int q = 0;
-    const int n0 = plan.blk_first[blockIdx.x], n1 = plan.blk_first[blockIdx.x + 1];
-    for (int n = n0; n < n1; ++n) {
-        const WorkItem it = plan.items[n];
+    Cursor cu; cu.q = 0; cu.head = 0;
+    for (;;) {
+        mbar_wait(r.full(cu.q), r.phase(cu.q));           // the first load of the next item (or the end message) is there
+        const WorkItem it = r.mail[cu.q % NB];
+        if (it.box == SJ_ITEM_END) break;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
-        if (kb >= ke) continue;
         const TShape sh = plan.shape[it.shape];
-        const bool src = src_in_chunk(p, kb, ke);
-#define SJ_E_ITEM(PD_, SRC_) e_tma_item<T, NT, NST, NS, PD_, SRC_, UNI, GENERAL>(p, bs, it, sh, r, kb, ke, q)
-        if (GENERAL) { if (src) SJ_E_ITEM(0, true); else SJ_E_ITEM(0, false); }
-        else if (it.box < 0) { if (src) SJ_E_ITEM(4, true); else SJ_E_ITEM(4, false); }
-        else if (it.kind == 1) { if (src) SJ_E_ITEM(1, true); else SJ_E_ITEM(1, false); }
-        else if (it.kind == 2) { if (src) SJ_E_ITEM(2, true); else SJ_E_ITEM(2, false); }
-        else { if (src) SJ_E_ITEM(3, true); else SJ_E_ITEM(3, false); }
-#undef SJ_E_ITEM
+        if (it.pad == 0) e_tma_dispatch<T, NT, NB, 0, true, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else if (it.pad == 2) e_tma_dispatch<T, NT, NB, 1, true, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else if (it.pad == 3) e_tma_dispatch<T, NT, NB, 2, true, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else if (p.n_slots <= 1) e_tma_dispatch<T, NT, NB, 1, false, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        else e_tma_dispatch<T, NT, NB, 2, false, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
     }
 }

@@ -6,7 +6,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <queue>
 
 #include "sj_tma.cuh"
 
@@ -93,10 +92,23 @@ void sj_tma_free(sj_sim *s) {
 
 // Static schedule: items sorted by cost, each given to the least-loaded block (LPT); a block then walks its items in
 // that order.  cost = planes loaded (run + 1 partial plane).
-static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int grid_cap, TmaList &out) {
+// bytes one plane of the item stages in the ring (the cost unit of the schedule): 3 halo tiles of 20 B per thread and
+// own tiles of 16 B per thread -- own fields, auxiliaries, 6 polarisation tiles per pole slot (E-pass)
+static int item_weight(const sj_sim *s, const WorkItem &w, int which) {
+    const bool general = w.box >= 0 && w.kind == 0;
+    const int ns = which == 0 ? 0 : (w.pad == 0 ? 0 : w.pad == 1 ? std::max(s->n_slots, 1) : w.pad - 1);
+    // edge / corner and mixed-material tiles are bound by instruction latency, not by their bytes: measured factors
+    static const double wgen = getenv("SJ_TMA_WGEN") ? atof(getenv("SJ_TMA_WGEN")) : 1.0, wmix = getenv("SJ_TMA_WMIX") ? atof(getenv("SJ_TMA_WMIX")) : 1.0;
+    const double f = (general ? wgen : 1.0) * ((which == 1 && w.pad == 1) ? wmix : 1.0);
+    return (int)(f * (3 * 20 + (3 + (general ? 6 : 1) + 6 * ns) * 16));
+}
+
+static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int which, int grid_cap, TmaList &out) {
     free_list(out);
     if (items.empty()) return 0;
-    std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return (a.ke - a.kb) > (b.ke - b.kb); });
+    auto cost = [&](const WorkItem &w) { return (long long)(w.ke - w.kb + 1) * item_weight(s, w, which); };
+    auto by_cost = [&](const WorkItem &a, const WorkItem &b) { return cost(a) > cost(b); };
+    std::stable_sort(items.begin(), items.end(), by_cost);
     {   // the last quarter of the work is cut into runs of at most `fine` planes: fine grains even out the end of the kernel
         static const int fine = getenv("SJ_TMA_FINE") ? atoi(getenv("SJ_TMA_FINE")) : 6;
         const size_t keep = items.size() - items.size() / 4;
@@ -107,26 +119,16 @@ static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int grid_cap,
             for (int kb = w.kb; kb < w.ke; kb += len) { WorkItem c = w; c.kb = kb; c.ke = std::min(kb + len, w.ke); cut.push_back(c); }
         }
         if (fine > 0) items.swap(cut);
-        std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return (a.ke - a.kb) > (b.ke - b.kb); });
+        std::stable_sort(items.begin(), items.end(), by_cost);
     }
+    // dynamic queue: the kernels' producers pull the next item with an atomic, heaviest first
     const int grid = std::max(1, std::min(grid_cap, (int)items.size()));
-    typedef std::pair<long long, int> LB;     // (load, block)
-    std::priority_queue<LB, std::vector<LB>, std::greater<LB>> pq;
-    for (int b = 0; b < grid; ++b) pq.push(LB(0, b));
-    std::vector<std::vector<WorkItem>> per(grid);
-    for (const WorkItem &w : items) {
-        LB lb = pq.top(); pq.pop();
-        per[lb.second].push_back(w);
-        lb.first += (w.ke - w.kb) + 1;
-        pq.push(lb);
-    }
-    std::vector<WorkItem> flat; std::vector<int> first(grid + 1, 0);
-    for (int b = 0; b < grid; ++b) { first[b] = (int)flat.size(); flat.insert(flat.end(), per[b].begin(), per[b].end()); }
-    first[grid] = (int)flat.size();
+    const std::vector<WorkItem> &flat = items;
+    const int zero[2] = {0, 0};
     CK(cudaMalloc((void **)&out.items, flat.size() * sizeof(WorkItem)));
-    CK(cudaMalloc((void **)&out.first, first.size() * sizeof(int)));
+    CK(cudaMalloc((void **)&out.first, sizeof zero));
     CK(cudaMemcpy(out.items, flat.data(), flat.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(out.first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(out.first, zero, sizeof zero, cudaMemcpyHostToDevice));
     out.n_items = (int)flat.size(); out.grid = grid;
     return 0;
 }
@@ -149,7 +151,6 @@ int sj_tma_build_geometry(sj_sim *s) {
     if (cc < 9 || !encode_fn()) { t.mode = 0; return 0; }          // no TMA on this device / driver: register kernels only
     const int V = s->prec == SJ_F64 ? 2 : 4;
     t.nt = 224;
-    const int nt_gen = 96;             // edge / corner tiles: thin strips, heavy stages -> small blocks
     const int zc_int = env_int("SJ_TMA_ZC", s->int_zchunk);
     const int zc_gen = env_int("SJ_TMA_ZCG", 6);       // edge / corner tiles are bound by instruction latency: many short items
     struct Reg { int box, kind, i0, i1, j0, j1, k0, k1; };
@@ -174,7 +175,7 @@ int sj_tma_build_geometry(sj_sim *s) {
         const int w = R.i1 - R.i0, h = R.j1 - R.j0, nz = R.k1 - R.k0;
         if (w <= 0 || h <= 0 || nz <= 0) continue;
         int nvx, th;
-        pick_shape(w, h, V, (R.box >= 0 && R.kind == 0) ? nt_gen : t.nt, nvx, th);
+        pick_shape(w, h, V, t.nt, nvx, th);
         const int sh = shape_index(s, nvx, th, V);
         if (sh < 0) { t.mode = 0; return 0; }
         // planes per item: runs of about zc_int planes, evened out; thin regions (the z boxes) in one run
@@ -185,14 +186,12 @@ int sj_tma_build_geometry(sj_sim *s) {
             for (int j0 = R.j0; j0 < R.j1; j0 += th)
                 for (int i0 = R.i0; i0 < R.i1; i0 += tw) {
                     WorkItem wi = {R.box, 0, i0, j0, kb, std::min(kb + zc, R.k1), 0, R.kind, std::min(i0 + tw, R.i1), std::min(j0 + th, R.j1), sh, 0};
-                    t.geo[(R.box >= 0 && R.kind == 0) ? 1 : 0].push_back(wi);
+                    t.geo[0].push_back(wi);
                 }
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    int rc = upload_schedule(s, replicate_sets(t.geo[0], s->g.n_sets), n_sm * env_int("SJ_TMA_HBLK", 2), t.h[0]); if (rc) return rc;
-    rc = upload_schedule(s, replicate_sets(t.geo[1], s->g.n_sets), n_sm * env_int("SJ_TMA_HGBLK", 2), t.h[1]); if (rc) return rc;
-    return 0;
+    return upload_schedule(s, replicate_sets(t.geo[0], s->g.n_sets), 0, n_sm * env_int("SJ_TMA_BLK", 1), t.h[0]);
 }
 
 int sj_tma_build_materials(sj_sim *s) {
@@ -219,19 +218,14 @@ int sj_tma_build_materials(sj_sim *s) {
     // ---- E-pass schedules: classify the geometry items by material, per tile shape ----
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    static const char *knob[2][4] = {{"SJ_TMA_E0BLK", "SJ_TMA_E1BLK", "SJ_TMA_E2BLK", "SJ_TMA_E3BLK"},
-                                     {"SJ_TMA_G0BLK", "SJ_TMA_G1BLK", "SJ_TMA_G2BLK", "SJ_TMA_G3BLK"}};
-    static const int dflt[2][4] = {{2, 1, 2, 1}, {2, 1, 2, 1}};
-    for (int g = 0; g < 2; ++g) {
-        std::vector<WorkItem> cls[4];
-        for (int sh = 0; sh < t.n_shapes; ++sh) {
-            std::vector<WorkItem> sub;
-            for (const WorkItem &w : t.geo[g]) if (w.shape == sh) sub.push_back(w);
-            int rc = sj_classify_items(s, sub, t.shapes[sh].tw, t.shapes[sh].th, cls); if (rc) return rc;
-        }
-        for (int c = 0; c < 4; ++c) {
-            int rc = upload_schedule(s, replicate_sets(cls[c], s->g.n_sets), n_sm * env_int(knob[g][c], dflt[g][c]), t.e[g][c]); if (rc) return rc;
-        }
+    std::vector<WorkItem> cls[4], all;
+    for (int sh = 0; sh < t.n_shapes; ++sh) {
+        std::vector<WorkItem> sub;
+        for (const WorkItem &w : t.geo[0]) if (w.shape == sh) sub.push_back(w);
+        int rc = sj_classify_items(s, sub, t.shapes[sh].tw, t.shapes[sh].th, cls); if (rc) return rc;
     }
+    for (int c = 0; c < 4; ++c)
+        for (WorkItem w : cls[c]) { w.pad = c; all.push_back(w); }      // pad = material class of the item
+    { int rc = upload_schedule(s, replicate_sets(all, s->g.n_sets), 1, n_sm * env_int("SJ_TMA_BLK", 1), t.e[0][0]); if (rc) return rc; }
     return 0;
 }
