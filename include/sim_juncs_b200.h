@@ -188,6 +188,22 @@ int sj_plane_ptr(sj_sim *sim, int comp, int set, int32_t k, void **dev_ptr, size
  * halo of `lower` (after an E-pass).  Stream-ordered on both simulations' streams. */
 int sj_halo_exchange(sj_sim *lower, sj_sim *upper, int which);
 
+/* ---- z-slabs inside the library (the reference's counterpart is meep's MPI chunking under `meep::initialize mpi`,
+ * src/main.cpp:20) -------------------------------------------------------------------------------------------------
+ * Every slab is one sj_sim created with its [kz0, kz1).  Once the neighbours are connected, sj_run / sj_run_group need
+ * nothing else: the kernels that update a slab's boundary plane write it straight into the neighbour's halo over
+ * NVLink (peer-mapped memory) and the slabs order themselves through mailbox words on the device; the step still
+ * replays as one CUDA graph per slab.  Fields and monitors equal the single-GPU run bit for bit. */
+typedef struct { unsigned char bytes[256]; } sj_peer_handle;
+/* one process per GPU: export this slab's CUDA-IPC handle, hand it to the neighbours' processes (any byte transport),
+ * connect with the handles of the slab below / above (NULL where there is none) -- before the first step. */
+int sj_export_peer(sj_sim *sim, sj_peer_handle *out);
+int sj_connect_peers(sj_sim *sim, const sj_peer_handle *lower, const sj_peer_handle *upper);
+/* one process, several devices (or several slabs on one device): connect two stacked slabs directly */
+int sj_connect_local(sj_sim *lower, sj_sim *upper);
+/* sj_run for all slabs of a process (bottom to top), enqueued so that no slab's launch queue starves its neighbours */
+int sj_run_group(sj_sim **sims, int32_t n_slabs, int64_t n_steps, int32_t save_span);
+
 /* ---- inspection ------------------------------------------------------------------------- */
 /* Copy a whole component (owned planes [kz0,kz1), dense (n0+1)(n1+1) rows) to the host as doubles. */
 int sj_get_field(sj_sim *sim, int comp, int set, double *out);

@@ -73,6 +73,10 @@ SYMBOLS = {
     "sj_sample": (C.c_int, [_vp, _vp]),
     "sj_plane_ptr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "sj_halo_exchange": (C.c_int, [_vp, _vp, C.c_int]),
+    "sj_export_peer": (C.c_int, [_vp, C.c_char_p]),
+    "sj_connect_peers": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "sj_connect_local": (C.c_int, [_vp, _vp]),
+    "sj_run_group": (C.c_int, [C.POINTER(_vp), C.c_int32, C.c_int64, C.c_int32]),
     "sj_get_field": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "sj_run_timed": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
     "sj_profile_kernels": (C.c_int, [_vp, C.c_int32, _dp]),

@@ -258,6 +258,8 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     }
     int rc = alloc_zero(s, (void **)&s->step_dev, sizeof(long long)); if (rc) return rc;
     rc = alloc_zero(s, (void **)&s->flags, 4 * sizeof(int)); if (rc) return rc;
+    rc = alloc_zero(s, (void **)&s->sync_dev, 4 * sizeof(unsigned long long)); if (rc) return rc;
+    CK(cudaDeviceSynchronize());        // the zero fills above ran on the legacy stream; the simulation's stream is non-blocking
     return SJ_OK;
 }
 
@@ -276,6 +278,9 @@ extern "C" void sj_destroy(sj_sim *s) {
     for (int q = 0; q < SJ_MAX_SRC; ++q) for (int c = 0; c < 3; ++c) cudaFree(s->srcw[q][c]);
     cudaFree(s->mt_chi); cudaFree(s->mt_coef); cudaFree(s->mt_np); cudaFree(s->drive);
     cudaFree(s->mon_idx); cudaFree(s->mon_w); cudaFree(s->series); cudaFree(s->step_dev); cudaFree(s->flags);
+    if (s->peer_up.ipc) { cudaIpcCloseMemHandle(s->peer_up.F); cudaIpcCloseMemHandle(s->peer_up.sync); }
+    if (s->peer_down.ipc) { cudaIpcCloseMemHandle(s->peer_down.F); cudaIpcCloseMemHandle(s->peer_down.sync); }
+    cudaFree(s->sync_dev);
     cudaEventDestroy(s->ev_a); cudaEventDestroy(s->ev_b); cudaEventDestroy(s->ev_fork);
     for (int a = 0; a < SJ_N_AUX; ++a) { cudaStreamDestroy(s->aux[a]); cudaEventDestroy(s->ev_join[a]); }
     cudaStreamDestroy(s->stream);
@@ -789,6 +794,8 @@ extern "C" int sj_add_monitors(sj_sim *s, int comp, int32_t n, const double *xyz
     if (s) cudaSetDevice(s->g.device);
     if (!s || comp < 0 || comp > 5 || n < 0 || (n && !xyz)) return fail(s, SJ_ERR_ARG, "bad monitor arguments");
     if (s->n_mon) return fail(s, SJ_ERR_STATE, "monitors already added");
+    if (comp >= 3 && s->kz1 < s->g.n[2] + 1)
+        return fail(s, SJ_ERR_UNSUPPORTED, "H-component monitors in a slab with an upper neighbour: the upper H halo is never exchanged");
     s->n_mon = n; s->mon_comp = comp;
     s->mon_xyz.assign(xyz, xyz + 3 * (size_t)n);
     std::vector<long long> idx((size_t)n * 8, -1);
@@ -831,6 +838,8 @@ static int do_sample(sj_sim *s, cudaStream_t st, long long base_step, int base_c
     if (s->n_mon == 0) return 0;
     MonDev m; m.n_mon = s->n_mon; m.comp = s->mon_comp; m.idx = s->mon_idx; m.w = s->mon_w; m.series = s->series; m.flags = s->flags;
     const int nt = s->n_mon * s->g.n_sets;
+    // a stencil may reach into the upper halo: wait until the upper slab's bottom E plane of the last step has landed
+    m.wait_flag = s->peer_up.F ? s->sync_dev : NULL;
     if (s->prec == SJ_F64) { KParams<double> p; fill_params(s, p); sample_monitors<double><<<(nt + 127) / 128, 128, 0, st>>>(p, m, base_step, base_cursor, span); }
     else { KParams<float> p; fill_params(s, p); sample_monitors<float><<<(nt + 127) / 128, 128, 0, st>>>(p, m, base_step, base_cursor, span); }
     s->launches++;
@@ -856,6 +865,7 @@ extern "C" int sj_sample_at(sj_sim *s, int comp, int32_t n, const double *xyz, d
     CK(cudaMemcpyAsync(dw, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemsetAsync(dflag, 0, sizeof(int), s->stream));
     MonDev m; m.n_mon = n; m.comp = comp; m.idx = didx; m.w = dw; m.series = dout; m.flags = dflag;
+    m.wait_flag = s->peer_up.F ? s->sync_dev : NULL;
     // cursor = 0: base_step is the current step and the span is never reached
     if (s->prec == SJ_F64) { KParams<double> p; fill_params(s, p); sample_monitors<double><<<(unsigned)((nt + 127) / 128), 128, 0, s->stream>>>(p, m, s->steps_done, 0, 1 << 30); }
     else { KParams<float> p; fill_params(s, p); sample_monitors<float><<<(unsigned)((nt + 127) / 128), 128, 0, s->stream>>>(p, m, s->steps_done, 0, 1 << 30); }
@@ -909,6 +919,31 @@ static int graph_build(sj_sim *s) {
     return 0;
 }
 
+// steps [i0, i1) of a run whose sampling cadence counts from step 0 of the run (reference src/disp.cpp:719-741):
+// sample when i % save_span == 0, then step.  st: the stream the work is enqueued on.
+static int run_range(sj_sim *s, int64_t i0, int64_t i1, int32_t save_span, long long base_step, int base_cursor, cudaStream_t st) {
+    static const bool graph_env = getenv("SJ_NO_GRAPH") == NULL;
+    const bool use_graph = graph_env && !s->trace_on;
+    int rc;
+    for (int64_t i = i0; i < i1; ++i) {
+        if (i % save_span == 0) { rc = do_sample(s, st, base_step, base_cursor, save_span); if (rc) return rc; s->n_samples++; }
+        if (use_graph && s->graph_launches >= 0) {
+            if (!s->step_graph) { rc = graph_build(s); if (rc) return rc; }
+            if (s->step_graph) {
+                CK(cudaGraphLaunch(s->step_graph, st));
+                s->steps_done++; s->launches += s->graph_launches;
+                continue;
+            }
+        }
+        rc = do_pass(s, 0, s->kz0, s->kz1, st); if (rc) return rc;
+        rc = do_pass(s, 1, s->kz0, s->kz1, st); if (rc) return rc;
+        tick_kernel<<<1, 1, 0, st>>>(s->step_dev);
+        s->steps_done++; s->launches++;
+    }
+    CK(cudaGetLastError());
+    return SJ_OK;
+}
+
 // bound_geom::run loop body (reference src/disp.cpp:719-741)
 extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
     if (s) cudaSetDevice(s->g.device);
@@ -917,25 +952,109 @@ extern "C" int sj_run(sj_sim *s, int64_t n_steps, int32_t save_span) {
     int rc = ensure_drive(s, s->steps_done + n_steps); if (rc) return rc;
     const int n_new = (int)((n_steps + save_span - 1) / save_span);
     rc = ensure_series(s, s->n_samples + n_new); if (rc) return rc;
-    const long long base_step = s->steps_done; const int base_cursor = s->n_samples;
-    static const bool graph_env = getenv("SJ_NO_GRAPH") == NULL;
-    const bool use_graph = graph_env && !s->trace_on;
-    for (int64_t i = 0; i < n_steps; ++i) {
-        if (i % save_span == 0) { rc = do_sample(s, s->stream, base_step, base_cursor, save_span); if (rc) return rc; s->n_samples++; }
-        if (use_graph && s->graph_launches >= 0) {
-            if (!s->step_graph) { rc = graph_build(s); if (rc) return rc; }
-            if (s->step_graph) {
-                CK(cudaGraphLaunch(s->step_graph, s->stream));
-                s->steps_done++; s->launches += s->graph_launches;
-                continue;
-            }
+    return run_range(s, 0, n_steps, save_span, s->steps_done, s->n_samples, s->stream);
+}
+
+// The same loop for the z-slabs of one simulation held by one process (one sj_sim per slab, stacked bottom to top and
+// connected with sj_connect_local): the slabs order themselves through their mailbox flags on the device, so the host
+// only has to keep every slab's queue fed -- the steps are enqueued round-robin in short chunks (a slab's kernels wait
+// for its neighbours; a host thread blocked on one slab's full launch queue would starve the others).  Slabs that share
+// a device are enqueued step by step on one stream, bottom slab first, which is the order their flags need.
+extern "C" int sj_run_group(sj_sim **sims, int32_t n, int64_t n_steps, int32_t save_span) {
+    if (!sims || n < 1 || n_steps < 0) return SJ_ERR_ARG;
+    if (save_span <= 0) save_span = 1;
+    bool shared = false;
+    for (int a = 0; a < n; ++a) for (int b = a + 1; b < n; ++b) shared |= (sims[a]->g.device == sims[b]->g.device);
+    std::vector<long long> base_step(n); std::vector<int> base_cursor(n);
+    for (int a = 0; a < n; ++a) {
+        sj_sim *s = sims[a];
+        cudaSetDevice(s->g.device);
+        int rc = ensure_drive(s, s->steps_done + n_steps); if (rc) return rc;
+        rc = ensure_series(s, s->n_samples + (int)((n_steps + save_span - 1) / save_span)); if (rc) return rc;
+        base_step[a] = s->steps_done; base_cursor[a] = s->n_samples;
+        if (shared && a > 0) {          // everything goes through the bottom slab's stream: order it after this slab's set-up
+            cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            cudaEventRecord(e, s->stream); cudaStreamWaitEvent(sims[0]->stream, e, 0); cudaEventDestroy(e);
         }
-        rc = do_pass(s, 0, s->kz0, s->kz1, s->stream); if (rc) return rc;
-        rc = do_pass(s, 1, s->kz0, s->kz1, s->stream); if (rc) return rc;
-        tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev);
-        s->steps_done++; s->launches++;
     }
-    CK(cudaGetLastError());
+    const int64_t chunk = shared ? 1 : 16;
+    for (int64_t i0 = 0; i0 < n_steps; i0 += chunk)
+        for (int a = 0; a < n; ++a) {
+            sj_sim *s = sims[a];
+            cudaSetDevice(s->g.device);
+            int rc = run_range(s, i0, std::min(i0 + chunk, n_steps), save_span, base_step[a], base_cursor[a], shared ? sims[0]->stream : s->stream);
+            if (rc) return rc;
+        }
+    if (shared)                         // later calls on the other slabs' own streams see the finished run
+        for (int a = 1; a < n; ++a) {
+            cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            cudaEventRecord(e, sims[0]->stream); cudaStreamWaitEvent(sims[a]->stream, e, 0); cudaEventDestroy(e);
+        }
+    return SJ_OK;
+}
+
+// ---- z-slab neighbours ---------------------------------------------------------------------------------------
+struct PeerWire {              // what sj_export_peer writes into the caller's 256-byte buffer
+    cudaIpcMemHandle_t f, sync;
+    long long fcs, set_stride, plane;
+    int nzl, kz0, kz1, n_sets, esz, magic;
+};
+static_assert(sizeof(PeerWire) <= 256, "sj_peer_handle too small");
+
+extern "C" int sj_export_peer(sj_sim *s, sj_peer_handle *out) {
+    if (!s || !out) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
+    PeerWire w; memset(&w, 0, sizeof w);
+    CK(cudaIpcGetMemHandle(&w.f, s->F));
+    CK(cudaIpcGetMemHandle(&w.sync, s->sync_dev));
+    w.fcs = s->set_stride * s->g.n_sets; w.set_stride = s->set_stride; w.plane = s->plane;
+    w.nzl = s->nzl; w.kz0 = s->kz0; w.kz1 = s->kz1; w.n_sets = s->g.n_sets; w.esz = (int)s->esz; w.magic = 0x534a5031;
+    memset(out, 0, sizeof *out);
+    memcpy(out, &w, sizeof w);
+    return SJ_OK;
+}
+
+static int open_peer(sj_sim *s, const sj_peer_handle *h, bool upper, sj_sim::Peer &p) {
+    PeerWire w; memcpy(&w, h, sizeof w);
+    if (w.magic != 0x534a5031 || w.plane != s->plane || w.n_sets != s->g.n_sets || w.esz != (int)s->esz ||
+        (upper ? w.kz0 != s->kz1 : w.kz1 != s->kz0))
+        return fail(s, SJ_ERR_ARG, "peer handle does not describe the adjacent slab of the same simulation");
+    CK(cudaIpcOpenMemHandle(&p.F, w.f, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&p.sync, w.sync, cudaIpcMemLazyEnablePeerAccess));
+    p.fcs = w.fcs; p.set_stride = w.set_stride; p.nzl = w.nzl; p.ipc = true;
+    return SJ_OK;
+}
+
+extern "C" int sj_connect_peers(sj_sim *s, const sj_peer_handle *lower, const sj_peer_handle *upper) {
+    if (!s) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
+    if (s->steps_done) return fail(s, SJ_ERR_STATE, "connect the slabs before the first step");
+    graph_drop(s);
+    if (lower) { int rc = open_peer(s, lower, false, s->peer_down); if (rc) return rc; }
+    if (upper) { int rc = open_peer(s, upper, true, s->peer_up); if (rc) return rc; }
+    return SJ_OK;
+}
+
+extern "C" int sj_connect_local(sj_sim *lo, sj_sim *up) {
+    if (!lo || !up || lo->kz1 != up->kz0 || lo->plane != up->plane || lo->esz != up->esz || lo->g.n_sets != up->g.n_sets)
+        return fail(lo ? lo : up, SJ_ERR_ARG, "slabs are not stacked / incompatible");
+    sj_sim *s = lo;
+    if (lo->steps_done || up->steps_done) return fail(lo, SJ_ERR_STATE, "connect the slabs before the first step");
+    if (lo->g.device != up->g.device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, lo->g.device, up->g.device));
+        if (!can) return fail(lo, SJ_ERR_UNSUPPORTED, "no peer access between the two devices");
+        cudaSetDevice(lo->g.device); cudaError_t e = cudaDeviceEnablePeerAccess(up->g.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaSetDevice(up->g.device); e = cudaDeviceEnablePeerAccess(lo->g.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+    }
+    graph_drop(lo); graph_drop(up);
+    lo->peer_up.F = up->F; lo->peer_up.sync = up->sync_dev; lo->peer_up.fcs = up->set_stride * up->g.n_sets;
+    lo->peer_up.set_stride = up->set_stride; lo->peer_up.nzl = up->nzl; lo->peer_up.ipc = false;
+    up->peer_down.F = lo->F; up->peer_down.sync = lo->sync_dev; up->peer_down.fcs = lo->set_stride * lo->g.n_sets;
+    up->peer_down.set_stride = lo->set_stride; up->peer_down.nzl = lo->nzl; up->peer_down.ipc = false;
     return SJ_OK;
 }
 
@@ -1015,6 +1134,7 @@ extern "C" int sj_sync(sj_sim *s) {
     CK(cudaStreamSynchronize(s->stream));
     int fl[4] = {0, 0, 0, 0};
     CK(cudaMemcpy(fl, s->flags, sizeof fl, cudaMemcpyDeviceToHost));
+    if (fl[1]) return fail(s, SJ_ERR_STATE, "a z-slab neighbour did not deliver its boundary plane within 10 s");
     if (fl[0]) return fail(s, SJ_ERR_DIVERGED, "monitor sample exceeded 1000 or is not finite (divergence)");
     return SJ_OK;
 }

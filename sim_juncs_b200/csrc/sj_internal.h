@@ -55,6 +55,29 @@ struct KParams {
     const long long *step;// device step counter
 };
 
+// z-slab neighbours (sj_connect_*): where my boundary plane goes and the mailbox words that order the exchange.
+// Protocol (step n = device step counter): after the E-pass of step n the upper slab has written its bottom E plane
+// into my upper halo and set my flag_e = n + 1; my H-pass of step n waits for flag_e >= n before it touches that halo,
+// writes its top H plane into the upper slab's lower halo and sets that slab's flag_h = n + 1, which the upper slab's
+// E-pass of step n waits for.  The waits sit in the producer thread of the boundary items only.
+template <typename T>
+struct PeerLink {
+    T *F;                             // neighbour's field allocation (peer-mapped); NULL = no neighbour connected
+    long long fcs, set_stride;        // its component and set strides in elements
+    int kl;                           // its local plane that receives my boundary plane (a halo plane of the neighbour)
+    unsigned long long *flag;         // its mailbox word I set when the plane has landed
+};
+template <typename T>
+struct SlabLinks {
+    PeerLink<T> up, down;             // up: receives my top H plane; down: receives my bottom E plane
+    unsigned long long *flag_e;       // mine: set by `up` (its bottom E plane is in my upper halo)
+    unsigned long long *flag_h;       // mine: set by `down` (its top H plane is in my lower halo)
+    unsigned int *done;               // [2] boundary-item completion counters (H-pass, E-pass)
+    int n_bnd[2];                     // consumer-warp completions that finish the boundary plane of a pass
+    int *err;                         // [1] set when a wait timed out
+};
+#define SJ_BND_FLAG 0x100             // WorkItem::shape bit: the item is the slab's boundary plane of this pass
+
 // interior box + its fixed z-chunk grid (chunk c covers [k_lo + c*zchunk, k_lo + (c+1)*zchunk))
 struct IntGeom {
     int i_lo, i_hi, j_lo, j_hi, k_lo, k_hi;
@@ -93,7 +116,8 @@ struct TmaState {
     int n_shapes = 0;
     TShape shapes[SJ_TMA_MAX_SHAPES];
     void *maps = nullptr;         // CUtensorMap[n_shapes][SJ_TMAP_PER_SHAPE] in device memory
-    std::vector<WorkItem> geo[2]; // geometry items of one field set before material classification: [class A | general]
+    std::vector<WorkItem> geo[2]; // geometry items of one field set: [H-pass | E-pass (before material classification)]
+    int n_bnd[2] = {0, 0};        // boundary-plane items per field set in the two lists
     TmaList h[2] = {};            // H-pass: [class A (interior + faces) | general (edges, corners)]
     TmaList e[2][4] = {};         // E-pass: same split x material class (0: one non-dispersive material, 1: mixed,
                                   //         2 / 3: one material with 1 / 2 poles)
@@ -106,6 +130,7 @@ struct MonDev {
     const double *w;      // [n_mon][8]
     double *series;       // [cap][n_mon][n_sets]
     int *flags;           // [0] = diverged
+    const unsigned long long *wait_flag;   // z-slab runs: mailbox word to wait on before sampling (NULL otherwise)
 };
 
 // ---- host-side state -------------------------------------------------------------------
@@ -192,6 +217,10 @@ struct sj_sim {
     double pole_points_int;   // same, restricted to the interior-kernel box
     double pml_cells;
     TmaState tma;
+    // z-slab neighbours: raw peer pointers (same process) or CUDA-IPC mappings (other processes)
+    struct Peer { void *F = nullptr; void *sync = nullptr; long long fcs = 0, set_stride = 0; int nzl = 0; bool ipc = false; };
+    Peer peer_up, peer_down;
+    unsigned long long *sync_dev = nullptr;   // [0] flag_e, [1] flag_h, [2] done counters (2 x u32), [3] spare
     bool trace_reg = false;   // force the register kernels (profiling the old path)
     std::string err;
 };

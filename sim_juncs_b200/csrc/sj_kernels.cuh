@@ -986,6 +986,11 @@ __global__ void sample_monitors(KParams<T> p, MonDev m, long long base_step, int
     if (t >= m.n_mon * p.n_sets) return;
     const int set = t / m.n_mon, mon = t % m.n_mon;
     const long long step = *p.step;
+    if (m.wait_flag) {                  // z-slab run: the upper slab's bottom E plane of the last step must be in my halo
+        const long long t0 = clock64();
+        while (*(volatile const unsigned long long *)m.wait_flag < (unsigned long long)step && clock64() - t0 < 20000000000LL) {}
+        __threadfence_system();
+    }
     const int cursor = base_cursor + (int)((step - base_step) / save_span);
     const T *F = (m.comp < 3 ? p.E[m.comp] : p.H[m.comp - 3]) + (long long)set * p.set_stride;
     double res = 0.0;

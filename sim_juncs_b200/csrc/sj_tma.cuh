@@ -57,6 +57,38 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
+// ---- slab exchange helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+// producer side: wait until the neighbour's plane for this step is in my halo, then order the TMA reads after it
+__device__ __forceinline__ void wait_halo(const unsigned long long *flag, unsigned long long need, int *err) {
+    if (!flag) return;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < need) {
+        if (clock64() - t0 > 20000000000LL) { *err = 1; break; }     // ~10 s: the neighbour is gone; flag it, do not hang
+    }
+    asm volatile("fence.proxy.async;\n" ::: "memory");
+}
+// consumer side, after a boundary item's remote stores: the warp that completes the plane publishes it
+__device__ __forceinline__ void boundary_done(unsigned int *done, int n_total, unsigned long long *peer_flag, unsigned long long value) {
+    __threadfence_system();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned int old = atomicAdd(done, 1u);
+        if ((int)old == n_total - 1) {
+            *done = 0u;
+            __threadfence_system();
+            st_release_sys(peer_flag, value);
+        }
+    }
+}
+
 // ---- the staging ring ------------------------------------------------------------------------------------
 // One ring of `cap` bytes per block holds the plane loads of every item class back to back: load number q (counted per
 // block, in the order both sides derive from the item list) takes `len` contiguous bytes at the head, or at offset 0 if
@@ -132,8 +164,8 @@ __device__ __forceinline__ int zcoord(int a, int n_sets, int set, int planes, in
 // aux slots: class A (GENERAL = false): 1 (the normal B of a face tile; unused by interior tiles);
 //            GENERAL: 6 (Bx, By, Bz, Ux, Uy, Uz)
 template <typename T, int NT, int NB>
-__device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const Ring<NB> &r,
-                                              int k_lo, int k_hi) {
+__device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const SlabLinks<T> &lk,
+                                              const Ring<NB> &r, int k_lo, int k_hi) {
     typedef Slots<NT> SL;
     Producer<NB> pr; pr.init();
     for (;;) {
@@ -143,12 +175,14 @@ __device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxS
         bool first = true;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
         if (kb >= ke) continue;                           // (never in a whole-slab pass)
-        const TShape sh = plan.shape[it.shape];
-        const CUtensorMap *mp = plan.maps + it.shape * SJ_TMAP_PER_SHAPE;
+        const TShape sh = plan.shape[it.shape & 0xff];
+        const CUtensorMap *mp = plan.maps + (it.shape & 0xff) * SJ_TMAP_PER_SHAPE;
         const uint32_t hb = (uint32_t)(sh.hp * (sh.th + 1)) * sizeof(T), ob = (uint32_t)(sh.tw * sh.th) * sizeof(T);
         const bool general = it.box >= 0 && it.kind == 0;
         const int naux = general ? 6 : (it.box >= 0 ? 1 : 0);
         const int len_full = 3 * SL::HALO + (3 + (general ? 6 : 1)) * SL::OWN;
+        // the slab's top plane reads E of the plane above it: the upper slab's bottom plane of the previous step
+        if ((it.shape & SJ_BND_FLAG) && lk.up.F) wait_halo(lk.flag_e, (unsigned long long)*p.step, lk.err);
         int bi = 0, bj = 0, bz = 1, bk0 = 0;
         const CUtensorMap *mb = mp;
         if (it.box >= 0) {
@@ -199,8 +233,8 @@ __device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxS
 // LATE: the load is released after the arithmetic instead of right after the shared-memory reads (fewer live registers:
 // the reads can be interleaved with the arithmetic; used by the two-blocks-per-SM build)
 template <typename T, int NT, int NB, int PD, bool LATE>
-__device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const WorkItem &it, const TShape &sh,
-                                           const Ring<NB> &r, int kb, int ke, Cursor &cu) {
+__device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const SlabLinks<T> &lk, const WorkItem &it,
+                                           const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu) {
     typedef Slots<NT> SL;
     constexpr int LEN_FULL = 3 * SL::HALO + (3 + (PD == 0 ? 6 : 1)) * SL::OWN, LEN_PART = 2 * SL::HALO;
     constexpr int V = 16 / (int)sizeof(T);
@@ -239,6 +273,7 @@ __device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<
         if (PD == 0 || PD == 2) { syi = p.sig[1][2 * j]; syh = p.sig[1][2 * j + 1]; iyh = p.siginv[1][2 * j + 1]; }
     }
     const bool jok = (j <= p.n[1] - 1);
+    const bool send = (it.shape & SJ_BND_FLAG) && lk.up.F != nullptr;      // block-uniform
 
     Vec<T, V> ex0, ey0, ex1, ey1, ez0, ezj, exj, hx, hy, hz, bx, by, bz, ux, uy, uz;
     bx.zero(); by.zero(); bz.zero(); ux.zero(); uy.zero(); uz.zero();
@@ -339,21 +374,26 @@ __device__ __forceinline__ void h_tma_item(const KParams<T> &p, const PmlBoxSet<
             if (PD == 0 || PD == 2) by.store(pB + bcs);
             if (PD == 0 || PD == 3) bz.store(pB + 2 * bcs);
             if (PD == 0) { ux.store(pU); uy.store(pU + bcs); uz.store(pU + 2 * bcs); }
+            if (send) {     // the slab's top plane: the same values go straight into the upper slab's lower halo
+                T *q = lk.up.F + 3 * lk.up.fcs + (long long)it.set * lk.up.set_stride + (long long)lk.up.kl * plane + (long long)j * p.pitch + i0;
+                hx.store(q); hy.store(q + lk.up.fcs); hz.store(q + 2 * lk.up.fcs);
+            }
         }
         if (LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
         ex1 = ex0; ey1 = ey0;
         pH -= plane; pB -= bplane; pU -= bplane;
     }
+    if (send) boundary_done(lk.done, lk.n_bnd[0], lk.up.flag, (unsigned long long)*p.step + 1ull);
 }
 
 template <typename T, int NT, int NB, int MINB>
-__global__ void __launch_bounds__(NT + 32, MINB) h_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, int cap,
-                                                         int k_lo, int k_hi) {
+__global__ void __launch_bounds__(NT + 32, MINB) h_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, const SlabLinks<T> lk,
+                                                         int cap, int k_lo, int k_hi) {
     extern __shared__ unsigned char sj_tma_smem[];
     Ring<NB> r;
     ring_setup<NB>(r, sj_tma_smem, cap, NT / 32);
     if (threadIdx.x >= NT) {
-        if (threadIdx.x == NT) h_tma_produce<T, NT, NB>(p, bs, plan, r, k_lo, k_hi);
+        if (threadIdx.x == NT) h_tma_produce<T, NT, NB>(p, bs, plan, lk, r, k_lo, k_hi);
         return;
     }
     Cursor cu; cu.q = 0; cu.head = 0;
@@ -362,12 +402,12 @@ __global__ void __launch_bounds__(NT + 32, MINB) h_tma(const KParams<T> p, const
         const WorkItem it = r.mail[cu.q % NB];
         if (it.box == SJ_ITEM_END) break;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
-        const TShape sh = plan.shape[it.shape];
-        if (it.box < 0) h_tma_item<T, NT, NB, 4, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else if (it.kind == 0) h_tma_item<T, NT, NB, 0, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else if (it.kind == 1) h_tma_item<T, NT, NB, 1, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else if (it.kind == 2) h_tma_item<T, NT, NB, 2, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else h_tma_item<T, NT, NB, 3, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        const TShape sh = plan.shape[it.shape & 0xff];
+        if (it.box < 0) h_tma_item<T, NT, NB, 4, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else if (it.kind == 0) h_tma_item<T, NT, NB, 0, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else if (it.kind == 1) h_tma_item<T, NT, NB, 1, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else if (it.kind == 2) h_tma_item<T, NT, NB, 2, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else h_tma_item<T, NT, NB, 3, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
     }
 }
 
@@ -393,8 +433,8 @@ __device__ __forceinline__ int item_slots(const KParams<T> &p, const WorkItem &i
 }
 
 template <typename T, int NT, int NB>
-__device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const Ring<NB> &r,
-                                              int k_lo, int k_hi) {
+__device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const SlabLinks<T> &lk,
+                                              const Ring<NB> &r, int k_lo, int k_hi) {
     typedef Slots<NT> SL;
     constexpr int V = 16 / (int)sizeof(T);
     Producer<NB> pr; pr.init();
@@ -406,12 +446,14 @@ __device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxS
         bool first = true;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
         if (kb >= ke) continue;                           // (never in a whole-slab pass)
-        const TShape sh = plan.shape[it.shape];
-        const CUtensorMap *mp = plan.maps + it.shape * SJ_TMAP_PER_SHAPE;
+        const TShape sh = plan.shape[it.shape & 0xff];
+        const CUtensorMap *mp = plan.maps + (it.shape & 0xff) * SJ_TMAP_PER_SHAPE;
         const uint32_t hb = (uint32_t)(sh.hp * (sh.th + 1)) * sizeof(T), ob = (uint32_t)(sh.tw * sh.th) * sizeof(T);
         const bool general = it.box >= 0 && it.kind == 0;
         const int naux = general ? 6 : (it.box >= 0 ? 1 : 0);
         const int ns = item_slots(p, it);
+        // the slab's bottom plane reads H of the plane below it: the lower slab's top plane of this step
+        if ((it.shape & SJ_BND_FLAG) && lk.down.F) wait_halo(lk.flag_h, (unsigned long long)*p.step + 1ull, lk.err);
         // same layout as EStage<NT, ns, general>
         const int off_e = 3 * SL::HALO, off_aux = off_e + 3 * SL::OWN, off_p = off_aux + (general ? 6 : 1) * SL::OWN;
         const int len_full = off_p + 6 * ns * SL::OWN;
@@ -469,8 +511,8 @@ __device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxS
 }
 
 template <typename T, int NT, int NB, int NS, int PD, bool SRC, bool UNI, bool LATE>
-__device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const WorkItem &it, const TShape &sh,
-                                           const Ring<NB> &r, int kb, int ke, Cursor &cu) {
+__device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const SlabLinks<T> &lk, const WorkItem &it,
+                                           const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu) {
     typedef Slots<NT> SL;
     typedef EStage<NT, NS, PD == 0> ES;
     constexpr int V = 16 / (int)sizeof(T);
@@ -523,6 +565,7 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
         if (PD == 0 || PD == 2) { syi = p.sig[1][2 * j]; iyi = p.siginv[1][2 * j]; syh = p.sig[1][2 * j + 1]; }
     }
     const bool jin = (j >= 1 && j <= p.n[1] - 1);
+    const bool send = (it.shape & SJ_BND_FLAG) && lk.down.F != nullptr;    // block-uniform
     T chi_u = T(0), eps_u = T(0), cfu[NS1][3];
 #pragma unroll
     for (int s_ = 0; s_ < NS1; ++s_)
@@ -663,6 +706,10 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                     if (pol.need[c][s]) pol.prv[c][s].store(bprv + (3 * s + c) * pcs + xg);
+            if (send) {     // the slab's bottom plane: the same values go straight into the lower slab's upper halo
+                T *q = lk.down.F + (long long)set * lk.down.set_stride + (long long)lk.down.kl * plane + (long long)j * p.pitch + i0;
+                ex.store(q); ey.store(q + lk.down.fcs); ez.store(q + 2 * lk.down.fcs);
+            }
         }
         if (LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
         hxm = hx0; hym = hy0;
@@ -672,13 +719,14 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
         }
         pE += plane; pD += bplane; pU += bplane; pm += plane; xg += plane;
     }
+    if (send) boundary_done(lk.done + 1, lk.n_bnd[1], lk.down.flag, (unsigned long long)step + 1ull);
 }
 
 template <typename T, int NT, int NB, int NS, bool UNI, bool LATE>
-__device__ __forceinline__ void e_tma_dispatch(const KParams<T> &p, const PmlBoxSet<T> &bs, const WorkItem &it, const TShape &sh,
-                                               const Ring<NB> &r, int kb, int ke, Cursor &cu) {
+__device__ __forceinline__ void e_tma_dispatch(const KParams<T> &p, const PmlBoxSet<T> &bs, const SlabLinks<T> &lk, const WorkItem &it,
+                                               const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu) {
     const bool src = src_in_chunk(p, kb, ke);
-#define SJ_E_ITEM(PD_, SRC_) e_tma_item<T, NT, NB, NS, PD_, SRC_, UNI, LATE>(p, bs, it, sh, r, kb, ke, cu)
+#define SJ_E_ITEM(PD_, SRC_) e_tma_item<T, NT, NB, NS, PD_, SRC_, UNI, LATE>(p, bs, lk, it, sh, r, kb, ke, cu)
     if (it.box < 0) { if (src) SJ_E_ITEM(4, true); else SJ_E_ITEM(4, false); }
     else if (it.kind == 0) { if (src) SJ_E_ITEM(0, true); else SJ_E_ITEM(0, false); }
     else if (it.kind == 1) { if (src) SJ_E_ITEM(1, true); else SJ_E_ITEM(1, false); }
@@ -689,13 +737,13 @@ __device__ __forceinline__ void e_tma_dispatch(const KParams<T> &p, const PmlBox
 
 // One launch per E-pass: every item class (interior / face / edge tiles x material class) through the same ring.
 template <typename T, int NT, int NB, int MINB>
-__global__ void __launch_bounds__(NT + 32, MINB) e_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, int cap,
-                                                         int k_lo, int k_hi) {
+__global__ void __launch_bounds__(NT + 32, MINB) e_tma(const KParams<T> p, const PmlBoxSet<T> bs, const TmaPlan plan, const SlabLinks<T> lk,
+                                                         int cap, int k_lo, int k_hi) {
     extern __shared__ unsigned char sj_tma_smem[];
     Ring<NB> r;
     ring_setup<NB>(r, sj_tma_smem, cap, NT / 32);
     if (threadIdx.x >= NT) {
-        if (threadIdx.x == NT) e_tma_produce<T, NT, NB>(p, bs, plan, r, k_lo, k_hi);
+        if (threadIdx.x == NT) e_tma_produce<T, NT, NB>(p, bs, plan, lk, r, k_lo, k_hi);
         return;
     }
     Cursor cu; cu.q = 0; cu.head = 0;
@@ -704,11 +752,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) e_tma(const KParams<T> p, const
         const WorkItem it = r.mail[cu.q % NB];
         if (it.box == SJ_ITEM_END) break;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
-        const TShape sh = plan.shape[it.shape];
-        if (it.pad == 0) e_tma_dispatch<T, NT, NB, 0, true, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else if (it.pad == 2) e_tma_dispatch<T, NT, NB, 1, true, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else if (it.pad == 3) e_tma_dispatch<T, NT, NB, 2, true, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else if (p.n_slots <= 1) e_tma_dispatch<T, NT, NB, 1, false, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
-        else e_tma_dispatch<T, NT, NB, 2, false, MINB == 2>(p, bs, it, sh, r, kb, ke, cu);
+        const TShape sh = plan.shape[it.shape & 0xff];
+        if (it.pad == 0) e_tma_dispatch<T, NT, NB, 0, true, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else if (it.pad == 2) e_tma_dispatch<T, NT, NB, 1, true, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else if (it.pad == 3) e_tma_dispatch<T, NT, NB, 2, true, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else if (p.n_slots <= 1) e_tma_dispatch<T, NT, NB, 1, false, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+        else e_tma_dispatch<T, NT, NB, 2, false, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
     }
 }

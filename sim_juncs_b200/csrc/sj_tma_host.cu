@@ -107,7 +107,10 @@ static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int which, in
     free_list(out);
     if (items.empty()) return 0;
     auto cost = [&](const WorkItem &w) { return (long long)(w.ke - w.kb + 1) * item_weight(s, w, which); };
-    auto by_cost = [&](const WorkItem &a, const WorkItem &b) { return cost(a) > cost(b); };
+    auto by_cost = [&](const WorkItem &a, const WorkItem &b) {
+        const int ba = (a.shape & SJ_BND_FLAG) != 0, bb = (b.shape & SJ_BND_FLAG) != 0;
+        return ba != bb ? ba > bb : cost(a) > cost(b);
+    };
     std::stable_sort(items.begin(), items.end(), by_cost);
     {   // the last quarter of the work is cut into runs of at most `fine` planes: fine grains even out the end of the kernel
         static const int fine = getenv("SJ_TMA_FINE") ? atoi(getenv("SJ_TMA_FINE")) : 6;
@@ -171,6 +174,7 @@ int sj_tma_build_geometry(sj_sim *s) {
             add(0, L[0], B.lo[1], B.hi[1], 0); add(Hh[0], N1x, B.lo[1], B.hi[1], 0);
         } else add(B.lo[0], B.hi[0], B.lo[1], B.hi[1], 1);
     }
+    std::vector<WorkItem> geo;
     for (const Reg &R : regs) {
         const int w = R.i1 - R.i0, h = R.j1 - R.j0, nz = R.k1 - R.k0;
         if (w <= 0 || h <= 0 || nz <= 0) continue;
@@ -186,8 +190,22 @@ int sj_tma_build_geometry(sj_sim *s) {
             for (int j0 = R.j0; j0 < R.j1; j0 += th)
                 for (int i0 = R.i0; i0 < R.i1; i0 += tw) {
                     WorkItem wi = {R.box, 0, i0, j0, kb, std::min(kb + zc, R.k1), 0, R.kind, std::min(i0 + tw, R.i1), std::min(j0 + th, R.j1), sh, 0};
-                    t.geo[0].push_back(wi);
+                    geo.push_back(wi);
                 }
+    }
+    // A slab with a neighbour above (below) sends the top H plane (bottom E plane) of every step: that plane becomes
+    // items of its own, flagged and first in the queue, so it is on its way while the rest of the slab is updated.
+    t.n_bnd[0] = t.n_bnd[1] = 0;
+    for (int which = 0; which < 2; ++which) {
+        const bool has = which == 0 ? (s->kz1 < s->g.n[2] + 1) : (s->kz0 > 0);
+        const int kb_ = which == 0 ? s->kz1 - 1 : s->kz0;
+        for (const WorkItem &w : geo) {
+            if (!has || !(w.kb <= kb_ && kb_ < w.ke)) { t.geo[which].push_back(w); continue; }
+            WorkItem b = w; b.kb = kb_; b.ke = kb_ + 1; b.shape |= SJ_BND_FLAG;
+            t.geo[which].push_back(b); t.n_bnd[which]++;
+            if (w.kb < kb_) { WorkItem r = w; r.ke = kb_; t.geo[which].push_back(r); }
+            if (kb_ + 1 < w.ke) { WorkItem r = w; r.kb = kb_ + 1; t.geo[which].push_back(r); }
+        }
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -221,7 +239,7 @@ int sj_tma_build_materials(sj_sim *s) {
     std::vector<WorkItem> cls[4], all;
     for (int sh = 0; sh < t.n_shapes; ++sh) {
         std::vector<WorkItem> sub;
-        for (const WorkItem &w : t.geo[0]) if (w.shape == sh) sub.push_back(w);
+        for (const WorkItem &w : t.geo[1]) if ((w.shape & 0xff) == sh) sub.push_back(w);
         int rc = sj_classify_items(s, sub, t.shapes[sh].tw, t.shapes[sh].th, cls); if (rc) return rc;
     }
     for (int c = 0; c < 4; ++c)

@@ -22,6 +22,17 @@ static int tma_pass(sj_sim *s, int which, cudaStream_t st) {
     const TmaList &l = which == 0 ? s->tma.h[0] : s->tma.e[0][0];
     if (!l.n_items) return 0;
     TmaPlan plan; tma_plan<T>(s, l, plan);
+    SlabLinks<T> lk; memset(&lk, 0, sizeof lk);
+    if (s->peer_up.F) {          // my top H plane -> the upper slab's lower halo (its local plane 0), then its flag_h
+        lk.up.F = (T *)s->peer_up.F; lk.up.fcs = s->peer_up.fcs; lk.up.set_stride = s->peer_up.set_stride; lk.up.kl = 0;
+        lk.up.flag = (unsigned long long *)s->peer_up.sync + 1;
+    }
+    if (s->peer_down.F) {        // my bottom E plane -> the lower slab's upper halo (its last local plane), then its flag_e
+        lk.down.F = (T *)s->peer_down.F; lk.down.fcs = s->peer_down.fcs; lk.down.set_stride = s->peer_down.set_stride;
+        lk.down.kl = s->peer_down.nzl - 1; lk.down.flag = (unsigned long long *)s->peer_down.sync;
+    }
+    lk.flag_e = s->sync_dev; lk.flag_h = s->sync_dev + 1; lk.done = (unsigned int *)(s->sync_dev + 2); lk.err = s->flags + 1;
+    lk.n_bnd[0] = s->tma.n_bnd[0] * s->g.n_sets * (NT / 32); lk.n_bnd[1] = s->tma.n_bnd[1] * s->g.n_sets * (NT / 32);
     // SJ_TMA_BLK = blocks per SM (1: the whole shared memory as one ring, 255 registers; 2: two rings, 128 registers)
     static const int blk = tma_env("SJ_TMA_BLK", 1);
     static const int cap_kb = tma_env("SJ_TMA_RING_KB", blk == 2 ? 104 : 208);
@@ -31,11 +42,11 @@ static int tma_pass(sj_sim *s, int which, cudaStream_t st) {
     if (which == 0) {
         auto kern = blk == 2 ? h_tma<T, NT, NB, 2> : h_tma<T, NT, NB, 1>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        TR(s, "h_tma", st, kern<<<l.grid, NT + 32, smem, st__>>>(p, bs, plan, cap, s->kz0, s->kz1));
+        TR(s, "h_tma", st, kern<<<l.grid, NT + 32, smem, st__>>>(p, bs, plan, lk, cap, s->kz0, s->kz1));
     } else {
         auto kern = blk == 2 ? e_tma<T, NT, NB, 2> : e_tma<T, NT, NB, 1>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        TR(s, "e_tma", st, kern<<<l.grid, NT + 32, smem, st__>>>(p, bs, plan, cap, s->kz0, s->kz1));
+        TR(s, "e_tma", st, kern<<<l.grid, NT + 32, smem, st__>>>(p, bs, plan, lk, cap, s->kz0, s->kz1));
     }
     s->launches++;
     CK(cudaGetLastError());

@@ -225,6 +225,35 @@ class Sim:
         if rc:
             raise SjError("sj_halo_exchange failed %d: %s" % (rc, lower.L.sj_last_error(lower.h).decode()))
 
+    # ---- z-slabs inside the library (include/sim_juncs_b200.h, "z-slabs inside the library") ----
+    def export_peer(self):
+        """256-byte CUDA-IPC description of this slab, to be handed to the neighbouring slabs' processes"""
+        buf = C.create_string_buffer(256)
+        self._ck(self.L.sj_export_peer(self.h, buf))
+        return buf.raw
+
+    def connect_peers(self, lower=None, upper=None):
+        """lower / upper: export_peer() bytes of the slab below / above (other processes), None where there is none"""
+        self._ck(self.L.sj_connect_peers(self.h, lower, upper))
+
+    @staticmethod
+    def connect_local(lower, upper):
+        """two stacked slabs held by this process (any devices with peer access, or the same device)"""
+        rc = lower.L.sj_connect_local(lower.h, upper.h)
+        if rc:
+            raise SjError("sj_connect_local failed %d: %s" % (rc, lower.L.sj_last_error(lower.h).decode()))
+
+    @staticmethod
+    def run_group(sims, n_steps, save_span=1, sync=True):
+        """sj_run for all slabs of this process, bottom to top"""
+        arr = (C.c_void_p * len(sims))(*[s.h for s in sims])
+        rc = sims[0].L.sj_run_group(arr, len(sims), int(n_steps), int(save_span))
+        if rc:
+            raise SjError("sj_run_group failed %d: %s" % (rc, "; ".join(s.L.sj_last_error(s.h).decode() for s in sims)))
+        if sync:
+            for s in sims:
+                s.sync()
+
     def run_timed(self, n_steps, save_span=1):
         ms = C.c_double()
         self._ck(self.L.sj_run_timed(self.h, int(n_steps), int(save_span), C.byref(ms)))

@@ -35,6 +35,44 @@ def slab_range(n_planes, rank, world, weights=None):
     return cuts[rank], cuts[rank + 1]
 
 
+def connect_slabs(sim, rank, world, group=None):
+    """One process per GPU: exchange the slabs' CUDA-IPC handles over torch.distributed (any backend -- the handles are
+    256 bytes each) and connect every slab to the one below and above.  After this sj_run / Sim.run step the whole
+    stack: the boundary planes travel inside the step kernels (peer stores over NVLink) and the slabs order themselves
+    on the device (csrc/sj_tma.cuh), no collective call per step."""
+    mine = sim.export_peer()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    sim.connect_peers(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank + 1 < world else None)
+    dist.barrier(group=group)      # nobody steps before every mapping exists
+
+
+class SlabGroup:
+    """All z-slabs of one simulation inside ONE process: `make_slab(kz, device)` builds the slab [kz0, kz1) on a device
+    (a Sim or a BoundGeom-like object with a `.sim`); the slabs are connected through peer memory and stepped together."""
+
+    def __init__(self, n_planes, devices, make_slab):
+        world = len(devices)
+        self.kz = [slab_range(n_planes, r, world) for r in range(world)]
+        self.parts = [make_slab(self.kz[r], devices[r]) for r in range(world)]
+        self.sims = [getattr(p, "sim", p) for p in self.parts]
+        from .engine import Sim
+        for lo, up in zip(self.sims[:-1], self.sims[1:]):
+            Sim.connect_local(lo, up)
+
+    def run(self, n_steps, save_span=1, sync=True):
+        from .engine import Sim
+        Sim.run_group(self.sims, n_steps, save_span, sync)
+
+    def monitors(self):
+        """every monitor is evaluated by the slab that owns it; the others hold zeros"""
+        return sum(s.monitors() for s in self.sims)
+
+    def field(self, comp, iset=0):
+        import numpy as np
+        return np.concatenate([s.field(comp, iset) for s in self.sims], axis=0)
+
+
 class HaloExchanger:
     """Persistent P2P op lists for the two exchanges.  `plane(comp, set, k)` must return a contiguous
     tensor view of plane k (global index; k0-1 and k1 are the halo planes) of component `comp`."""
