@@ -3,21 +3,26 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f64|f32]
 
-A "step" is one full Yee time step (H-pass + E-pass incl. PML, ADE and source) of every field set
-over the whole grid, monitors sampled every save_span steps as the reference does.
-  N = 1 : BASELINE configs[1], junctions/Au_graphene_box at production resolution (181^3 cells,
-          complex fields = 2 field sets, Drude Au + graphene sheet + Lorentz SiO2), scene fixture
-          scenes/json/Au_graphene_box.json.
-  N > 1 : the same scene in a box N times taller (z-slab per rank, weak scaling), one rank per GPU,
-          one-plane halo exchange of the tangential fields per half step over NCCL.
-`value` is timed with CUDA events with everything resident in HBM; `e2e` runs the same steps through
-the public BoundGeom API with host buffers (source table upload + monitor read-back per save inside
-the timed region).  `--impl reference` times the CPU oracle (meep-structured restatement; meep itself
-is not installable here) on the host cores on the same workload.
+A "step" is one full Yee time step (H-pass + E-pass incl. PML, ADE and source) of every field set over the whole
+grid, monitors sampled every save_span steps as the reference does (src/disp.cpp:719-741).
+
+Workload at every N: BASELINE configs[1], junctions/Au_graphene_box at production resolution -- 181^3 cells, complex
+fields = 2 field sets, Drude-Lorentz Au + graphene sheet + Lorentz SiO2, fp64 -- entered the way a user enters it:
+scenes/Au_graphene_box/params.conf + junc.geom through the package's own conf / CGS readers and BoundGeom.
+  N = 1 : the whole box on one GPU.
+  N > 1 : the SAME box cut into N z-slabs, one rank per GPU (strong scaling).  The slabs are connected inside the
+          library (CUDA-IPC peer memory): the step kernels write a slab's boundary plane straight into the neighbour's
+          halo over NVLink and the slabs order themselves through device-side flags; no collective per step.
+`value`: K steps timed with CUDA events on the simulation's stream, bracketed by barrier + synchronize, max over ranks;
+the region is repeated (--repeats, default 5) and the median is reported.  `e2e`: the same K steps through the public
+API by the host clock, with the source drive table uploaded from the host and every monitor sample read back to the
+host inside the timed region (max over ranks).  `--impl reference` times the CPU oracle (meep-structured C/OpenMP
+restatement; meep itself is not installable here) on all host cores on the same workload; rank 0 only.
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -31,15 +36,16 @@ import numpy as np  # noqa: E402
 
 SCENE = "Au_graphene_box"
 SAVE_SPAN = 20
+WORKLOAD = "junctions/Au_graphene_box 181^3 cells x 2 field sets (complex), res 10 -> 181/18"
 
 
 def load_settings():
-    with open(os.path.join(ROOT, "scenes", "json", SCENE + ".json")) as fp:
-        st = json.load(fp)["settings"]
-    from sim_juncs_b200.settings import ParseSettings
-    s = ParseSettings()
-    for k, v in st.items():
-        setattr(s, k, v)
+    """params.conf of the scene through the package's own reader (argparse.h semantics), as `sim_geom` would"""
+    from sim_juncs_b200.settings import settings_from
+    d = os.path.join(ROOT, "scenes", SCENE)
+    s = settings_from(os.path.join(d, "params.conf"))
+    s.geom_fname = os.path.join(d, os.path.basename(s.geom_fname or "junc.geom"))
+    s.save_span = SAVE_SPAN
     s.out_dir = "/tmp"
     return s
 
@@ -73,7 +79,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
@@ -85,21 +91,29 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def oracle_problem(st, nz_mult=1):
+def oracle_problem(st):
     """The same workload for the CPU oracle (masks from the C restatement of the CSG tests)."""
     from helpers import oracle_bound_geom, oracle_raster
     from sim_juncs_b200.scene import Scene
-    sc = Scene.load(os.path.join(ROOT, "scenes", "json", SCENE + ".json"))
+    sc = Scene.from_geom(st.geom_fname, st)
     masks = [oracle_raster(sc, st, c) for c in range(3)]
     o, n_t = oracle_bound_geom(sc, st, masks, nsets=2)
     return o
 
 
+def host_threads():
+    """all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)          # read by libgomp when the oracle library is loaded
+    return n
+
+
 def run_reference(args):
-    """CPU arm: the oracle port on all host threads, same config/metric/unit."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """CPU arm: the oracle port on all host threads, same workload / metric / unit as the repo arm at this N (the
+    workload does not depend on N: strong scaling).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    want = host_threads()
     from oracle import oracle as orc
     st = load_settings()
     n = st.grid_cells()
@@ -114,27 +128,22 @@ def run_reference(args):
     val = float(n) ** 3 * 2 * args.steps / dt
     line = {"impl": "reference", "metric": "yee_cell_updates_per_s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "junctions/Au_graphene_box 181^3 cells x 2 field sets (complex), res 10 -> 181/18",
-                       "scene": "scenes/Au_graphene_box/junc.geom (re-authored, see DESIGN.md)"},
-            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scene": "scenes/Au_graphene_box/junc.geom (re-authored, see DESIGN.md)"},
+            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "threads_requested": want,
                              "sample": "%d full-grid oracle steps (meep-structured C/OpenMP restatement; meep itself is absent)" % args.steps},
             "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cuda_tensor_from_ptr(torch, ptr, nbytes, device):
-    class _P:
-        pass
-    p = _P()
-    p.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-    return torch.as_tensor(p, device=device)
+def plane_weights(n, pml_cells):
+    """relative bytes per z-plane: planes inside the z-PML carry the UPML auxiliaries of every cell"""
+    return [1.22 if (k < pml_cells or k > n - pml_cells) else 1.0 for k in range(n + 1)]
 
 
 def run_ours(args):
     import torch
     from sim_juncs_b200.bound_geom import BoundGeom
-    from sim_juncs_b200.engine import Sim
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,73 +163,114 @@ def run_ours(args):
     esz = 8 if prec == "f64" else 4
     n_sets = 2
     peak, peak_src = measured_peak()
-    scene_path = os.path.join(ROOT, "scenes", "json", SCENE + ".json")
     sampler = ClockSampler(local)
+    K, W = args.steps, args.warmup
+    cells = float(n) ** 3
 
-    if world == 1:
-        bg = BoundGeom(st, scene_path, precision=prec, n_sets=n_sets, device=local)
-        sim = bg.sim
-        cells = float(n) ** 3
-        l0 = sim.launches()
-        sim.run(args.warmup, SAVE_SPAN)
-        sampler.start()
-        l1 = sim.launches()
-        ms = sim.run_timed(args.steps, SAVE_SPAN)
-        launches = sim.launches() - l1
-        extended = False
-        if len(sampler.samples) < 4:          # timed region shorter than a few nvidia-smi polls: keep the same load running
-            extended = True
-            t_end = time.time() + 1.5
-            while time.time() < t_end:
-                sim.run(50, SAVE_SPAN)
-        sampler.stop_flag = True
-        value = cells * n_sets * args.steps / (ms * 1e-3)
-        bytes_step = sim.bytes_per_step()
-        # ---- dominant kernel roofline, timed live with CUDA events on a scratch simulation ----
-        scratch = BoundGeom(st, scene_path, precision=prec, n_sets=n_sets, device=local).sim
-        scratch.run(40, SAVE_SPAN)
-        prof = scratch.profile_kernels(reps=10)
-        cnt = scratch.counts()
-        alg_e = n_sets * (cnt["interior_cells"] * (9 * esz + 3) + 3 * esz * cnt["pole_points_interior"])
-        alg_h = n_sets * cnt["interior_cells"] * 9 * esz
-        dom = "e_interior" if prof["e_interior"] >= prof["h_interior"] else "h_interior"
-        alg = alg_e if dom == "e_interior" else alg_h
-        achieved = alg / (prof[dom] * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if prec == "f64" and os.path.exists(tp):
-            traffic = json.load(open(tp))["traffic_bytes_per_pass"].get(dom)
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": traffic, "kernel_ms": prof,
-                    "algorithmic_bytes_per_launch": alg,
-                    "step": {"algorithmic_bytes": bytes_step, "achieved_gbs": bytes_step / (ms * 1e-3 / args.steps) / 1e9,
-                             "frac": bytes_step / (ms * 1e-3 / args.steps) / 1e9 / peak}}
-        del scratch
-        # ---- end to end through the public API with host buffers ----
-        bg2 = BoundGeom(st, scene_path, precision=prec, n_sets=n_sets, device=local)
-        bg2.sim.run(args.warmup, SAVE_SPAN)
-        host = torch.empty((args.steps // SAVE_SPAN + 2, bg2.sim.n_mon, n_sets), dtype=torch.float64).pin_memory()
+    kz = None
+    if world > 1:
+        from sim_juncs_b200.parallel import connect_slabs, slab_range
+        kz = slab_range(n + 1, rank, world, plane_weights(n, int(st.pml_thickness * st.resolution)))
+
+    def make():
+        bg = BoundGeom(st, None, precision=prec, n_sets=n_sets, device=local, kz=kz)
+        if world > 1:
+            connect_slabs(bg.sim, rank, world)
+        return bg
+
+    def barrier():
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        done = 0
-        d2h = 0
-        while done < args.steps:
-            chunk = min(SAVE_SPAN, args.steps - done)
-            bg2.sim.run(chunk, SAVE_SPAN, sync=False)
-            done += chunk
-        m = bg2.sim.monitors()                # D2H of every sample taken in the timed region
-        d2h = m.nbytes
-        bg2.sim.sync()
-        te = time.perf_counter() - t0
-        e2e_val = cells * n_sets * args.steps / te
-        n_src = 1
-        e2e = {"value": e2e_val, "unit": "cell-updates/s", "h2d_bytes_per_step": n_src * n_sets * 2 * esz,
-               "d2h_bytes_per_step": d2h / max(args.steps, 1),
-               "note": "BoundGeom/sj_run in save_span chunks: host-computed source table uploaded (H2D), monitor series read back to host (D2H) inside the timed region"}
-        del host
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-timed: K steps, CUDA events on the simulation's stream, repeated; median of the max over ranks ----
+    bg = make()
+    sim = bg.sim
+    sim.run(W, SAVE_SPAN)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    times = []
+    l1 = sim.launches()
+    for rep in range(args.repeats):
+        barrier()
+        ms = sim.run_timed(K, SAVE_SPAN)            # synchronises the stream on both sides of the K steps
+        barrier()
+        times.append(max_over_ranks(ms))
+    launches = (sim.launches() - l1) // args.repeats
+    extended = False
+    if len(sampler.samples) < 6 or world > 1:       # keep the same load running while nvidia-smi gets its samples
+        extended = True
+        t_end = time.time() + 1.2
+        flag = 1
+        while flag:
+            sim.run(60, SAVE_SPAN)
+            flag = int(max_over_ranks(1.0 if time.time() < t_end else 0.0)) if world > 1 else int(time.time() < t_end)
+    sampler.stop_flag = True
+    ms = statistics.median(times)
+    value = cells * n_sets * K / (ms * 1e-3)
+    bytes_step = max_over_ranks(sim.bytes_per_step()) if world == 1 else None
+    del bg, sim
+
+    # ---- end to end through the public API with host buffers: fresh simulation, K steps by the host clock ----
+    bg2 = make()
+    bg2.sim.run(W, SAVE_SPAN)
+    up0 = bg2.sim.h2d_bytes()
+    barrier()
+    t0 = time.perf_counter()
+    done = 0
+    while done < K:                                   # BoundGeom.run's own chunking (save_span steps per call)
+        chunk = min(SAVE_SPAN, K - done)
+        bg2.sim.run(chunk, SAVE_SPAN, sync=False)
+        done += chunk
+    mon = bg2.sim.monitors()                          # D2H of every sample of this rank (synchronises)
+    bg2.sim.sync()
+    te = max_over_ranks(time.perf_counter() - t0)
+    h2d = bg2.sim.h2d_bytes() - up0
+    e2e = {"value": cells * n_sets * K / te, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / K,
+           "d2h_bytes_per_step": mon.nbytes / K,
+           "note": "BoundGeom/sj_run in save_span chunks by the host clock (max over ranks); inside the timed region: the host-"
+                   "evaluated source drive table for these steps is uploaded (%d B, the warm-up table does not reach that far) "
+                   "and the monitor series is read back to the host" % int(h2d)}
+    del bg2
+
+    roofline, cpu, per_rank = None, None, None
+    if world == 1:
+        # ---- per-kernel roofline, timed live with CUDA events on a scratch simulation ----
+        scratch = make().sim
+        scratch.run(40, SAVE_SPAN)
+        prof = scratch.profile_kernels(reps=20)
+        cnt = scratch.counts()
+        alg = {"h_pass": n_sets * (cnt["cells"] * 9 * esz + 4 * esz * cnt["pml_cells"]),
+               "e_pass": n_sets * (cnt["cells"] * (9 * esz + 3) + 3 * esz * cnt["pole_points"] + 4 * esz * cnt["pml_cells"])}
+        t_ms = {"h_pass": prof["h_interior"], "e_pass": prof["e_interior"]}
+        kern = {k: {"kernel": "h_tma" if k == "h_pass" else "e_tma", "ms": t_ms[k], "algorithmic_bytes": alg[k],
+                    "achieved_gbs": alg[k] / (t_ms[k] * 1e-3) / 1e9, "frac": alg[k] / (t_ms[k] * 1e-3) / 1e9 / peak} for k in alg}
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_r2.json")
+        if prec == "f64" and os.path.exists(tp):
+            traffic = json.load(open(tp)).get(kern[dom]["kernel"])
+        step_gbs = bytes_step / (ms * 1e-3 / K) / 1e9
+        roofline = {"bound": "hbm", "kernel": kern[dom]["kernel"], "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
+                    "h_pass_ms": t_ms["h_pass"], "h_pass_bytes": alg["h_pass"], "h_pass_frac": kern["h_pass"]["frac"],
+                    "e_pass_ms": t_ms["e_pass"], "e_pass_bytes": alg["e_pass"], "e_pass_frac": kern["e_pass"]["frac"],
+                    "step_algorithmic_bytes": bytes_step, "step_achieved_gbs": step_gbs, "step_frac": step_gbs / peak,
+                    "families": "the step is two persistent TMA kernels, each covering interior, PML-face and PML-edge cells "
+                                "of its half-pass; the four r1 families are inside them"}
+        del scratch
         # ---- CPU baseline: the oracle on a bounded sample of the same workload ----
-        cpu = None
         if not args.no_cpu:
+            host_threads()
             from oracle import oracle as orc
             o = oracle_problem(st)
             o.step()
@@ -232,107 +282,23 @@ def run_ours(args):
             tc = time.time() - t0
             cpu = {"value": cells * 2 * k / tc, "unit": "cell-updates/s", "cores": orc.lib().orc_num_threads(), "kind": "port",
                    "sample": "%d full-grid steps of the same 181^3 x 2-set workload (oracle/fdtd_oracle.c, OpenMP)" % k}
-        line = {"metric": "yee_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": prec, "data": "synthetic",
-                "config": {"workload": "junctions/Au_graphene_box 181^3 cells x 2 field sets (complex), res 10 -> 181/18",
-                           "scene": "scenes/Au_graphene_box/junc.geom (re-authored, see DESIGN.md)", "save_span": SAVE_SPAN,
-                           "l2": "working set %.0f MB per step >> 126 MB L2 (no flush needed)" % (bytes_step / 1e6)},
+    if rank == 0:
+        cfg = {"workload": WORKLOAD, "scene": "scenes/Au_graphene_box/params.conf + junc.geom (re-authored, see DESIGN.md) through the own conf/CGS readers",
+               "save_span": SAVE_SPAN, "repeats": args.repeats, "ms_per_step_all_repeats": [t / K for t in times],
+               "l2": "fields + auxiliaries of a step (2.4 GB) >> 126 MB L2; no flush needed"}
+        if world > 1:
+            cfg["decomposition"] = "%d z-slabs of the same box, %s planes; boundary planes written into the neighbour's halo by the step " \
+                                   "kernels (peer stores over NVLink, CUDA-IPC mapped), device-side flags, one CUDA graph per step and rank" \
+                                   % (world, "/".join(str(b - a) for a, b in [slab_range(n + 1, r, world, plane_weights(n, int(st.pml_thickness * st.resolution))) for r in range(world)]))
+        line = {"metric": "yee_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": prec, "data": "synthetic", "config": cfg,
                 "clocks": dict(sampler.summary(), extended_sampling=extended), "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
-        return
-
-    # ------------------------------------------------------------------ N > 1: z-slabs, weak scaling
-    st_tall_n2 = n * world                     # box world x taller in z
-    from sim_juncs_b200.parallel import slab_range
-    kz = slab_range(st_tall_n2 + 1, rank, world)
-    from sim_juncs_b200.scene import LIGHT_SPEED, Scene
-    sc = Scene.load(scene_path)
-    sim = Sim((n, n, st_tall_n2), st.resolution, pml=st.pml_thickness, precision=prec, n_sets=n_sets, kz=kz, device=local)
-    nodes = sc.node_array()
-    regions = []
-    for reg in sc.regions:
-        thick = 1.0 / st.resolution if reg.make_2d else 1.0
-        if reg.make_2d:
-            for i in range(3):
-                nodes[reg.root].M[3 * i + 2] = nodes[reg.root].M[3 * i + 2] * thick
-        regions.append((reg.root, reg.eps if reg.eps is not None else st.ambient_eps,
-                        [(w0 / st.um_scale, g / st.um_scale, sg / thick, not ud) for (w0, g, sg, ud) in reg.poles_raw]))
-    sim.rasterize(st.ambient_eps, nodes, regions)
-    info, (p1, p2) = sc.sources[0], sc.source_boxes[0]
-    cba = LIGHT_SPEED * st.um_scale
-    sim.add_gaussian_source(info.component, p1, p2, info.amplitude, 1 / (info.wavelen * st.um_scale), info.width * cba,
-                            info.phase, info.start_time * cba, info.end_time * cba, True)
-    sim.add_monitors(np.array(sc.monitor_locs), comp=0)
-    from sim_juncs_b200.parallel import SlabRunner
-    runner = SlabRunner(sim, kz, n_sets, dev, save_span=SAVE_SPAN, overlap=not args.no_overlap)
-    stream = runner.tstream                    # the stream the kernels and the NCCL ordering live on
-
-    def step(i):
-        runner.step()
-
-    for i in range(args.warmup):
-        step(i)
-    dist.barrier()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    l1 = sim.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0 and len(sampler.samples) < 4:
-        t_end = time.time() + 1.5
-        flag = torch.ones(1, device=dev)
-    else:
-        t_end = 0.0
-        flag = torch.zeros(1, device=dev)
-    dist.broadcast(flag, 0)
-    if flag.item() > 0:                       # keep the same load running while nvidia-smi samples
-        for i in range(300):
-            step(args.warmup + args.steps + i)
-        torch.cuda.synchronize()
-    sampler.stop_flag = True
-    ms = float(ms.item())
-    cells = float(n) * n * st_tall_n2
-    value = cells * n_sets * args.steps / (ms * 1e-3)
-    # ---- end to end: the same K steps by the host clock, each rank's monitor series read back to the host
-    #      (D2H) inside the timed region; max over ranks
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    runner.synchronize()
-    mon = sim.monitors()
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = cells * n_sets * args.steps / float(te.item())
-    launches = (sim.launches() - l1) * args.steps // max(runner.i - args.warmup, 1)
-    if rank == 0:
-        line = {"metric": "yee_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": prec, "data": "synthetic",
-                "config": {"workload": "Au_graphene_box scene in a box %dx taller in z: %dx%dx%d cells x 2 field sets, one z-slab per GPU" % (world, n, n, st_tall_n2),
-                           "halo": "Hx,Hy up / Ex,Ey down, one plane per half step, NCCL send/recv" +
-                                   ("" if args.no_overlap else ", boundary plane first and on the wire while the rest of the slab runs"),
-                           "save_span": SAVE_SPAN},
-                "clocks": sampler.summary(), "gpu_launches": launches,
-                "e2e": {"value": e2e_val, "unit": "cell-updates/s", "h2d_bytes_per_step": 2 * n_sets * 2 * esz,
-                        "d2h_bytes_per_step": mon.nbytes / max(runner.i, 1),
-                        "note": "SlabRunner.step loop by the host clock (max over ranks), source table uploads and the read-back of every rank's monitor series inside the timed region"},
-                "halo_bytes_per_step_per_rank": runner.halo.bytes_per_step(),
-                "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line))
-    dist.destroy_process_group()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -340,12 +306,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--repeats", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange the halos after each full half-pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.repeats = max(args.repeats, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -209,16 +209,17 @@ int sj_run_group(sj_sim **sims, int32_t n_slabs, int64_t n_steps, int32_t save_s
 int sj_get_field(sj_sim *sim, int comp, int set, double *out);
 /* sj_run bracketed by CUDA events on the simulation's stream; *ms = device time of the n_steps. */
 int sj_run_timed(sj_sim *sim, int64_t n_steps, int32_t save_span, double *ms);
-/* Average device time (ms, CUDA events, `reps` back-to-back launches each) of the four kernel
- * families over the owned slab: out[0] H interior, out[1] E interior, out[2] H PML boxes (all),
- * out[3] E PML boxes (all).  Advances nothing logically (call on a scratch simulation). */
+/* Average device time (ms, CUDA events, `reps` back-to-back launches each) of the step's kernels over the owned slab:
+ * out[0] the H-pass kernel, out[1] the E-pass kernel (each one persistent TMA kernel covering interior and PML cells;
+ * out[2] = out[3] = 0).  With SJ_TMA=0 (register kernels): H interior, E interior, H PML lists, E PML lists.
+ * Advances nothing logically (call on a scratch simulation). */
 int sj_profile_kernels(sj_sim *sim, int32_t reps, double out[4]);
 /* out[0] owned cells, out[1] interior-kernel cells, out[2] PML-kernel cells, out[3] pole-points
  * (sum over E-component points of n_poles) in the slab, out[4] pole-points inside the interior
  * box, out[5] true PML cells (any sigma != 0). */
 int sj_get_counts(sj_sim *sim, double out[6]);
-/* Per-run statistics for bench.py: kernels launched and device-timed milliseconds so far. */
-int sj_get_stats(const sj_sim *sim, int64_t *kernel_launches, double *reserved);
+/* Per-run statistics for bench.py: kernels launched so far and bytes of source drive table uploaded (host -> device). */
+int sj_get_stats(const sj_sim *sim, int64_t *kernel_launches, double *h2d_bytes);
 /* Algorithmic bytes one full step moves for this configuration. */
 double sj_bytes_per_step(const sj_sim *sim);
 

@@ -62,6 +62,7 @@ static int upload_sig(sj_sim *s, int d) {
 static int alloc_zero(sj_sim *s, void **p, size_t bytes) {
     CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
     CK(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+    CK(cudaDeviceSynchronize());        // the legacy-stream fill is not ordered with the simulation's non-blocking stream
     return 0;
 }
 
@@ -471,6 +472,17 @@ int sj_finish_materials(sj_sim *s) {
     std::vector<sj_material> sorted(nm);
     for (int nw = 0; nw < nm; ++nw) { sorted[nw] = s->mats[order[nw]]; lut[order[nw]] = (uint8_t)nw; s->lut_inv[nw] = (uint8_t)order[nw]; ident &= (order[nw] == nw); }
     s->mats_sorted = sorted;
+    {   // every index byte must name a table entry (an unknown id would be remapped to material 0 silently)
+        unsigned *dh; CK(cudaMalloc((void **)&dh, 256 * sizeof(unsigned))); CK(cudaMemset(dh, 0, 256 * sizeof(unsigned)));
+        CK(cudaDeviceSynchronize());
+        for (int c = 0; c < 3; ++c)
+            present_kernel<<<296, 256, 0, s->stream>>>(s->mat[c] + s->plane, s->plane * (s->nzl - 2), dh);
+        unsigned hh[256];
+        CK(cudaMemcpyAsync(hh, dh, sizeof hh, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        cudaFree(dh);
+        for (int i = nm; i < 256; ++i) if (hh[i]) return fail(s, SJ_ERR_ARG, "material index outside the material table");
+    }
     if (!ident) {
         uint8_t *dl; CK(cudaMalloc((void **)&dl, 256)); CK(cudaMemcpy(dl, lut, 256, cudaMemcpyHostToDevice));
         for (int c = 0; c < 3; ++c)
@@ -747,6 +759,7 @@ static int ensure_drive(sj_sim *s, long long upto) {
     cudaFree(s->drive); s->drive = NULL;
     int rc = s->prec == SJ_F64 ? upload_vec<double>(s, tab, &s->drive) : upload_vec<float>(s, tab, &s->drive);
     if (rc) return rc;
+    s->h2d_bytes += (double)tab.size() * s->esz;
     s->drive_steps = steps; s->drive_dirty = false;
     return 0;
 }
@@ -816,6 +829,9 @@ static int ensure_series(sj_sim *s, int need) {
     const int cap = std::max(need, 2 * s->series_cap);
     double *nw;
     const size_t row = (size_t)s->n_mon * s->g.n_sets;
+    // sj_sample / sj_pass take caller streams that are not ordered with s->stream: everything queued anywhere on the device
+    // must have written the old buffer before it is copied and freed
+    CK(cudaDeviceSynchronize());
     CK(cudaMalloc((void **)&nw, cap * row * sizeof(double)));
     CK(cudaMemsetAsync(nw, 0, cap * row * sizeof(double), s->stream));
     if (s->series) CK(cudaMemcpyAsync(nw, s->series, (size_t)s->n_samples * row * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
@@ -1081,6 +1097,24 @@ extern "C" int sj_profile_kernels(sj_sim *s, int32_t reps, double out[4]) {
     if (!s || !out || reps < 1) return SJ_ERR_ARG;
     cudaSetDevice(s->g.device);
     int rc = ensure_drive(s, s->steps_done + 1); if (rc) return rc;
+    if (s->tma.mode == 3 && s->n_slots <= 2) {
+        // the step is two persistent kernels (csrc/sj_tma.cuh): out[0] = the H-pass kernel, out[1] = the E-pass kernel, each
+        // timed alone with CUDA events over `reps` back-to-back launches; the PML cells are inside them (out[2] = out[3] = 0)
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int which = 0; which < 2; ++which) {
+            for (int rep = -2; rep < reps; ++rep) {
+                if (rep == 0) CK(cudaEventRecord(e0, s->stream));
+                rc = do_pass(s, which, s->kz0, s->kz1, s->stream); if (rc) return rc;
+            }
+            CK(cudaEventRecord(e1, s->stream));
+            CK(cudaEventSynchronize(e1));
+            float f = 0; CK(cudaEventElapsedTime(&f, e0, e1));
+            out[which] = f / reps; out[2 + which] = 0.0;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return SJ_OK;
+    }
     return s->prec == SJ_F64 ? sj_profile_f64(s, reps, out) : sj_profile_f32(s, reps, out);
 }
 
@@ -1254,7 +1288,7 @@ extern "C" int sj_get_field(sj_sim *s, int comp, int set, double *out) {
 extern "C" int sj_get_stats(const sj_sim *s, int64_t *launches, double *reserved) {
     if (!s) return SJ_ERR_ARG;
     if (launches) *launches = s->launches;
-    if (reserved) *reserved = 0.0;
+    if (reserved) *reserved = s->h2d_bytes;     // bytes of source drive table uploaded so far (host -> device)
     return SJ_OK;
 }
 

@@ -216,6 +216,7 @@ struct sj_sim {
     double pole_points;       // sum over E component points of n_poles (owned slab)
     double pole_points_int;   // same, restricted to the interior-kernel box
     double pml_cells;
+    double h2d_bytes = 0;     // source drive table bytes uploaded so far
     TmaState tma;
     // z-slab neighbours: raw peer pointers (same process) or CUDA-IPC mappings (other processes)
     struct Peer { void *F = nullptr; void *sync = nullptr; long long fcs = 0, set_stride = 0; int nzl = 0; bool ipc = false; };

@@ -275,6 +275,12 @@ class Sim:
         self.L.sj_get_stats(self.h, C.byref(n), None)
         return n.value
 
+    def h2d_bytes(self):
+        """bytes of source drive table uploaded to the device so far"""
+        b = C.c_double()
+        self.L.sj_get_stats(self.h, None, C.byref(b))
+        return b.value
+
     def bytes_per_step(self):
         return self.L.sj_bytes_per_step(self.h)
 

@@ -29,9 +29,11 @@ def slab_range(n_planes, rank, world, weights=None):
     while len(cuts) < world:
         cuts.append(n_planes)
     cuts.append(n_planes)
-    for r in range(1, world + 1):          # every rank owns at least one plane
-        cuts[r] = max(cuts[r], cuts[r - 1] + 1)
     cuts[world] = n_planes
+    for r in range(1, world):              # every rank owns at least one plane: push up from below, then down from above
+        cuts[r] = max(cuts[r], cuts[r - 1] + 1)
+    for r in range(world - 1, 0, -1):
+        cuts[r] = min(cuts[r], cuts[r + 1] - 1)
     return cuts[rank], cuts[rank + 1]
 
 
