@@ -28,6 +28,9 @@ import sys
 import threading
 import time
 
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, where the one JSON line belongs
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

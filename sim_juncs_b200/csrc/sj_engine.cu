@@ -165,7 +165,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
     {
         const int L[3] = {s->lo[0], s->lo[1], s->lo[2]}, Hh[3] = {s->hi[0], s->hi[1], s->hi[2]};
         const int N1[3] = {n[0] + 1, n[1] + 1, n[2] + 1};
-        int bl[SJ_N_PML_BOX][3], bh[SJ_N_PML_BOX][3];
+        int bl[6][3], bh[6][3];
         // z-low, z-high: full xy ; y-low, y-high: z interior ; x-low, x-high: y,z interior
         int q = 0;
         bl[q][0] = 0; bh[q][0] = N1[0]; bl[q][1] = 0; bh[q][1] = N1[1]; bl[q][2] = 0; bh[q][2] = L[2]; ++q;
@@ -174,25 +174,51 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
         bl[q][0] = 0; bh[q][0] = N1[0]; bl[q][1] = Hh[1]; bh[q][1] = N1[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
         bl[q][0] = 0; bh[q][0] = L[0]; bl[q][1] = L[1]; bh[q][1] = Hh[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
         bl[q][0] = Hh[0]; bh[q][0] = N1[0]; bl[q][1] = L[1]; bh[q][1] = Hh[1]; bl[q][2] = L[2]; bh[q][2] = Hh[2]; ++q;
-        for (int b = 0; b < SJ_N_PML_BOX; ++b) {
-            sj_sim::Box B;
-            for (int d = 0; d < 3; ++d) { B.lo[d] = bl[b][d]; B.hi[d] = bh[b][d]; }
-            B.lo[2] = std::max(B.lo[2], s->kz0); B.hi[2] = std::min(B.hi[2], s->kz1);
-            B.bx = B.hi[0] - B.lo[0]; B.by = B.hi[1] - B.lo[1]; B.bz = B.hi[2] - B.lo[2];
-            if (B.bx <= 0 || B.by <= 0 || B.bz <= 0) continue;
-            B.bpitch = ((B.bx + 3) / 4) * 4;
-            B.bplane = (long long)B.bpitch * B.by;
-            B.bset = B.bplane * B.bz;
-            const size_t bytes = (size_t)B.bset * g->n_sets * s->esz;
-            {
-                int rc = alloc_zero(s, &B.base, 12 * bytes); if (rc) return rc;
+        // Every shell box is cut into rectangles: the part with a single non-zero sigma ("face", kind = its normal
+        // direction) and the frame around it where sigmas overlap (kind 0: edges, corners).  Each rectangle is a region
+        // with its own compact allocation: a face keeps only the normal component's D and B (2 arrays), a frame the full
+        // [D(3) | B(3) | U_D(3) | U_B(3)].
+        const int N1x = N1[0], N1y = N1[1];
+        for (int b = 0; b < 6; ++b) {
+            const int zlo = std::max(bl[b][2], s->kz0), zhi = std::min(bh[b][2], s->kz1);
+            if (zlo >= zhi) continue;
+            struct Rect { int i0, i1, j0, j1, kind; };
+            std::vector<Rect> rects;
+            const bool zbox = b < 2, ybox = b >= 2 && b < 4;
+            if (zbox) {
+                rects.push_back({L[0], Hh[0], L[1], Hh[1], 3});
+                rects.push_back({0, N1x, 0, L[1], 0}); rects.push_back({0, N1x, Hh[1], N1y, 0});
+                rects.push_back({0, L[0], L[1], Hh[1], 0}); rects.push_back({Hh[0], N1x, L[1], Hh[1], 0});
+            } else if (ybox) {
+                rects.push_back({L[0], Hh[0], bl[b][1], bh[b][1], 2});
+                rects.push_back({0, L[0], bl[b][1], bh[b][1], 0}); rects.push_back({Hh[0], N1x, bl[b][1], bh[b][1], 0});
+            } else rects.push_back({bl[b][0], bh[b][0], bl[b][1], bh[b][1], 1});
+            for (const Rect &R : rects) {
+                sj_sim::Box B;
+                B.lo[0] = R.i0; B.hi[0] = R.i1; B.lo[1] = R.j0; B.hi[1] = R.j1; B.lo[2] = zlo; B.hi[2] = zhi;
+                B.kind = R.kind; B.narr = R.kind ? 2 : 12;
+                B.bx = B.hi[0] - B.lo[0]; B.by = B.hi[1] - B.lo[1]; B.bz = B.hi[2] - B.lo[2];
+                if (B.bx <= 0 || B.by <= 0 || B.bz <= 0) continue;
+                if ((int)s->boxes.size() >= SJ_N_PML_BOX) return fail(s, SJ_ERR_UNSUPPORTED, "too many PML regions");
+                B.bpitch = ((B.bx + 3) / 4) * 4;
+                B.bplane = (long long)B.bpitch * B.by;
+                B.bset = B.bplane * B.bz;
+                const size_t bytes = (size_t)B.bset * g->n_sets * s->esz;
+                int rc = alloc_zero(s, &B.base, (size_t)B.narr * bytes); if (rc) return rc;
                 for (int c = 0; c < 3; ++c) {
-                    B.D[c] = (char *)B.base + (size_t)c * bytes; B.B[c] = (char *)B.base + (size_t)(3 + c) * bytes;
-                    B.UD[c] = (char *)B.base + (size_t)(6 + c) * bytes; B.UB[c] = (char *)B.base + (size_t)(9 + c) * bytes;
+                    if (B.kind) {   // only component kind-1 exists: D at array 0, B at array 1; the other pointers are never used
+                        const long long off = (long long)(c - (B.kind - 1)) * (long long)bytes;
+                        B.D[c] = (char *)B.base + off; B.B[c] = (char *)B.base + (long long)bytes + off;
+                        B.UD[c] = B.base; B.UB[c] = B.base;
+                    } else {
+                        B.D[c] = (char *)B.base + (size_t)c * bytes; B.B[c] = (char *)B.base + (size_t)(3 + c) * bytes;
+                        B.UD[c] = (char *)B.base + (size_t)(6 + c) * bytes; B.UB[c] = (char *)B.base + (size_t)(9 + c) * bytes;
+                    }
                 }
+                s->pml_cells += (double)B.bx * B.by * B.bz;
+                s->pml_bytes += (double)B.narr * bytes;
+                s->boxes.push_back(B);
             }
-            s->pml_cells += (double)B.bx * B.by * B.bz;
-            s->boxes.push_back(B);
         }
     }
     // work lists of the tiled PML kernels: one entry per thread block.  Every box is cut into
@@ -213,18 +239,7 @@ extern "C" int sj_create(const sj_grid *g, sj_sim **out) {
             const sj_sim::Box &B = s->boxes[bi];
             struct Rect { int i0, i1, j0, j1, kind; };
             std::vector<Rect> rects;
-            const bool zbox = (B.lo[0] == 0 && B.hi[0] == N1x && B.lo[1] == 0 && B.hi[1] == N1y);
-            const bool ybox = !zbox && (B.lo[0] == 0 && B.hi[0] == N1x);
-            if (zbox) {
-                rects.push_back({L[0], Hh[0], L[1], Hh[1], 3});
-                rects.push_back({0, N1x, 0, L[1], 0}); rects.push_back({0, N1x, Hh[1], N1y, 0});
-                rects.push_back({0, L[0], L[1], Hh[1], 0}); rects.push_back({Hh[0], N1x, L[1], Hh[1], 0});
-            } else if (ybox) {
-                rects.push_back({L[0], Hh[0], B.lo[1], B.hi[1], 2});
-                rects.push_back({0, L[0], B.lo[1], B.hi[1], 0}); rects.push_back({Hh[0], N1x, B.lo[1], B.hi[1], 0});
-            } else {
-                rects.push_back({B.lo[0], B.hi[0], B.lo[1], B.hi[1], 1});
-            }
+            rects.push_back({B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.kind});
             for (const Rect &R : rects) {
                 if (R.i1 <= R.i0 || R.j1 <= R.j0) continue;
                 const bool nar = (R.i1 - R.i0 <= s->pml_lx_n * V);
@@ -324,11 +339,13 @@ static int upload_material_table(sj_sim *s) {
     if (rc) return rc;
     CK(cudaMalloc((void **)&s->mt_np, SJ_MAX_MAT * sizeof(int)));
     CK(cudaMemcpy(s->mt_np, np.data(), SJ_MAX_MAT * sizeof(int), cudaMemcpyHostToDevice));
-    // polarisation slots (dense over the slab; loads are skipped where the material has no pole)
-    if (slots != s->n_slots || !s->Pall) {
+    // polarisation slots: [parity][slot][comp][set] arrays over the local planes [p_k0, p_k0 + p_nzp) that hold a pole
+    // material (set by sj_finish_materials before this call); loads are skipped where the material has no pole
+    if (slots != s->n_slots || !s->Pall || s->p_k0 != s->p_alloc_k0 || s->p_nzp != s->p_alloc_nzp) {
         cudaFree(s->Pall); s->Pall = NULL;
-        const size_t bytes = (size_t)2 * std::max(slots, 1) * 3 * s->set_stride * s->g.n_sets * s->esz;
+        const size_t bytes = (size_t)2 * std::max(slots, 1) * 3 * s->plane * s->p_nzp * s->g.n_sets * s->esz;
         rc = alloc_zero(s, &s->Pall, bytes); if (rc) return rc;
+        s->p_alloc_k0 = s->p_k0; s->p_alloc_nzp = s->p_nzp; s->p_bytes = (double)bytes;
     }
     for (int q = 0; q < SJ_MAX_POLES; ++q) {
         s->np_thr[q] = 1 << 30;
@@ -350,6 +367,14 @@ __global__ void count_pole_points(const uint8_t *mat, const int *np, long long p
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// flags[kl] = 1 if plane kl of the material array holds an id with poles (ids >= first_disp)
+__global__ void plane_pole_kernel(const uint8_t *mat, long long plane, int first_disp, int *flags) {
+    const uint8_t *a = mat + (long long)blockIdx.y * plane;
+    int any = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane && !any; t += (long long)gridDim.x * blockDim.x) any |= (a[t] >= first_disp);
+    if (__syncthreads_or(any) && threadIdx.x == 0) flags[blockIdx.y] = 1;
 }
 
 __global__ void present_kernel(const uint8_t *a, long long n, unsigned *hist) {
@@ -500,6 +525,21 @@ int sj_finish_materials(sj_sim *s) {
         CK(cudaStreamSynchronize(s->stream));
         cudaFree(dh);
         for (int i = 0; i < 256; ++i) s->present[i] = hh[i] != 0;
+    }
+    {   // local planes that hold a pole material (any E component): only those get polarisation storage
+        int *df; CK(cudaMalloc((void **)&df, s->nzl * sizeof(int))); CK(cudaMemset(df, 0, s->nzl * sizeof(int)));
+        CK(cudaDeviceSynchronize());
+        for (int c = 0; c < 3; ++c)
+            plane_pole_kernel<<<dim3(8, s->nzl), 256, 0, s->stream>>>(s->mat[c], s->plane, s->first_disp, df);
+        std::vector<int> hf(s->nzl);
+        CK(cudaMemcpyAsync(hf.data(), df, hf.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        cudaFree(df);
+        int a = -1, b = -1;
+        for (int kl = 1; kl < s->nzl - 1; ++kl) if (hf[kl]) { if (a < 0) a = kl; b = kl; }
+        static const bool dense = getenv("SJ_P_DENSE") != NULL;
+        if (dense) { a = 0; b = s->nzl - 1; }
+        s->p_k0 = a < 0 ? 1 : a; s->p_nzp = a < 0 ? 1 : b - a + 1;
     }
     int rc = upload_material_table(s); if (rc) return rc;
     rc = count_box(s, 0, s->g.n[0] + 1, 0, s->g.n[1] + 1, s->kz0, s->kz1, &s->pole_points); if (rc) return rc;
@@ -842,11 +882,14 @@ static int ensure_series(sj_sim *s, int need) {
 }
 
 // ---- kernel parameter assembly + launches ------------------------------------------------------
-static int do_pass(sj_sim *s, int which, int k0, int k1, cudaStream_t st) {
+static bool tma_step(const sj_sim *s) { return s->tma.mode == 3 && s->n_slots <= 2 && !s->trace_reg; }
+
+// tick: the E-pass kernel of a full step also advances the device step counter (TMA path only; see tma_step)
+static int do_pass(sj_sim *s, int which, int k0, int k1, cudaStream_t st, bool tick = false) {
     // whole-slab passes go through the TMA-staged column kernels (sj_tma.cuh); plane-restricted ones and scenes with more
     // than two pole slots through the register kernels
     if (((s->tma.mode >> which) & 1) && k0 <= s->kz0 && k1 >= s->kz1 && (which == 0 || s->n_slots <= 2) && !s->trace_reg)
-        return s->prec == SJ_F64 ? sj_tma_pass_f64(s, which, st) : sj_tma_pass_f32(s, which, st);
+        { const bool tk = tick && tma_step(s); return s->prec == SJ_F64 ? sj_tma_pass_f64(s, which, st, tk) : sj_tma_pass_f32(s, which, st, tk); }
     return s->prec == SJ_F64 ? sj_launch_pass_f64(s, which, k0, k1, st) : sj_launch_pass_f32(s, which, k0, k1, st);
 }
 
@@ -922,8 +965,8 @@ static int graph_build(sj_sim *s) {
     const long long l0 = s->launches;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = do_pass(s, 0, s->kz0, s->kz1, s->stream);
-    if (!rc) rc = do_pass(s, 1, s->kz0, s->kz1, s->stream);
-    if (!rc) { tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev); s->launches++; }
+    if (!rc) rc = do_pass(s, 1, s->kz0, s->kz1, s->stream, true);
+    if (!rc && !tma_step(s)) { tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev); s->launches++; }
     cudaGraph_t g = NULL;
     const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
     s->graph_launches = s->launches - l0; s->launches = l0;
@@ -952,9 +995,9 @@ static int run_range(sj_sim *s, int64_t i0, int64_t i1, int32_t save_span, long 
             }
         }
         rc = do_pass(s, 0, s->kz0, s->kz1, st); if (rc) return rc;
-        rc = do_pass(s, 1, s->kz0, s->kz1, st); if (rc) return rc;
-        tick_kernel<<<1, 1, 0, st>>>(s->step_dev);
-        s->steps_done++; s->launches++;
+        rc = do_pass(s, 1, s->kz0, s->kz1, st, true); if (rc) return rc;
+        if (!tma_step(s)) { tick_kernel<<<1, 1, 0, st>>>(s->step_dev); s->launches++; }
+        s->steps_done++;
     }
     CK(cudaGetLastError());
     return SJ_OK;
@@ -1147,8 +1190,9 @@ extern "C" int sj_trace_step(sj_sim *s) {
     s->trace_on = true; s->tr_ev.clear(); s->tr_name.clear();
     CK(cudaEventCreate(&s->tr_origin)); CK(cudaEventRecord(s->tr_origin, s->stream));
     rc = do_pass(s, 0, s->kz0, s->kz1, s->stream); if (rc) return rc;
-    rc = do_pass(s, 1, s->kz0, s->kz1, s->stream); if (rc) return rc;
-    tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev); s->steps_done++;
+    rc = do_pass(s, 1, s->kz0, s->kz1, s->stream, true); if (rc) return rc;
+    if (!tma_step(s)) tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev);
+    s->steps_done++;
     s->trace_on = false;
     CK(cudaStreamSynchronize(s->stream));
     for (int a = 0; a < s->n_aux; ++a) CK(cudaStreamSynchronize(s->aux[a]));

@@ -9,7 +9,7 @@
 
 #define SJ_MAX_SRC 4
 #define SJ_MAX_MAT 256
-#define SJ_N_PML_BOX 6
+#define SJ_N_PML_BOX 18         // regions of the PML shell: 2 z boxes x 5 + 2 y boxes x 3 + 2 x boxes
 #define SJ_N_AUX 10
 
 // ---- kernel parameter blocks (passed by value) ---------------------------------------------
@@ -36,8 +36,10 @@ struct KParams {
     T *E[3];
     T *H[3];
     const uint8_t *mat[3];
-    T *Pall;              // polarisation: [parity][slot][comp][set][...] in one allocation
+    T *Pall;              // polarisation: [parity][slot][comp][set][planes p_k0 .. p_k0 + p_nzp) of the slab] in one allocation
     long long p_comp_stride;
+    long long p_set_stride;   // p_nzp * plane: only the local planes [p_k0, p_k0 + p_nzp) that hold pole materials are stored
+    int p_k0, p_nzp;
     int n_slots;
     int np_thr[SJ_MAX_POLES]; // material ids >= np_thr[s] have more than s poles (table sorted by pole count)
     const T *mt_chi;      // [SJ_MAX_MAT] 1/eps_inf
@@ -166,6 +168,8 @@ struct sj_sim {
     uint8_t *masks[3];        // region masks from the rasterizer (same layout)
     bool smoothed = false;    // materials come from the smooth_n > 0 rasterizer (ids are not region masks)
     void *Pall;
+    int p_alloc_k0 = -1, p_alloc_nzp = -1; double p_bytes = 0;
+    int p_k0 = 1, p_nzp = 1;  // local planes [p_k0, p_k0 + p_nzp) have polarisation storage (the planes that hold pole materials)
     int n_slots;
     int np_thr[SJ_MAX_POLES];
     void *mt_chi, *mt_eps, *mt_coef; int *mt_np;
@@ -187,7 +191,7 @@ struct sj_sim {
     std::vector<sj_material> mats;         // as given by the caller / rasterizer (id = caller id)
     std::vector<sj_material> mats_sorted;  // device order: non-dispersive first
 
-    struct Box { int lo[3], hi[3]; int bx, by, bz, bpitch; long long bplane, bset; void *base; void *D[3], *B[3], *UD[3], *UB[3]; };
+    struct Box { int lo[3], hi[3]; int bx, by, bz, bpitch; int kind, narr; long long bplane, bset; void *base; void *D[3], *B[3], *UD[3], *UB[3]; };
     std::vector<Box> boxes;
 
     std::vector<HostSource> srcs;
@@ -216,6 +220,7 @@ struct sj_sim {
     double pole_points;       // sum over E component points of n_poles (owned slab)
     double pole_points_int;   // same, restricted to the interior-kernel box
     double pml_cells;
+    double pml_bytes = 0;     // bytes of UPML auxiliary storage
     double h2d_bytes = 0;     // source drive table bytes uploaded so far
     TmaState tma;
     // z-slab neighbours: raw peer pointers (same process) or CUDA-IPC mappings (other processes)
@@ -249,8 +254,8 @@ int sj_classify_items(sj_sim *s, const std::vector<WorkItem> &items, int tile_w,
 int sj_tma_build_geometry(sj_sim *s);          // shapes + geometry items + H-pass schedules (once, at create)
 int sj_tma_build_materials(sj_sim *s);         // tensor maps + E-pass schedules (after every material upload)
 void sj_tma_free(sj_sim *s);
-int sj_tma_pass_f64(sj_sim *s, int which, cudaStream_t st);
-int sj_tma_pass_f32(sj_sim *s, int which, cudaStream_t st);
+int sj_tma_pass_f64(sj_sim *s, int which, cudaStream_t st, bool tick);
+int sj_tma_pass_f32(sj_sim *s, int which, cudaStream_t st, bool tick);
 // sj_raster.cu
 int sj_raster_launch(sj_sim *s, double ambient_eps, int n_nodes, const sj_csg_node *nodes, int n_regions,
                      const sj_region *regions, int smooth_n, double smooth_rad);

@@ -109,6 +109,11 @@ template <typename T>
 __device__ __forceinline__ int pole_count(const KParams<T> &p, int m) {
     return (m >= p.np_thr[0]) + (m >= p.np_thr[1]) + (m >= p.np_thr[2]) + (m >= p.np_thr[3]);
 }
+// offset that turns a field index xg (set, local plane, row, x) into the index of the same point in a polarisation array
+template <typename T>
+__device__ __forceinline__ long long pol_shift(const KParams<T> &p, int set) {
+    return (long long)set * (p.set_stride - p.p_set_stride) + (long long)p.p_k0 * p.plane;
+}
 // base of the parity-`par` half; (slot s, component c) sits at + (3 s + c) * p_comp_stride
 template <typename T>
 __device__ __forceinline__ T *pol_base(const KParams<T> &p, int par) {
@@ -363,7 +368,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
         if (st) {
             ex.load(pE); ey.load((pE + fcs)); ez.load((pE + fcs2));
             if (GEN) {
-                pol.load(p, parity, xg, mx, my, mz);
+                pol.load(p, parity, xg - pol_shift(p, set), mx, my, mz);
                 // material bytes of the next plane (a halo plane always exists)
                 load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
             }
@@ -397,7 +402,7 @@ __device__ __forceinline__ void e_interior_body(const KParams<T> &p, const IntGe
             }
             ex.store(pE); ey.store((pE + fcs)); ez.store((pE + fcs2));
             if (GEN) {
-                pol.store(p, parity, xg);
+                pol.store(p, parity, xg - pol_shift(p, set));
 #pragma unroll
                 for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; }
             }
@@ -482,7 +487,7 @@ __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const I
     const long long plane = p.plane;
     const int pitch = p.pitch;
     const bool edge = st && (lx == 0) && (i0 > 0);
-    const long long pcs = p.p_comp_stride;
+    const long long pcs = p.p_comp_stride, psh = pol_shift(p, set);
     const T *bcur = p.Pall + (long long)parity * p.n_slots * 3 * pcs;          // parity half read as "current"
     T *bprv = p.Pall + (long long)(parity ^ 1) * p.n_slots * 3 * pcs;          // read as "previous", written as new
 
@@ -509,8 +514,8 @@ __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const I
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const bool nd_ = st && ((nd >> (3 * s + c)) & 1u);
-                sg.issue(stg, 8 + (c * NS + s) * 2, bcur + (3 * s + c) * pcs + xgp, nd_);
-                sg.issue(stg, 9 + (c * NS + s) * 2, bprv + (3 * s + c) * pcs + xgp, nd_);
+                sg.issue(stg, 8 + (c * NS + s) * 2, bcur + (3 * s + c) * pcs + (xgp - psh), nd_);
+                sg.issue(stg, 9 + (c * NS + s) * 2, bprv + (3 * s + c) * pcs + (xgp - psh), nd_);
             }
     };
 
@@ -598,7 +603,7 @@ __device__ __forceinline__ void e_interior_stg_body(const KParams<T> &p, const I
             for (int s = 0; s < NS; ++s)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    if ((need_c >> (3 * s + c)) & 1u) pp[c][s].store(bprv + (3 * s + c) * pcs + xg);
+                    if ((need_c >> (3 * s + c)) & 1u) pp[c][s].store(bprv + (3 * s + c) * pcs + (xg - psh));
         }
         hxm = hx0; hym = hy0;
         hz_pc = hz_pn; hy_pc = hy_pn;
@@ -873,9 +878,9 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0 || PD == 3) dz.load((pD + bcs2));
             if (PD == 0) { ux.load(pU); uy.load((pU + bcs)); uz.load((pU + bcs2)); }
             if (GEN) {
-                pol.load(p, parity, xg, mx, my, mz);
+                pol.load(p, parity, xg - pol_shift(p, set), mx, my, mz);
                 load_bytes<V>(pm + plane, nx_); load_bytes<V>((pm + mcs) + plane, ny_); load_bytes<V>((pm + mcs2) + plane, nz_);
-            } else if (POL) pol.load_all(p, parity, xg);
+            } else if (POL) pol.load_all(p, parity, xg - pol_shift(p, set));
         } else { hx0.zero(); hy0.zero(); hz0.zero(); }
         if (rowm) { hzj.load((pH + fcs2) - pitch); hxj.load(pH - pitch); } else { hzj.zero(); hxj.zero(); }
         T hz_e = T(0), hy_e = T(0);       // tile-edge neighbours, issued with the plane's other loads
@@ -924,7 +929,7 @@ __device__ __forceinline__ void e_pml_body(const KParams<T> &p, const PmlBox<T> 
             if (PD == 0 || PD == 2) dy.store((pD + bcs));
             if (PD == 0 || PD == 3) dz.store((pD + bcs2));
             if (PD == 0) { ux.store(pU); uy.store((pU + bcs)); uz.store((pU + bcs2)); }
-            if (POL) pol.store(p, parity, xg);
+            if (POL) pol.store(p, parity, xg - pol_shift(p, set));
             if (GEN) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) { mx[v] = nx_[v]; my[v] = ny_[v]; mz[v] = nz_[v]; }

@@ -17,7 +17,8 @@ static void fill_params(const sj_sim *s, KParams<T> &p) {
     p.kz0 = s->kz0; p.nzl = s->nzl; p.n_sets = s->g.n_sets;
     p.F = (T *)s->F; p.fcs = s->set_stride * s->g.n_sets;
     for (int c = 0; c < 3; ++c) { p.E[c] = (T *)s->E[c]; p.H[c] = (T *)s->H[c]; p.mat[c] = s->mat[c]; p.sig[c] = (const T *)s->sigd[c]; p.siginv[c] = (const T *)s->siginvd[c]; }
-    p.Pall = (T *)s->Pall; p.p_comp_stride = s->set_stride * s->g.n_sets; p.n_slots = std::max(s->n_slots, 1);
+    p.Pall = (T *)s->Pall; p.p_k0 = s->p_k0; p.p_nzp = s->p_nzp; p.p_set_stride = s->plane * s->p_nzp;
+    p.p_comp_stride = p.p_set_stride * s->g.n_sets; p.n_slots = std::max(s->n_slots, 1);
     for (int q = 0; q < SJ_MAX_POLES; ++q) p.np_thr[q] = s->np_thr[q];
     p.mt_eps = (const T *)s->mt_eps; p.mt_chi = (const T *)s->mt_chi; p.mt_np = s->mt_np; p.mt_coef = (const T *)s->mt_coef; p.first_disp = s->first_disp;
     p.courant = (T)s->g.courant;

@@ -29,7 +29,9 @@ struct TmaPlan {
     TShape shape[SJ_TMA_MAX_SHAPES];
     const WorkItem *items;                // sorted: heaviest first, fine-grained ones last
     int n_items;
-    int *queue;                           // [0] next item to hand out, [1] producers that have drained the queue
+    int *queue;                           // [0] next item to hand out, [1] producers that have drained the queue,
+                                          // [2] blocks whose consumers have finished
+    long long *tick;                      // E-pass kernel of a full step: the last block to finish advances the step counter
 };
 #define SJ_ITEM_END (-99)                 // WorkItem::box of the end-of-queue message
 
@@ -216,7 +218,7 @@ __device__ __forceinline__ void h_tma_produce(const KParams<T> &p, const PmlBoxS
                     tma_load_3d(d + 3 * SL::HALO + (6 + c) * SL::OWN, mb, bi, bj, zcoord(9 + c, p.n_sets, it.set, bz, k - bk0), bar);
                 }
             } else if (naux) {
-                tma_load_3d(d + 3 * SL::HALO + 3 * SL::OWN, mb, bi, bj, zcoord(3 + (it.kind - 1), p.n_sets, it.set, bz, k - bk0), bar);
+                tma_load_3d(d + 3 * SL::HALO + 3 * SL::OWN, mb, bi, bj, zcoord(1, p.n_sets, it.set, bz, k - bk0), bar);     // a face region stores [D_n | B_n]
             }
         }
     }
@@ -491,13 +493,13 @@ __device__ __forceinline__ void e_tma_produce(const KParams<T> &p, const PmlBoxS
                     tma_load_3d(d + off_aux + (3 + c) * SL::OWN, mb, bi, bj, zcoord(6 + c, p.n_sets, it.set, bz, k - bk0), bar);
                 }
             } else if (naux) {
-                tma_load_3d(d + off_aux, mb, bi, bj, zcoord(it.kind - 1, p.n_sets, it.set, bz, k - bk0), bar);
+                tma_load_3d(d + off_aux, mb, bi, bj, zcoord(0, p.n_sets, it.set, bz, k - bk0), bar);     // a face region stores [D_n | B_n]
             }
             for (int c = 0; c < 3; ++c)
                 for (int s = 0; s < ns; ++s) {
                     const int ac = (parity * p.n_slots + s) * 3 + c, ap = ((parity ^ 1) * p.n_slots + s) * 3 + c;
-                    tma_load_3d(d + off_p + ((c * ns + s) * 2) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ac, p.n_sets, it.set, p.nzl, kl), bar);
-                    tma_load_3d(d + off_p + ((c * ns + s) * 2 + 1) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ap, p.n_sets, it.set, p.nzl, kl), bar);
+                    tma_load_3d(d + off_p + ((c * ns + s) * 2) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ac, p.n_sets, it.set, p.p_nzp, kl - p.p_k0), bar);
+                    tma_load_3d(d + off_p + ((c * ns + s) * 2 + 1) * SL::OWN, mp + SJ_TMAP_P_OWN, it.i0, it.j0, zcoord(ap, p.n_sets, it.set, p.p_nzp, kl - p.p_k0), bar);
                 }
         }
     }
@@ -547,7 +549,7 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
     }
     const long long mcs = p.set_stride, mcs2 = 2 * p.set_stride;
     const uint8_t *pm = p.mat[0] + xl0;
-    const long long pcs = p.p_comp_stride;
+    const long long pcs = p.p_comp_stride, psh = pol_shift(p, set);
     T *bprv = p.Pall + (long long)(parity ^ 1) * p.n_slots * 3 * pcs;          // read as "previous", written as new
 
     T sxi[V], ixi[V], sxh[V];
@@ -621,6 +623,9 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
                 pol.need[c][s] = (npmax > s);
                 pol.cur[c][s].load(sP + ((c * NS + s) * 2) * OWN_E + oc);
                 pol.prv[c][s].load(sP + ((c * NS + s) * 2 + 1) * OWN_E + oc);
+                // a mixed tile stages every slot of every cell; what its materials do not use is not polarisation data
+                // (outside the stored plane range the tile even aliases another array) and must read as zero
+                if (GEN && !pol.need[c][s]) { pol.cur[c][s].zero(); pol.prv[c][s].zero(); }
             }
         }
         if (!LATE) { __syncwarp(); if (lane == 0) mbar_arrive(r.empty(cu.q)); }
@@ -705,7 +710,7 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
             for (int s = 0; s < NS; ++s)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    if (pol.need[c][s]) pol.prv[c][s].store(bprv + (3 * s + c) * pcs + xg);
+                    if (pol.need[c][s]) pol.prv[c][s].store(bprv + (3 * s + c) * pcs + (xg - psh));
             if (send) {     // the slab's bottom plane: the same values go straight into the lower slab's upper halo
                 T *q = lk.down.F + (long long)set * lk.down.set_stride + (long long)lk.down.kl * plane + (long long)j * p.pitch + i0;
                 ex.store(q); ey.store(q + lk.down.fcs); ez.store(q + 2 * lk.down.fcs);
@@ -758,5 +763,9 @@ __global__ void __launch_bounds__(NT + 32, MINB) e_tma(const KParams<T> p, const
         else if (it.pad == 3) e_tma_dispatch<T, NT, NB, 2, true, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
         else if (p.n_slots <= 1) e_tma_dispatch<T, NT, NB, 1, false, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
         else e_tma_dispatch<T, NT, NB, 2, false, MINB == 2>(p, bs, lk, it, sh, r, kb, ke, cu);
+    }
+    if (plan.tick) {        // end of the step: every block has read the step counter for the last time
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NT));      // the consumer warps of this block
+        if (threadIdx.x == 0 && atomicAdd(plan.queue + 2, 1) == (int)gridDim.x - 1) { plan.queue[2] = 0; *plan.tick += 1; }
     }
 }

@@ -127,7 +127,7 @@ static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int which, in
     // dynamic queue: the kernels' producers pull the next item with an atomic, heaviest first
     const int grid = std::max(1, std::min(grid_cap, (int)items.size()));
     const std::vector<WorkItem> &flat = items;
-    const int zero[2] = {0, 0};
+    const int zero[4] = {0, 0, 0, 0};
     CK(cudaMalloc((void **)&out.items, flat.size() * sizeof(WorkItem)));
     CK(cudaMalloc((void **)&out.first, sizeof zero));
     CK(cudaMemcpy(out.items, flat.data(), flat.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
@@ -154,7 +154,17 @@ int sj_tma_build_geometry(sj_sim *s) {
     if (cc < 9 || !encode_fn()) { t.mode = 0; return 0; }          // no TMA on this device / driver: register kernels only
     const int V = s->prec == SJ_F64 ? 2 : 4;
     t.nt = 224;
-    const int zc_int = env_int("SJ_TMA_ZC", s->int_zchunk);
+    int n_sm_ = 148;
+    cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, dev);
+    // planes per item: about 16, fewer in a thin slab so that every SM still gets several items to pull (a slab of 23
+    // planes cut into two runs per tile leaves 1.6 items per block and a third of the machine idle at the end)
+    int zc_int = env_int("SJ_TMA_ZC", 0);
+    if (zc_int <= 0) {
+        const int V_ = s->prec == SJ_F64 ? 2 : 4;
+        const long long tiles_xy = (long long)((s->g.n[0] + 1 + 26 * V_ - 1) / (26 * V_)) * ((s->g.n[1] + 1 + 7) / 8);
+        const long long planes = (long long)(s->kz1 - s->kz0) * tiles_xy * s->g.n_sets;
+        zc_int = (int)std::min<long long>(s->int_zchunk, std::max<long long>(4, planes / (5LL * n_sm_)));
+    }
     const int zc_gen = env_int("SJ_TMA_ZCG", 6);       // edge / corner tiles are bound by instruction latency: many short items
     struct Reg { int box, kind, i0, i1, j0, j1, k0, k1; };
     std::vector<Reg> regs;
@@ -163,16 +173,7 @@ int sj_tma_build_geometry(sj_sim *s) {
     regs.push_back(Reg{-1, 0, L[0], Hh[0], L[1], Hh[1], std::max(L[2], s->kz0), std::min(Hh[2], s->kz1)});
     for (size_t bi = 0; bi < s->boxes.size(); ++bi) {
         const sj_sim::Box &B = s->boxes[bi];
-        const bool zbox = (B.lo[0] == 0 && B.hi[0] == N1x && B.lo[1] == 0 && B.hi[1] == N1y);
-        const bool ybox = !zbox && (B.lo[0] == 0 && B.hi[0] == N1x);
-        auto add = [&](int i0, int i1, int j0, int j1, int kind) { regs.push_back(Reg{(int)bi, kind, i0, i1, j0, j1, B.lo[2], B.hi[2]}); };
-        if (zbox) {
-            add(L[0], Hh[0], L[1], Hh[1], 3);
-            add(0, N1x, 0, L[1], 0); add(0, N1x, Hh[1], N1y, 0); add(0, L[0], L[1], Hh[1], 0); add(Hh[0], N1x, L[1], Hh[1], 0);
-        } else if (ybox) {
-            add(L[0], Hh[0], B.lo[1], B.hi[1], 2);
-            add(0, L[0], B.lo[1], B.hi[1], 0); add(Hh[0], N1x, B.lo[1], B.hi[1], 0);
-        } else add(B.lo[0], B.hi[0], B.lo[1], B.hi[1], 1);
+        regs.push_back(Reg{(int)bi, B.kind, B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.lo[2], B.hi[2]});
     }
     std::vector<WorkItem> geo;
     for (const Reg &R : regs) {
@@ -218,7 +219,7 @@ int sj_tma_build_materials(sj_sim *s) {
     // ---- tensor maps (F and the boxes never move; P is re-allocated when the slot count changes) ----
     std::vector<CUtensorMap> maps((size_t)t.n_shapes * SJ_TMAP_PER_SHAPE);
     memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
-    const long long f_units = 6LL * s->g.n_sets * s->nzl, p_units = 2LL * std::max(s->n_slots, 1) * 3 * s->g.n_sets * s->nzl;
+    const long long f_units = 6LL * s->g.n_sets * s->nzl, p_units = 2LL * std::max(s->n_slots, 1) * 3 * s->g.n_sets * s->p_nzp;
     for (int i = 0; i < t.n_shapes; ++i) {
         const TShape &sh = t.shapes[i];
         CUtensorMap *m = &maps[(size_t)i * SJ_TMAP_PER_SHAPE];
@@ -227,7 +228,7 @@ int sj_tma_build_materials(sj_sim *s) {
         rc = make_map(s, m + SJ_TMAP_P_OWN, s->Pall, s->pitch, s->rows, p_units, s->plane, sh.tw, sh.th); if (rc) return rc;
         for (size_t b = 0; b < s->boxes.size(); ++b) {
             const sj_sim::Box &B = s->boxes[b];
-            rc = make_map(s, m + SJ_TMAP_BOX0 + b, B.base, B.bpitch, B.by, 12LL * s->g.n_sets * B.bz, B.bplane, sh.tw, sh.th); if (rc) return rc;
+            rc = make_map(s, m + SJ_TMAP_BOX0 + b, B.base, B.bpitch, B.by, (long long)B.narr * s->g.n_sets * B.bz, B.bplane, sh.tw, sh.th); if (rc) return rc;
         }
     }
     cudaFree(t.maps); t.maps = NULL;

@@ -7,14 +7,14 @@ template <typename T>
 static void tma_plan(const sj_sim *s, const TmaList &l, TmaPlan &plan) {
     plan.maps = (const CUtensorMap *)s->tma.maps;
     for (int i = 0; i < SJ_TMA_MAX_SHAPES; ++i) plan.shape[i] = s->tma.shapes[i];
-    plan.items = l.items; plan.n_items = l.n_items; plan.queue = l.first;
+    plan.items = l.items; plan.n_items = l.n_items; plan.queue = l.first; plan.tick = nullptr;
 }
 
 static int tma_env(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
 
 // one persistent kernel per half-pass: one block per SM, the whole shared memory as its staging ring
 template <typename T>
-static int tma_pass(sj_sim *s, int which, cudaStream_t st) {
+static int tma_pass(sj_sim *s, int which, cudaStream_t st, bool tick) {
     KParams<T> p; fill_params(s, p);
     PmlBoxSet<T> bs; memset(&bs, 0, sizeof bs);
     for (size_t bi = 0; bi < s->boxes.size(); ++bi) fill_box(s->boxes[bi], bs.b[bi], s->g.n_sets);
@@ -22,6 +22,7 @@ static int tma_pass(sj_sim *s, int which, cudaStream_t st) {
     const TmaList &l = which == 0 ? s->tma.h[0] : s->tma.e[0][0];
     if (!l.n_items) return 0;
     TmaPlan plan; tma_plan<T>(s, l, plan);
+    if (which == 1 && tick) plan.tick = s->step_dev;
     SlabLinks<T> lk; memset(&lk, 0, sizeof lk);
     if (s->peer_up.F) {          // my top H plane -> the upper slab's lower halo (its local plane 0), then its flag_h
         lk.up.F = (T *)s->peer_up.F; lk.up.fcs = s->peer_up.fcs; lk.up.set_stride = s->peer_up.set_stride; lk.up.kl = 0;
