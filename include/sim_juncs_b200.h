@@ -218,6 +218,10 @@ int sj_profile_kernels(sj_sim *sim, int32_t reps, double out[4]);
  * (sum over E-component points of n_poles) in the slab, out[4] pole-points inside the interior
  * box, out[5] true PML cells (any sigma != 0). */
 int sj_get_counts(sj_sim *sim, double out[6]);
+/* Device memory of this slab in bytes: out[0] E and H, out[1] polarisation (stored only over the planes that hold pole
+ * materials), out[2] UPML auxiliaries (faces keep the normal D and B only), out[3] material indices, out[4] their sum,
+ * out[5] number of planes with polarisation storage. */
+int sj_memory(const sj_sim *sim, double out[6]);
 /* Per-run statistics for bench.py: kernels launched so far and bytes of source drive table uploaded (host -> device). */
 int sj_get_stats(const sj_sim *sim, int64_t *kernel_launches, double *h2d_bytes);
 /* Algorithmic bytes one full step moves for this configuration. */

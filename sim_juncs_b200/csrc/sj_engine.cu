@@ -1182,6 +1182,17 @@ extern "C" int sj_get_counts(sj_sim *s, double out[6]) {
     return SJ_OK;
 }
 
+extern "C" int sj_memory(const sj_sim *s, double out[6]) {
+    if (!s || !out) return SJ_ERR_ARG;
+    out[0] = 6.0 * (double)s->set_stride * s->g.n_sets * s->esz;                       // E, H
+    out[1] = s->p_bytes;                                                               // polarisation (both parities)
+    out[2] = s->pml_bytes;                                                             // UPML auxiliaries
+    out[3] = 3.0 * (double)s->set_stride * (1.0 + (s->masks[0] ? 1.0 : 0.0));          // material index bytes (+ region masks)
+    out[4] = out[0] + out[1] + out[2] + out[3];
+    out[5] = (double)s->p_nzp;                                                         // planes with polarisation storage
+    return SJ_OK;
+}
+
 extern "C" int sj_trace_step(sj_sim *s) {
     if (!s) return SJ_ERR_ARG;
     cudaSetDevice(s->g.device);

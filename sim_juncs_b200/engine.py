@@ -275,6 +275,12 @@ class Sim:
         self.L.sj_get_stats(self.h, C.byref(n), None)
         return n.value
 
+    def memory(self):
+        """device bytes of this slab by kind (sj_memory)"""
+        out = (C.c_double * 6)()
+        self._ck(self.L.sj_memory(self.h, out))
+        return dict(fields=out[0], polarisation=out[1], pml=out[2], materials=out[3], total=out[4], pol_planes=int(out[5]))
+
     def h2d_bytes(self):
         """bytes of source drive table uploaded to the device so far"""
         b = C.c_double()

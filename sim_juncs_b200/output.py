@@ -123,6 +123,39 @@ def save_field_samples(bg, out_dir, with_frequency=True):
     return write_field_samples_h5(d, os.path.join(out_dir, "field_samples.h5"))
 
 
+class _PhaseView:
+    """one phase of a batched CEP sweep, shaped like the BoundGeom of a single complex-field run with that phase"""
+
+    def __init__(self, bg, series, phase):
+        import copy
+        self.__dict__.update({k: getattr(bg, k) for k in ("monitor_clusters", "monitor_locs", "n_t_pts", "save_span", "problem",
+                                                          "ttot", "um_scale")})
+        self.time_bounds = bg.time_bounds
+        self.field_times = series
+        self.n_sets, self.phases, self.sim = 2, None, None
+        self.sources = []
+        for src in bg.sources:
+            c = copy.copy(src)
+            c.phase = src.phase + phase
+            self.sources.append(c)
+
+
+def save_phase_batch(bg, out_dir, indices=None):
+    """A BoundGeom run with phases = [phi_0 .. phi_{m-1}, phi_0 + pi/2 .. phi_{m-1} + pi/2] (every phase with its
+    quadrature, which is the imaginary part of meep's complex field for that phase): writes <out_dir>/phase_<index>/
+    field_samples.h5 per phase -- the file a single run with that source phase writes.  Returns the paths."""
+    m = len(bg.phases) // 2
+    if indices is None:
+        indices = list(range(m))
+    paths = []
+    for j in range(m):
+        series = [np.asarray(bg.field_times[j][i]).real + 1j * np.asarray(bg.field_times[j + m][i]).real
+                  for i in range(len(bg.field_times[j]))]
+        view = _PhaseView(bg, series, bg.phases[j])
+        paths.append(save_field_samples(view, os.path.join(out_dir, "phase_%03d" % indices[j])))
+    return paths
+
+
 # ---- whole-grid dumps (SURVEY N3): eps-000000.00.h5 at the start of run(), ex-<time>.h5 per save when dump_raw -------------
 def make_dec_str(t, n_digits_a, n_digits_b, dec_char="."):
     """argparse.h:390-431: zero-padded `aaa.bbb`; None where the reference returns -2 (too many integer digits)."""
