@@ -218,6 +218,9 @@ int sj_profile_kernels(sj_sim *sim, int32_t reps, double out[4]);
  * (sum over E-component points of n_poles) in the slab, out[4] pole-points inside the interior
  * box, out[5] true PML cells (any sigma != 0). */
 int sj_get_counts(sj_sim *sim, double out[6]);
+/* Algorithmic bytes per step of every owned plane (the terms of sj_bytes_per_step plane by plane): the weights a z-slab
+ * decomposition balances.  out: [kz1 - kz0] doubles. */
+int sj_plane_costs(sj_sim *sim, double *out);
 /* Device memory of this slab in bytes: out[0] E and H, out[1] polarisation (stored only over the planes that hold pole
  * materials), out[2] UPML auxiliaries (faces keep the normal D and B only), out[3] material indices, out[4] their sum,
  * out[5] number of planes with polarisation storage. */

@@ -44,10 +44,8 @@ def main():
     n = st.grid_cells()
     kz = None
     if world > 1:
-        from sim_juncs_b200.parallel import connect_slabs, slab_range
-        pml_cells = int(st.pml_thickness * st.resolution)
-        w = [1.22 if (k < pml_cells or k > n - pml_cells) else 1.0 for k in range(n + 1)]
-        kz = slab_range(n + 1, rank, world, w)
+        from sim_juncs_b200.parallel import balanced_slab, connect_slabs
+        kz = balanced_slab(lambda kz_: BoundGeom(st, fixture, precision=args.precision, n_sets=args.sets, device=local, kz=kz_), n + 1, rank, world)
     t0 = time.time()
     bg = BoundGeom(st, fixture, precision=args.precision, n_sets=args.sets, device=local, kz=kz)
     if world > 1:

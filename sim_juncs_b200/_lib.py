@@ -81,6 +81,7 @@ SYMBOLS = {
     "sj_run_timed": (C.c_int, [_vp, C.c_int64, C.c_int32, _dp]),
     "sj_profile_kernels": (C.c_int, [_vp, C.c_int32, _dp]),
     "sj_get_counts": (C.c_int, [_vp, _dp]),
+    "sj_plane_costs": (C.c_int, [_vp, _dp]),
     "sj_memory": (C.c_int, [_vp, _dp]),
     "sj_get_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), _dp]),
     "sj_bytes_per_step": (C.c_double, [_vp]),

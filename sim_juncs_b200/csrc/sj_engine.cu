@@ -1182,6 +1182,47 @@ extern "C" int sj_get_counts(sj_sim *s, double out[6]) {
     return SJ_OK;
 }
 
+// per-plane sums of n_poles over the three E-component material arrays
+__global__ void plane_pole_points_kernel(const uint8_t *m0, const uint8_t *m1, const uint8_t *m2, const int *np, long long plane,
+                                         int pitch, int nx1, unsigned long long *out) {
+    const uint8_t *a0 = m0 + (long long)(blockIdx.y + 1) * plane, *a1 = m1 + (long long)(blockIdx.y + 1) * plane, *a2 = m2 + (long long)(blockIdx.y + 1) * plane;
+    unsigned long long acc = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane; t += (long long)gridDim.x * blockDim.x)
+        if ((int)(t % pitch) < nx1) acc += np[a0[t]] + np[a1[t]] + np[a2[t]];
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + blockIdx.y, acc);
+}
+
+// Algorithmic bytes per step of every owned plane (the formula of sj_bytes_per_step, plane by plane): what a z-slab
+// decomposition has to balance -- planes inside the substrate carry polarisation traffic, planes inside the z-PML the
+// auxiliaries of every cell.  out: [kz1 - kz0].
+extern "C" int sj_plane_costs(sj_sim *s, double *out) {
+    if (!s || !out) return SJ_ERR_ARG;
+    cudaSetDevice(s->g.device);
+    const int nk = s->kz1 - s->kz0;
+    unsigned long long *d; int rc = alloc_zero(s, (void **)&d, (size_t)nk * 8); if (rc) return rc;
+    plane_pole_points_kernel<<<dim3(16, nk), 256, 0, s->stream>>>(s->mat[0], s->mat[1], s->mat[2], s->mt_np, s->plane, s->pitch,
+                                                                   s->g.n[0] + 1, d);
+    std::vector<unsigned long long> h(nk);
+    CK(cudaMemcpyAsync(h.data(), d, (size_t)nk * 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(d);
+    int in_xy[2];
+    for (int dd = 0; dd < 2; ++dd) {
+        int cnt = 0;
+        for (int i = 0; i <= s->g.n[dd]; ++i) if (s->sig[dd][2 * i] == 0.0 && s->sig[dd][2 * i + 1] == 0.0) ++cnt;
+        in_xy[dd] = cnt;
+    }
+    const double sz = (double)s->esz, per_plane = (double)s->g.n[0] * s->g.n[1], all_xy = (double)(s->g.n[0] + 1) * (s->g.n[1] + 1);
+    for (int k = 0; k < nk; ++k) {
+        const int kg = s->kz0 + k;
+        const bool zin = s->sig[2][2 * kg] == 0.0 && s->sig[2][2 * kg + 1] == 0.0;
+        const double pml = zin ? all_xy - (double)in_xy[0] * in_xy[1] : all_xy;
+        out[k] = s->g.n_sets * (per_plane * (18.0 * sz + 3.0) + 3.0 * sz * (double)h[k] + 8.0 * sz * pml);
+    }
+    return SJ_OK;
+}
+
 extern "C" int sj_memory(const sj_sim *s, double out[6]) {
     if (!s || !out) return SJ_ERR_ARG;
     out[0] = 6.0 * (double)s->set_stride * s->g.n_sets * s->esz;                       // E, H

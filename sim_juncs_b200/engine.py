@@ -275,6 +275,12 @@ class Sim:
         self.L.sj_get_stats(self.h, C.byref(n), None)
         return n.value
 
+    def plane_costs(self):
+        """algorithmic bytes per step of every owned plane (sj_plane_costs)"""
+        out = np.zeros(self.kz[1] - self.kz[0])
+        self._ck(self.L.sj_plane_costs(self.h, _dp(out)))
+        return out
+
     def memory(self):
         """device bytes of this slab by kind (sj_memory)"""
         out = (C.c_double * 6)()

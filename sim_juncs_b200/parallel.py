@@ -49,6 +49,24 @@ def connect_slabs(sim, rank, world, group=None):
     dist.barrier(group=group)      # nobody steps before every mapping exists
 
 
+def balanced_slab(make_slab, n_planes, rank, world, group=None):
+    """Owned planes of `rank` such that every rank moves about the same bytes per step.  The cost of a plane (substrate
+    planes carry polarisation traffic, z-PML planes the auxiliaries of every cell) is only known once the scene is
+    rasterized, so every rank builds its slab of an even split first (`make_slab(kz)` -> Sim or an object with `.sim`),
+    the per-plane costs are gathered and the cut is made again on the measured weights."""
+    kz = slab_range(n_planes, rank, world)
+    probe = make_slab(kz)
+    sim = getattr(probe, "sim", probe)
+    mine = [float(x) for x in sim.plane_costs()]
+    sim.close()
+    del probe, sim
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    weights = [w for part in parts for w in part]
+    assert len(weights) == n_planes
+    return slab_range(n_planes, rank, world, weights)
+
+
 class SlabGroup:
     """All z-slabs of one simulation inside ONE process: `make_slab(kz, device)` builds the slab [kz0, kz1) on a device
     (a Sim or a BoundGeom-like object with a `.sim`); the slabs are connected through peer memory and stepped together."""
