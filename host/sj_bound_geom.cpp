@@ -181,7 +181,9 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
                     if (sj_add_cw_source(sim, info.component, lo, hi, info.amplitude, 0.0, frequency, width, t_start, t_end, 3.0,
                                          integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(sim)); exit(1); }
                 } else {
-                    fprintf(stderr, "warning: magnetic-current sources are not implemented in the CUDA engine; source skipped\n");
+                    // same behaviour as the Python host (bound_geom.py): no silent change of the simulated problem
+                    fprintf(stderr, "error: magnetic-current sources (component %d) are not implemented in the CUDA engine\n", (int)info.component);
+                    exit(1);
                 }
                 sources.push_back(info);
                 ttot = sj_last_source_time(sim) + post_source_t * SJ_LIGHT_SPEED * s.um_scale;

@@ -1,7 +1,7 @@
 """`python -m sim_juncs_b200` -- the reference's command line (src/main.cpp:13-67) on the B200 engine,
 all in Python: argparse.h-compatible flags and params.conf (settings.py), the own CGS reader (cgs.py),
 BoundGeom on the C ABI, monitor series written by output.py.  Same phase timers on stdout.
-Engine-only extras: --fp32, --real-fields."""
+Engine-only extras: --fp32, --real-fields, --gpus N (z-slabs over N GPUs of this box, one process)."""
 import sys
 import time
 
@@ -15,6 +15,11 @@ def main(argv=None):
     precision = "f32" if "--fp32" in argv else "f64"
     n_sets = 1 if "--real-fields" in argv else 2
     argv = [a for a in argv if a not in ("--fp32", "--real-fields")]
+    gpus = None
+    if "--gpus" in argv:
+        i = argv.index("--gpus")
+        gpus = int(argv[i + 1])
+        del argv[i:i + 2]
     args = ParseSettings()
     ret = args.parse_args(argv)
     if ret:
@@ -25,7 +30,7 @@ def main(argv=None):
     args.correct_defaults()
     start = time.monotonic()
     try:
-        geom = BoundGeom(args, None, precision=precision, n_sets=n_sets)
+        geom = BoundGeom(args, None, precision=precision, n_sets=n_sets, gpus=gpus)
     except CgsError as e:
         print(e)
         return e.code

@@ -11,9 +11,43 @@ from .engine import Sim
 from .scene import COMPONENTS, LIGHT_SPEED, THICK_SCALE, Scene
 
 
+class _SlabStack:
+    """The `sim` of a BoundGeom that is spread over several GPUs: the z-slabs of one simulation, stepped together
+    (sj_run_group); monitors are evaluated by the slab that owns them."""
+
+    def __init__(self, sims):
+        self.sims = sims
+        self.dt = sims[0].dt
+        self.n_sets = sims[0].n_sets
+
+    def run(self, n_steps, save_span=1, sync=True):
+        Sim.run_group(self.sims, n_steps, save_span, sync)
+
+    def sync(self):
+        for s in self.sims:
+            s.sync()
+
+    def monitors(self):
+        return sum(s.monitors() for s in self.sims)
+
+    def field(self, comp, iset=0):
+        return np.concatenate([s.field(comp, iset) for s in self.sims], axis=0)
+
+    def last_source_time(self):
+        return self.sims[0].last_source_time()
+
+    def launches(self):
+        return sum(s.launches() for s in self.sims)
+
+
 class BoundGeom:
+    def __new__(cls, settings, scene=None, *args, gpus=None, **kw):
+        if gpus is not None and gpus != 1 and gpus != [0] and cls is BoundGeom:
+            return object.__new__(SlabBoundGeom)
+        return object.__new__(cls)
+
     def __init__(self, settings, scene=None, precision="f64", n_sets=2, integrated=True, device=-1, kz=None,
-                 verbose=False, phases=None):
+                 verbose=False, phases=None, gpus=None):
         """settings: ParseSettings (after correct_defaults); scene: Scene, a path to a .geom file or to a
         scene JSON, or None to read settings.geom_fname as the reference does (disp.cpp:556).
         n_sets = 2 reproduces meep's complex fields (the reference never calls use_real_fields).
@@ -171,3 +205,39 @@ class BoundGeom:
         plus <prefix>/field_samples.npz with the HDF5 paths as keys.  Returns the .h5 path."""
         from .output import save_field_samples
         return save_field_samples(self, fname_prefix)
+
+
+class SlabBoundGeom(BoundGeom):
+    """BoundGeom(..., gpus=N) or gpus=[device, ...]: the same simulation cut into z-slabs of equal bytes per step, one per
+    GPU, inside this process (the reference's counterpart is meep under MPI, src/main.cpp:20).  Results equal the single-
+    GPU run bit for bit; run() / save_field_times() / the getters are BoundGeom's."""
+
+    def __init__(self, settings, scene=None, precision="f64", n_sets=2, integrated=True, device=-1, kz=None,
+                 verbose=False, phases=None, gpus=None):
+        from .parallel import slab_range
+        devices = list(range(gpus)) if isinstance(gpus, int) else list(gpus)
+        world = len(devices)
+        if scene is None:
+            scene = settings.geom_fname
+        if isinstance(scene, str):
+            scene = Scene.load(scene) if scene.endswith(".json") else Scene.from_geom(scene, settings)
+        n_planes = settings.grid_cells() + 1
+
+        def build(cuts):
+            return [BoundGeom(settings, scene, precision=precision, n_sets=n_sets, integrated=integrated, device=devices[r],
+                              kz=cuts[r], verbose=verbose and r == 0, phases=phases) for r in range(world)]
+        parts = build([slab_range(n_planes, r, world) for r in range(world)])
+        weights = [float(x) for p in parts for x in p.sim.plane_costs()]
+        cuts = [slab_range(n_planes, r, world, weights) for r in range(world)]
+        for p in parts:
+            p.sim.close()
+        self.parts = build(cuts)
+        self.kz = cuts
+        for lo, up in zip(self.parts[:-1], self.parts[1:]):
+            Sim.connect_local(lo.sim, up.sim)
+        first = self.parts[0]
+        for k, v in first.__dict__.items():           # scene, settings, sources, monitors, ttot ... are the same in every part
+            if k != "sim":
+                setattr(self, k, v)
+        self.sim = _SlabStack([p.sim for p in self.parts])
+        self.t_raster = max(p.t_raster for p in self.parts)

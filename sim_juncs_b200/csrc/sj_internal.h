@@ -7,7 +7,7 @@
 
 #include "../../include/sim_juncs_b200.h"
 
-#define SJ_MAX_SRC 4
+#define SJ_MAX_SRC 16
 #define SJ_MAX_MAT 256
 #define SJ_N_PML_BOX 18         // regions of the PML shell: 2 z boxes x 5 + 2 y boxes x 3 + 2 x boxes
 #define SJ_N_AUX 10

@@ -54,7 +54,7 @@ def field_samples_dict(bg, with_frequency=True):
     # `frequency`: on the device (sj_read_spectra, one warp per monitor and bin) when the series are the simulation's own
     spectra = None
     sim = getattr(bg, "sim", None)
-    if with_frequency and sim is not None and getattr(bg, "phases", None) is None and len(bg.field_times) == n_locs \
+    if with_frequency and sim is not None and hasattr(sim, "spectra") and getattr(bg, "phases", None) is None and len(bg.field_times) == n_locs \
             and n_locs and all(len(f) == sim.L.sj_n_samples(sim.h) for f in bg.field_times):
         spectra = sim.spectra(0, 1 if bg.n_sets >= 2 else None)
     n_cl = len(bg.monitor_clusters)

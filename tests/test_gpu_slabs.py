@@ -105,3 +105,36 @@ def test_slabs_one_process_per_gpu_bitwise():
         (k0, k1), fields, _ = res[r]
         for a, b in zip(fields, ref_fields):
             assert np.array_equal(a, b[k0:k1])
+
+
+def test_bound_geom_gpus_on_one_device(scene_json, tmp_path):
+    """BoundGeom(gpus=[0, 0, 0]): the host-level entry to the slab stack (balanced cuts, run, save) against the plain
+    single-GPU BoundGeom -- same series, same field_samples.h5 datasets"""
+    from helpers import early_pulse, settings_from_doc
+    from sim_juncs_b200.bound_geom import BoundGeom
+    from sim_juncs_b200.scene import Scene
+    from sim_juncs_b200 import hdf5
+    path = scene_json("Au_graphene_box")
+    st = settings_from_doc(path)
+    st.grid_num = 57
+    st.resolution = 57 / 18.0
+    st.post_source_t = 2.0
+    st.save_span = 5
+    one = BoundGeom(st, early_pulse(Scene.load(path), 0.2), n_sets=2, device=0)
+    many = BoundGeom(st, early_pulse(Scene.load(path), 0.2), n_sets=2, gpus=[0, 0, 0])
+    assert len(many.parts) == 3 and many.kz[0][0] == 0 and many.kz[-1][1] == st.grid_cells() + 1
+    for bg in (one, many):
+        bg.run()
+    assert one.n_t_pts == many.n_t_pts and one.n_t_pts > 100
+    a, b = np.array(one.field_times), np.array(many.field_times)
+    assert np.abs(a).max() > 1e-6 and np.array_equal(a, b)
+    f1 = hdf5.File(one.save_field_times(str(tmp_path / "one")))
+    f2 = hdf5.File(many.save_field_times(str(tmp_path / "many")))
+    cn = sorted(k for k in f1.keys() if k.startswith("cluster_"))[0]
+    pn = sorted(k for k in f1[cn].keys() if k.startswith("point_"))[0]
+    t1 = f1[cn][pn]["time"].read()
+    t2 = f2[cn][pn]["time"].read()
+    assert np.array_equal(t1["Re"], t2["Re"]) and np.array_equal(t1["Im"], t2["Im"])
+    from helpers import rel_l2
+    q1, q2 = f1[cn][pn]["frequency"].read(), f2[cn][pn]["frequency"].read()
+    assert rel_l2(q2["Re"] + 1j * q2["Im"], q1["Re"] + 1j * q1["Im"]) < 1e-12      # device DFT vs host DFT of the same series
