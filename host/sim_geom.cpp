@@ -9,10 +9,11 @@ int main(int argc, char **argv) {
     parse_settings args;
     int ret = parse_args(&args, &argc, argv);
     if (ret) return ret;
-    int precision = SJ_F64, n_sets = 2;
+    int precision = SJ_F64, n_sets = 2, n_gpus = 1;
     for (int i = 1; i < argc; ++i) {                       // engine-only extras, not in the reference
         if (argv[i] && !strcmp(argv[i], "--fp32")) precision = SJ_F32;
         if (argv[i] && !strcmp(argv[i], "--real-fields")) n_sets = 1;
+        if (argv[i] && !strcmp(argv[i], "--gpus") && i + 1 < argc && argv[i + 1]) n_gpus = atoi(argv[i + 1]);
     }
     char *name = args.conf_fname ? args.conf_fname : strdup("params.conf");
     ret = parse_conf_file(&args, name);
@@ -22,7 +23,7 @@ int main(int argc, char **argv) {
 
     parse_ercode ercode = E_SUCCESS;
     auto start = std::chrono::steady_clock::now();
-    sj_bound_geom geom(args, &ercode, precision, n_sets);
+    sj_bound_geom geom(args, &ercode, precision, n_sets, 1, n_gpus);
     if (ercode) return (int)ercode;
     auto end_init = std::chrono::steady_clock::now();
     std::cout << "initialization completed in " << std::chrono::duration_cast<std::chrono::milliseconds>(end_init - start).count()

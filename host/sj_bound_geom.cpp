@@ -105,7 +105,7 @@ std::vector<sj_pole_raw> sj_bound_geom::parse_susceptibilities(value val, int *e
 }
 
 // ---- constructor (reference src/disp.cpp:482-645) -----------------------------------------------
-sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int precision, int p_n_sets, int integrated)
+sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int precision, int p_n_sets, int integrated, int n_gpus)
     : problem(s.geom_fname, sj_context_from_settings(s), ercode), sim(NULL) {
     if (ercode && *ercode != E_SUCCESS) { printf("Scene parsing failed, exiting.\n"); exit(1); }
     um_scale = s.um_scale; post_source_t = s.post_source_t; save_span = s.save_span; n_sets = p_n_sets;
@@ -119,7 +119,7 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
     const int n = (int)(2 * z_center * s.resolution + 0.5);          // meep::vol3d
     g.n[0] = g.n[1] = g.n[2] = n; n_cells[0] = n_cells[1] = n_cells[2] = n; g.a = s.resolution; g.courant = 0.5; g.pml_thickness = s.pml_thickness; g.pml_R = 1e-15;
     g.precision = precision; g.n_sets = n_sets; g.device = -1;
-    if (sj_create(&g, &sim)) { fprintf(stderr, "sj_create: %s\n", sj_last_error(sim)); exit(1); }
+    n_gpus = std::max(1, std::min(n_gpus, n + 1));
 
     std::vector<composite_object *> roots = problem.get_roots();
     std::vector<sj_csg_node> nodes;
@@ -147,10 +147,42 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
         }
     }
     auto t0 = std::chrono::steady_clock::now();
-    if (sj_rasterize_smooth(sim, s.ambient_eps, (int)nodes.size(), nodes.data(), (int)regions.size(), regions.data(),
-                            (int)s.smooth_n, s.smooth_rad)) {
-        fprintf(stderr, "sj_rasterize_smooth: %s\n", sj_last_error(sim)); exit(1);
+    // one sj_sim per z-slab: created and rasterized on its GPU (a slab rasterizes only its own planes)
+    auto build = [&](const std::vector<int> &cut) {
+        for (sj_sim *q : sims) sj_destroy(q);
+        sims.assign(n_gpus, NULL);
+        for (int r = 0; r < n_gpus; ++r) {
+            sj_grid gr = g;
+            if (n_gpus > 1) { gr.kz0 = cut[r]; gr.kz1 = cut[r + 1]; gr.device = getenv("SJ_ONE_DEVICE") ? 0 : r; }   // SJ_ONE_DEVICE: all slabs on GPU 0 (tests)
+            if (sj_create(&gr, &sims[r])) { fprintf(stderr, "sj_create: %s\n", sj_last_error(sims[r])); exit(1); }
+            if (sj_rasterize_smooth(sims[r], s.ambient_eps, (int)nodes.size(), nodes.data(), (int)regions.size(), regions.data(),
+                                    (int)s.smooth_n, s.smooth_rad)) {
+                fprintf(stderr, "sj_rasterize_smooth: %s\n", sj_last_error(sims[r])); exit(1);
+            }
+        }
+    };
+    std::vector<int> cut(n_gpus + 1);
+    for (int r = 0; r <= n_gpus; ++r) cut[r] = (int)((long long)(n + 1) * r / n_gpus);
+    build(cut);
+    if (n_gpus > 1) {       // cut again on the measured bytes per plane (substrate planes carry polarisation traffic)
+        std::vector<double> w(n + 1);
+        for (int r = 0; r < n_gpus; ++r) sj_plane_costs(sims[r], &w[cut[r]]);
+        double tot = 0, acc = 0; for (double x : w) tot += x;
+        int target = 1;
+        for (int k = 0; k <= n && target < n_gpus; ++k) {
+            acc += w[k];
+            while (target < n_gpus && acc >= tot * target / n_gpus) cut[target++] = k + 1;
+        }
+        for (int r = 1; r < n_gpus; ++r) cut[r] = std::max(cut[r], cut[r - 1] + 1);
+        for (int r = n_gpus - 1; r > 0; --r) cut[r] = std::min(cut[r], cut[r + 1] - 1);
+        build(cut);
+        for (int r = 0; r + 1 < n_gpus; ++r)
+            if (sj_connect_local(sims[r], sims[r + 1])) { fprintf(stderr, "sj_connect_local: %s\n", sj_last_error(sims[r])); exit(1); }
+        printf("z-slabs:");
+        for (int r = 0; r < n_gpus; ++r) printf(" [%d,%d)", cut[r], cut[r + 1]);
+        printf("\n");
     }
+    sim = sims[0];
     raster_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
     context &c = problem.get_context();
@@ -174,12 +206,14 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
                 const double t_start = info.start_time * c_by_a, t_end = info.end_time * c_by_a;
                 if (info.type == SJ_SRC_GAUSSIAN && info.component <= 2) {
                     printf("Adding Gaussian envelope: f=%f, w=%f, t_0=%f, t_f=%f (meep units)\n", frequency, width, t_start, t_end);
-                    if (sj_add_gaussian_source(sim, info.component, lo, hi, info.amplitude, 0.0, frequency, width, info.phase, t_start,
-                                               t_end, integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(sim)); exit(1); }
+                    for (sj_sim *q : sims)
+                        if (sj_add_gaussian_source(q, info.component, lo, hi, info.amplitude, 0.0, frequency, width, info.phase, t_start,
+                                                   t_end, integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(q)); exit(1); }
                 } else if (info.component <= 2) {
                     printf("Adding continuous wave: f=%f, w=%f, t_0=%f, t_f=%f (meep units)\n", frequency, width, t_start, t_end);
-                    if (sj_add_cw_source(sim, info.component, lo, hi, info.amplitude, 0.0, frequency, width, t_start, t_end, 3.0,
-                                         integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(sim)); exit(1); }
+                    for (sj_sim *q : sims)
+                        if (sj_add_cw_source(q, info.component, lo, hi, info.amplitude, 0.0, frequency, width, t_start, t_end, 3.0,
+                                             integrated, NULL)) { fprintf(stderr, "source: %s\n", sj_last_error(q)); exit(1); }
                 } else {
                     // same behaviour as the Python host (bound_geom.py): no silent change of the simulated problem
                     fprintf(stderr, "error: magnetic-current sources (component %d) are not implemented in the CUDA engine\n", (int)info.component);
@@ -205,13 +239,14 @@ sj_bound_geom::sj_bound_geom(const parse_settings &s, parse_ercode *ercode, int 
             monitor_clusters.push_back(monitor_locs.size());
         }
     }
-    if (!monitor_locs.empty() && sj_add_monitors(sim, SJ_EX, (int)monitor_locs.size(), &monitor_locs[0].x)) {
-        fprintf(stderr, "monitors: %s\n", sj_last_error(sim)); exit(1);
-    }
+    for (sj_sim *q : sims)
+        if (!monitor_locs.empty() && sj_add_monitors(q, SJ_EX, (int)monitor_locs.size(), &monitor_locs[0].x)) {
+            fprintf(stderr, "monitors: %s\n", sj_last_error(q)); exit(1);
+        }
     if (ercode) *ercode = E_SUCCESS;
 }
 
-sj_bound_geom::~sj_bound_geom() { sj_destroy(sim); }
+sj_bound_geom::~sj_bound_geom() { for (sj_sim *q : sims) sj_destroy(q); }
 
 // ---- run (reference src/disp.cpp:690-749) ---------------------------------------------------------
 int sj_bound_geom::run(const char *fname_prefix) {
@@ -222,9 +257,13 @@ int sj_bound_geom::run(const char *fname_prefix) {
     printf("starting simulations\n");
     auto t0 = std::chrono::steady_clock::now();
     int rc = 0;
-    if (fname_prefix && sj_dump::write_eps_from_sim(fname_prefix, sim, n_cells))      // fields.output_hdf5(Dielectric), disp.cpp:696
+    if (sims.size() > 1) {
+        if (dump_raw) printf("warning: whole-grid dumps (eps-*.h5, ex-*.h5) are written by single-GPU runs only\n");
+        rc = sj_run_group(sims.data(), (int)sims.size(), n_t_pts, save_span);
+    } else if (fname_prefix && sj_dump::write_eps_from_sim(fname_prefix, sim, n_cells))      // fields.output_hdf5(Dielectric), disp.cpp:696
         printf("warning: could not write %s/eps-000000.00.h5\n", fname_prefix);
-    if (dump_raw && fname_prefix) {
+    if (sims.size() > 1) {
+    } else if (dump_raw && fname_prefix) {
         // disp.cpp:709-737: at every save point the whole Ex field goes to ex-<time>.h5 before the step
         const int n_digits_a = (int)(ceil(log(ttot) / log(10)));
         const int n_digits_b = (int)ceil(-log((double)dt) / log(10.0)) + 1;
@@ -238,13 +277,17 @@ int sj_bound_geom::run(const char *fname_prefix) {
             if (rc == SJ_ERR_DIVERGED) rc = 0;
         }
     } else rc = sj_run(sim, n_t_pts, save_span);
-    if (!rc) rc = sj_sync(sim);
+    for (sj_sim *q : sims) { const int r2 = sj_sync(q); if (!rc) rc = r2; }
     if (rc == SJ_ERR_DIVERGED) printf("divergence in run (%s)\n", sj_last_error(sim));
     else if (rc) { printf("error in run: %s\n", sj_last_error(sim)); return rc; }
     run_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const size_t n_locs = monitor_locs.size(), ns = (size_t)sj_n_samples(sim);
-    std::vector<double> buf(std::max<size_t>(ns * n_locs * n_sets, 1));
+    std::vector<double> buf(std::max<size_t>(ns * n_locs * n_sets, 1)), part(buf.size());
     sj_read_monitors(sim, buf.data());
+    for (size_t r = 1; r < sims.size(); ++r) {          // every monitor is evaluated by the slab that owns it, zeros elsewhere
+        sj_read_monitors(sims[r], part.data());
+        for (size_t q = 0; q < buf.size(); ++q) buf[q] += part[q];
+    }
     field_times.assign(n_locs, std::vector<std::complex<double> >(ns));
     for (size_t i = 0; i < ns; ++i)
         for (size_t j = 0; j < n_locs; ++j) {
@@ -346,6 +389,11 @@ int sj_bound_geom::save_field_times(const char *fname_prefix) {
         sj_read_spectra(sim, 0, n_sets > 1 ? 1 : -1, &n_freq, NULL);
         std::vector<double> spec(std::max<size_t>((size_t)n_locs * n_freq * 2, 1));
         if (n_freq && n_locs && sj_read_spectra(sim, 0, n_sets > 1 ? 1 : -1, &n_freq, spec.data())) { printf("%s\n", sj_last_error(sim)); return -1; }
+        for (size_t r = 1; r < sims.size() && n_freq && n_locs; ++r) {      // the transform is linear: sum over the slabs
+            std::vector<double> part(spec.size());
+            if (sj_read_spectra(sims[r], 0, n_sets > 1 ? 1 : -1, &n_freq, part.data())) { printf("%s\n", sj_last_error(sims[r])); return -1; }
+            for (size_t q = 0; q < spec.size(); ++q) spec[q] += part[q];
+        }
         const size_t ngd = (size_t)(log((double)std::max<size_t>(monitor_clusters.size(), 1)) / log(10.0)) + 1;
         const size_t npd = (size_t)(log((double)std::max<size_t>(n_locs, 1)) / log(10.0)) + 1;
         size_t i = 0, off = 0;

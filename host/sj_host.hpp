@@ -32,8 +32,10 @@ int sj_flatten_tree(composite_object *root, std::vector<sj_csg_node> &nodes);
 
 class sj_bound_geom {
 public:
+    // n_gpus > 1: the simulation is cut into z-slabs of equal bytes per step, one per GPU of this box (the reference's
+    // counterpart is meep under MPI, src/main.cpp:20); results equal the single-GPU run bit for bit
     sj_bound_geom(const parse_settings &s, parse_ercode *ercode = NULL, int precision = SJ_F64, int n_sets = 2,
-                  int integrated = 1);
+                  int integrated = 1, int n_gpus = 1);
     ~sj_bound_geom();
     std::vector<sj_vec3> get_monitor_locs() { return monitor_locs; }
     std::vector<std::vector<std::complex<double> > > get_field_times() { return field_times; }
@@ -51,7 +53,8 @@ public:
     scene problem;
 
 private:
-    sj_sim *sim;
+    sj_sim *sim;                      // the bottom slab (the only one on a single GPU)
+    std::vector<sj_sim *> sims;       // all z-slabs, bottom to top
     std::vector<sj_source_info> sources;
     std::vector<sj_vec3> monitor_locs;
     std::vector<size_t> monitor_clusters;

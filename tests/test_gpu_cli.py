@@ -214,3 +214,29 @@ def test_cpp_hosts_write_the_whole_grid_dumps(exe, tmp_path):
             assert np.abs(x - y).max() <= 1e-12 * max(np.abs(y).max(), 1e-30), (f, ds)
             seen = max(seen, np.abs(y).max())
     assert seen > 1e-9
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="host/_ref/sim_geom is built where /root/reference exists")
+def test_cpp_host_gpus_flag_equals_single_gpu(tmp_path):
+    """host/sim_geom --gpus 3 (z-slabs inside the library; here all on GPU 0) writes the same field_samples.h5 series as
+    the plain run"""
+    from sim_juncs_b200 import hdf5
+    conf = os.path.join(ROOT, "scenes", "tests", "graphene_short.conf")
+    outs = []
+    for tag, extra, env in (("one", [], {}), ("three", ["--gpus", "3"], {"SJ_ONE_DEVICE": "1"})):
+        out = str(tmp_path / tag)
+        os.makedirs(out)
+        txt = subprocess.check_output([EXE, "--conf-file", conf, "--out-dir", out] + extra, cwd=ROOT, timeout=900,
+                                      env=dict(os.environ, **env)).decode()
+        assert "finished writing hdf5 file!" in txt
+        if extra:
+            assert "z-slabs:" in txt
+        f = hdf5.File(os.path.join(out, "field_samples.h5"))
+        cols = []
+        for cn in sorted(k for k in f.keys() if k.startswith("cluster_")):
+            for pn in sorted(k for k in f[cn].keys() if k.startswith("point_")):
+                t = f[cn][pn]["time"].read()
+                cols.append(t["Re"] + 1j * t["Im"])
+        outs.append(np.stack(cols, axis=1))
+    assert np.abs(outs[0]).max() > 1e-7
+    assert np.array_equal(outs[0], outs[1])
