@@ -168,6 +168,16 @@ int sj_read_monitors(sj_sim *sim, double *out);
  * real series.  *n_freq = T; out (may be NULL to query T): [n_monitors][T]{re, im} doubles. */
 int sj_read_spectra(sj_sim *sim, int32_t set_re, int32_t set_im, int32_t *n_freq, double *out);
 
+/* Pulse parameters of every monitor series, on the device: the front half of the reference's post-processing class
+ * `signal` (scripts/phases.py:94-157, 205-244, 289-357), which its phase sweeps evaluate in a Python loop over 1 600
+ * series x phases -- arrival-sample guess, 2 rfft of the rolled series, magnitude-weighted centre frequency, the band
+ * above CUT_ALPHA = 0.1 of the centre, unwrapped phase regressed on the frequency.  dt_sample: time between two samples
+ * (any unit; frequencies come out in its inverse).  out: [n_sets][n_monitors][10] doubles = f0, f0 bin, arrival-sample
+ * guess, t0_corr = -slope / 2 pi, phi_corr = fix_angle(intercept), slope, intercept, r value, f_min + 65536 f_max,
+ * status (bit 0: the reference would low-pass this series first -- run the host pipeline on it; bit 1: centre frequency
+ * above half the band; bit 2: band too narrow for a fit). */
+int sj_extract_cep(sj_sim *sim, double dt_sample, double *out);
+
 /* ---- z-slab halo exchange (one process per GPU; the caller moves the bytes) -------------
  * Fine-grained stepping used by the multi-GPU driver: half-passes restricted to local plane
  * ranges so boundary planes can be computed first and exchanged while the rest runs.         */

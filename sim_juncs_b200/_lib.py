@@ -68,6 +68,7 @@ SYMBOLS = {
     "sj_dt": (C.c_double, [_vp]),
     "sj_read_monitors": (C.c_int, [_vp, _dp]),
     "sj_read_spectra": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _dp]),
+    "sj_extract_cep": (C.c_int, [_vp, C.c_double, _dp]),
     "sj_pass": (C.c_int, [_vp, C.c_int, C.c_int32, C.c_int32, _vp]),
     "sj_tick": (C.c_int, [_vp, _vp]),
     "sj_sample": (C.c_int, [_vp, _vp]),

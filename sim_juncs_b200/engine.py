@@ -196,6 +196,15 @@ class Sim:
             self._ck(self.L.sj_read_spectra(self.h, int(set_re), im, C.byref(t), _dp(out)))
         return out[:, :, 0] + 1j * out[:, :, 1]
 
+    def extract_cep(self, dt_sample):
+        """pulse parameters of every monitor series on the device (sj_extract_cep): dict of [n_sets, n_mon] arrays"""
+        out = np.zeros((self.n_sets, self.n_mon, 10))
+        self._ck(self.L.sj_extract_cep(self.h, float(dt_sample), _dp(out)))
+        band = out[:, :, 8]
+        return dict(f0=out[:, :, 0], f0_ind=out[:, :, 1].astype(int), t0_ind=out[:, :, 2].astype(int), t0_corr=out[:, :, 3],
+                    phi_corr=out[:, :, 4], slope=out[:, :, 5], intercept=out[:, :, 6], rvalue=out[:, :, 7],
+                    f_min=(band % 65536).astype(int), f_max=(band // 65536).astype(int), status=out[:, :, 9].astype(int))
+
     def field(self, comp, iset=0):
         out = np.zeros(self.shape)
         self._ck(self.L.sj_get_field(self.h, comp, iset, _dp(out)))
