@@ -1,7 +1,8 @@
 """`python -m sim_juncs_b200` -- the reference's command line (src/main.cpp:13-67) on the B200 engine,
 all in Python: argparse.h-compatible flags and params.conf (settings.py), the own CGS reader (cgs.py),
 BoundGeom on the C ABI, monitor series written by output.py.  Same phase timers on stdout.
-Engine-only extras: --fp32, --real-fields, --gpus N (z-slabs over N GPUs of this box, one process)."""
+Engine-only extras: --fp32, --real-fields, --gpus N (z-slabs over N GPUs of this box, one process), --current-sources
+(src_time::is_integrated = false: the drive enters as a current on D; see scripts/compare_with_meep.py)."""
 import sys
 import time
 
@@ -14,7 +15,8 @@ def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     precision = "f32" if "--fp32" in argv else "f64"
     n_sets = 1 if "--real-fields" in argv else 2
-    argv = [a for a in argv if a not in ("--fp32", "--real-fields")]
+    integrated = "--current-sources" not in argv
+    argv = [a for a in argv if a not in ("--fp32", "--real-fields", "--current-sources")]
     gpus = None
     if "--gpus" in argv:
         i = argv.index("--gpus")
@@ -30,7 +32,7 @@ def main(argv=None):
     args.correct_defaults()
     start = time.monotonic()
     try:
-        geom = BoundGeom(args, None, precision=precision, n_sets=n_sets, gpus=gpus)
+        geom = BoundGeom(args, None, precision=precision, n_sets=n_sets, gpus=gpus, integrated=integrated)
     except CgsError as e:
         print(e)
         return e.code
