@@ -52,11 +52,14 @@ static int upload_vec(sj_sim *s, const std::vector<double> &v, void **dev) {
     return 0;
 }
 static int upload_sig(sj_sim *s, int d) {
-    std::vector<double> inv(s->sig[d].size());
+    // the device copies carry 16 entries of padding (sigma 0): the last vector of a row reads the table at the padding
+    // columns i > n of the grid as well (found by compute-sanitizer memcheck)
+    std::vector<double> sg(s->sig[d]), inv(s->sig[d].size());
     for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1 / (1.0 + s->sig[d][i]);   // meep: siginv = 1/(kap+sig)
+    sg.resize(sg.size() + 16, 0.0); inv.resize(inv.size() + 16, 1.0);
     int rc = s->prec == SJ_F64 ? upload_vec<double>(s, inv, &s->siginvd[d]) : upload_vec<float>(s, inv, &s->siginvd[d]);
     if (rc) return rc;
-    return s->prec == SJ_F64 ? upload_vec<double>(s, s->sig[d], &s->sigd[d]) : upload_vec<float>(s, s->sig[d], &s->sigd[d]);
+    return s->prec == SJ_F64 ? upload_vec<double>(s, sg, &s->sigd[d]) : upload_vec<float>(s, sg, &s->sigd[d]);
 }
 
 static int alloc_zero(sj_sim *s, void **p, size_t bytes) {
