@@ -53,6 +53,15 @@ struct Vec {
         for (int i = 0; i < V; ++i) q[i] = v[i];
         *reinterpret_cast<VT *>(p) = t;
     }
+    // streaming store (st.global.cs): the value is not read again before a whole pass has gone through the L2
+    __device__ __forceinline__ void store_cs(T *p) const {
+        typedef typename VecOf<T, V>::type VT;
+        VT t;
+        T *q = reinterpret_cast<T *>(&t);
+#pragma unroll
+        for (int i = 0; i < V; ++i) q[i] = v[i];
+        __stcs(reinterpret_cast<VT *>(p), t);
+    }
     __device__ __forceinline__ void zero() {
 #pragma unroll
         for (int i = 0; i < V; ++i) v[i] = T(0);
