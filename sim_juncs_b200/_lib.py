@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsimjuncs_b200.so")
+# SJ_LIB=NAME loads lib/libsimjuncs_b200_NAME.so instead: a build variant for A/B measurements (scripts/build_variant.sh)
+LIB_PATH = os.path.join(_HERE, "lib", "libsimjuncs_b200%s.so" % ("_" + os.environ["SJ_LIB"] if os.environ.get("SJ_LIB") else ""))
 
 SJ_MAX_POLES = 4
 SJ_F64, SJ_F32 = 0, 1

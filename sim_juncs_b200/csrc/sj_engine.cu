@@ -962,14 +962,26 @@ extern "C" int sj_sample(sj_sim *s, void *stream) {
     return 0;
 }
 
+// One full time step on stream st.  A slab that holds the whole grid and whose planes fit the L2 window takes one launch:
+// the fused wavefront kernel (step_tma in csrc/sj_tma.cuh); otherwise the H-pass and the E-pass are a launch each.
+static bool fused_step(const sj_sim *s) {
+    static const bool on = !(getenv("SJ_TMA_FUSE") && atoi(getenv("SJ_TMA_FUSE")) == 0);
+    return on && tma_step(s) && s->tma.wave > 0 && s->tma.f.n_items > 0 && !s->peer_up.F && !s->peer_down.F;
+}
+static int do_step(sj_sim *s, cudaStream_t st) {
+    if (fused_step(s)) return s->prec == SJ_F64 ? sj_tma_pass_f64(s, 2, st, true) : sj_tma_pass_f32(s, 2, st, true);
+    int rc = do_pass(s, 0, s->kz0, s->kz1, st); if (rc) return rc;
+    rc = do_pass(s, 1, s->kz0, s->kz1, st, true); if (rc) return rc;
+    if (!tma_step(s)) { tick_kernel<<<1, 1, 0, st>>>(s->step_dev); s->launches++; }
+    return 0;
+}
+
 // Capture one full step on the simulation's stream.  Every kernel argument is step-invariant (the drive table is
 // indexed by the device-side step counter), so the same graph serves every step until a setter changes a pointer.
 static int graph_build(sj_sim *s) {
     const long long l0 = s->launches;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = do_pass(s, 0, s->kz0, s->kz1, s->stream);
-    if (!rc) rc = do_pass(s, 1, s->kz0, s->kz1, s->stream, true);
-    if (!rc && !tma_step(s)) { tick_kernel<<<1, 1, 0, s->stream>>>(s->step_dev); s->launches++; }
+    int rc = do_step(s, s->stream);
     cudaGraph_t g = NULL;
     const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
     s->graph_launches = s->launches - l0; s->launches = l0;
@@ -997,9 +1009,7 @@ static int run_range(sj_sim *s, int64_t i0, int64_t i1, int32_t save_span, long 
                 continue;
             }
         }
-        rc = do_pass(s, 0, s->kz0, s->kz1, st); if (rc) return rc;
-        rc = do_pass(s, 1, s->kz0, s->kz1, st, true); if (rc) return rc;
-        if (!tma_step(s)) { tick_kernel<<<1, 1, 0, st>>>(s->step_dev); s->launches++; }
+        rc = do_step(s, st); if (rc) return rc;
         s->steps_done++;
     }
     CK(cudaGetLastError());
@@ -1157,6 +1167,18 @@ extern "C" int sj_profile_kernels(sj_sim *s, int32_t reps, double out[4]) {
             CK(cudaEventSynchronize(e1));
             float f = 0; CK(cudaEventElapsedTime(&f, e0, e1));
             out[which] = f / reps; out[2 + which] = 0.0;
+        }
+        if (fused_step(s)) {     // out[2] = the fused step kernel (both passes in one launch); it advances the step counter
+            for (int rep = -2; rep < reps; ++rep) {
+                if (rep == 0) CK(cudaEventRecord(e0, s->stream));
+                rc = ensure_drive(s, s->steps_done + 2); if (rc) return rc;
+                rc = do_step(s, s->stream); if (rc) return rc;
+                s->steps_done++;
+            }
+            CK(cudaEventRecord(e1, s->stream));
+            CK(cudaEventSynchronize(e1));
+            float f = 0; CK(cudaEventElapsedTime(&f, e0, e1));
+            out[2] = f / reps;
         }
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return SJ_OK;

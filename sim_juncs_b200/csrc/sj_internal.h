@@ -110,11 +110,17 @@ struct ItemList { WorkItem *dev; int n; };
 
 // ---- TMA-staged column kernels (sj_tma.cuh): tile shapes, tensor maps, per-block item schedules ----------------
 #define SJ_TMA_MAX_SHAPES 12
-struct TShape { int nvx, th, tw, hp; };   // vectors per tile row, tile rows, tile width and halo-box row pitch in elements
+#ifndef SJ_TMA_NT
+#define SJ_TMA_NT 224              // consumer threads per block of the TMA-staged kernels (7 warps + 1 producer warp at 255 registers)
+#endif
+// nvx vectors per tile row, th tile rows, tw tile width and hp halo-box row pitch in elements; a thread owns vector
+// t % nvx of rows t / nvx + s * ths, s < sub (sub = 2: tall tiles, two rows per thread -- a TMA box of twice the bytes costs
+// the TMA unit the same ~170 cycles); hs / os: bytes of a halo box / an own-cell tile in the staging ring (128-byte multiples)
+struct TShape { int nvx, th, tw, hp, sub, ths, hs, os; };
 struct TmaList { WorkItem *items; int *first; int n_items, grid; double bytes; };   // first: the queue counters {next item, drained producers}
 struct TmaState {
     int mode = 0;                 // bit 0: H-pass through the TMA kernels, bit 1: E-pass
-    int nt = 224;                 // consumer threads per block the shapes were sized for
+    int nt = SJ_TMA_NT;           // consumer threads per block the shapes were sized for
     int n_shapes = 0;
     TShape shapes[SJ_TMA_MAX_SHAPES];
     void *maps = nullptr;         // CUtensorMap[n_shapes][SJ_TMAP_PER_SHAPE] in device memory
@@ -123,6 +129,11 @@ struct TmaState {
     TmaList h[2] = {};            // H-pass: [class A (interior + faces) | general (edges, corners)]
     TmaList e[2][4] = {};         // E-pass: same split x material class (0: one non-dispersive material, 1: mixed,
                                   //         2 / 3: one material with 1 / 2 poles)
+    // fused step (one launch, z wavefront; single-slab runs whose plane fits the L2 window): both passes' items in one queue
+    TmaList f = {};
+    int wave = 0;                 // planes per z chunk (0: no fused list)
+    int n_chunks = 0;
+    int *grp = nullptr;           // device: [need (n_chunks) | done (n_chunks) | epoch]
 };
 
 struct MonDev {

@@ -49,36 +49,42 @@ static int make_map(sj_sim *s, CUtensorMap *m, void *base, int pitch, int rows, 
     return 0;
 }
 
-// tile shape for a w x h rectangle: nvx vectors per row, th rows, with nvx * th <= NT threads and the halo box
-// (nvx + 1) * (th + 1) vectors inside its slot (1.25 NT vectors).  Minimises the vectors a plane of the region makes the
-// TMA engine read (three curl inputs with halo + three own arrays, tile overhang past the region included) per useful
-// vector; ties go to the fuller thread block.
-static void pick_shape(int w, int h, int V, int NT, int &nvx_out, int &th_out) {
+// tile shape for a w x h rectangle: nvx vectors per row, th rows; a thread owns one vector of up to max_sub rows (ths rows
+// apart), so nvx * ceil(th / sub) <= NT threads.  Minimises the vectors a plane of the region makes the TMA engine read
+// (three curl inputs with halo + three own arrays, tile overhang past the region included) per useful vector; ties go to
+// the fuller thread block.  Tall tiles (sub = 2) halve the number of TMA operations per byte: the TMA unit of an SM takes
+// ~170 cycles per box of up to ~18 rows whatever its size (scripts/microbench/tma_rate.cu), which at 4 KB per box is no
+// more than the HBM rate.
+static void pick_shape(int w, int h, int V, int NT, int max_sub, int &nvx_out, int &th_out, int &sub_out) {
     const int nv = (w + V - 1) / V;
     double best = 1e30;
-    nvx_out = 1; th_out = 1;
-    for (int nvx = 1; nvx <= std::min(nv, 63); ++nvx) {
-        const int tiles_x = (nv + nvx - 1) / nvx;
-        if ((nv + tiles_x - 1) / tiles_x != nvx) continue;          // only balanced splits
-        if (nvx < std::min(nv, 6)) continue;                         // rows of at least 96 bytes where the region allows
-        if ((nvx & 1) && nvx != nv) continue;                        // tile rows are whole 32-byte sectors (DRAM granularity)
-        for (int th = 1; th <= std::min(h, 255); ++th) {
-            if (nvx * th > NT || (nvx + 1) * (th + 1) * 4 > NT * 5) continue;
-            const int tiles_y = (h + th - 1) / th;
-            if ((h + tiles_y - 1) / tiles_y != th) continue;
-            const double read = (double)tiles_x * tiles_y * (3.0 * (nvx + 1) * (th + 1) + 3.0 * nvx * th) / ((double)nv * h);
-            const double fill = (double)nvx * th / NT;
-            const double score = read + 0.6 * (1.0 - fill);
-            if (score < best) { best = score; nvx_out = nvx; th_out = th; }
+    nvx_out = 1; th_out = 1; sub_out = 1;
+    for (int sub = 1; sub <= max_sub; ++sub)
+        for (int nvx = 1; nvx <= std::min(nv, 63); ++nvx) {
+            const int tiles_x = (nv + nvx - 1) / nvx;
+            if ((nv + tiles_x - 1) / tiles_x != nvx) continue;          // only balanced splits
+            if (nvx < std::min(nv, 6)) continue;                         // rows of at least 96 bytes where the region allows
+            if ((nvx & 1) && nvx != nv) continue;                        // tile rows are whole 32-byte sectors (DRAM granularity)
+            for (int th = 1; th <= std::min(h, 255); ++th) {
+                const int ths = (th + sub - 1) / sub;
+                if (nvx * ths > NT) continue;
+                if (sub > 1 && th < 2 * sub) continue;
+                const int tiles_y = (h + th - 1) / th;
+                if ((h + tiles_y - 1) / tiles_y != th) continue;
+                const double read = (double)tiles_x * tiles_y * (3.0 * (nvx + 1) * (th + 1) + 3.0 * nvx * th) / ((double)nv * h);
+                const double fill = (double)nvx * th / (NT * sub);
+                const double score = read + 0.6 * (1.0 - fill);
+                if (score < best) { best = score; nvx_out = nvx; th_out = th; sub_out = sub; }
+            }
         }
-    }
 }
 
-static int shape_index(sj_sim *s, int nvx, int th, int V) {
+static int shape_index(sj_sim *s, int nvx, int th, int sub, int V) {
     TmaState &t = s->tma;
-    for (int i = 0; i < t.n_shapes; ++i) if (t.shapes[i].nvx == nvx && t.shapes[i].th == th) return i;
+    for (int i = 0; i < t.n_shapes; ++i) if (t.shapes[i].nvx == nvx && t.shapes[i].th == th && t.shapes[i].sub == sub) return i;
     if (t.n_shapes >= SJ_TMA_MAX_SHAPES) return -1;
-    t.shapes[t.n_shapes] = TShape{nvx, th, nvx * V, (nvx + 1) * V};
+    const int hs = ((nvx + 1) * (th + 1) * 16 + 127) / 128 * 128, os = (nvx * th * 16 + 127) / 128 * 128;
+    t.shapes[t.n_shapes] = TShape{nvx, th, nvx * V, (nvx + 1) * V, sub, (th + sub - 1) / sub, hs, os};
     return t.n_shapes++;
 }
 
@@ -88,6 +94,7 @@ void sj_tma_free(sj_sim *s) {
     TmaState &t = s->tma;
     cudaFree(t.maps); t.maps = NULL;
     for (int g = 0; g < 2; ++g) { free_list(t.h[g]); for (int c = 0; c < 4; ++c) free_list(t.e[g][c]); }
+    free_list(t.f); cudaFree(t.grp); t.grp = NULL; t.wave = 0;
 }
 
 // Static schedule: items sorted by cost, each given to the least-loaded block (LPT); a block then walks its items in
@@ -100,7 +107,8 @@ static int item_weight(const sj_sim *s, const WorkItem &w, int which) {
     // edge / corner and mixed-material tiles are bound by instruction latency, not by their bytes: measured factors
     static const double wgen = getenv("SJ_TMA_WGEN") ? atof(getenv("SJ_TMA_WGEN")) : 1.0, wmix = getenv("SJ_TMA_WMIX") ? atof(getenv("SJ_TMA_WMIX")) : 1.0;
     const double f = (general ? wgen : 1.0) * ((which == 1 && w.pad == 1) ? wmix : 1.0);
-    return (int)(f * (3 * 20 + (3 + (general ? 6 : 1) + 6 * ns) * 16));
+    const TShape &sh = s->tma.shapes[w.shape & 0xff];
+    return (int)(f * (3 * sh.hs + (3 + (general ? 6 : w.box >= 0 ? 1 : 0) + 6 * ns) * sh.os) / 64);
 }
 
 static int upload_schedule(sj_sim *s, std::vector<WorkItem> items, int which, int grid_cap, TmaList &out) {
@@ -153,7 +161,7 @@ int sj_tma_build_geometry(sj_sim *s) {
     cudaGetDevice(&dev); cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev);
     if (cc < 9 || !encode_fn()) { t.mode = 0; return 0; }          // no TMA on this device / driver: register kernels only
     const int V = s->prec == SJ_F64 ? 2 : 4;
-    t.nt = 224;
+    t.nt = SJ_TMA_NT;
     int n_sm_ = 148;
     cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, dev);
     // planes per item: about 16, fewer in a thin slab so that every SM still gets several items to pull (a slab of 23
@@ -161,10 +169,11 @@ int sj_tma_build_geometry(sj_sim *s) {
     int zc_int = env_int("SJ_TMA_ZC", 0);
     if (zc_int <= 0) {
         const int V_ = s->prec == SJ_F64 ? 2 : 4;
-        const long long tiles_xy = (long long)((s->g.n[0] + 1 + 26 * V_ - 1) / (26 * V_)) * ((s->g.n[1] + 1 + 7) / 8);
+        const long long tiles_xy = (long long)((s->g.n[0] + 1 + 26 * V_ - 1) / (26 * V_)) * ((s->g.n[1] + 1 + 15) / 16);
         const long long planes = (long long)(s->kz1 - s->kz0) * tiles_xy * s->g.n_sets;
         zc_int = (int)std::min<long long>(s->int_zchunk, std::max<long long>(4, planes / (5LL * n_sm_)));
     }
+    const int sub_int = env_int("SJ_TMA_SUB", 2), sub_face = env_int("SJ_TMA_SUB_FACE", 1);
     const int zc_gen = env_int("SJ_TMA_ZCG", 6);       // edge / corner tiles are bound by instruction latency: many short items
     struct Reg { int box, kind, i0, i1, j0, j1, k0, k1; };
     std::vector<Reg> regs;
@@ -179,10 +188,13 @@ int sj_tma_build_geometry(sj_sim *s) {
     for (const Reg &R : regs) {
         const int w = R.i1 - R.i0, h = R.j1 - R.j0, nz = R.k1 - R.k0;
         if (w <= 0 || h <= 0 || nz <= 0) continue;
-        int nvx, th;
-        pick_shape(w, h, V, t.nt, nvx, th);
-        const int sh = shape_index(s, nvx, th, V);
-        if (sh < 0) { t.mode = 0; return 0; }
+        // tall tiles (two rows per thread) for the interior and, optionally, the single-sigma faces; the half-height shape
+        // of a tall one is registered too: material classes whose plane load would not fit the ring twice take it
+        const int max_sub = R.box < 0 ? sub_int : (R.kind != 0 ? sub_face : 1);
+        int nvx, th, sub;
+        pick_shape(w, h, V, t.nt, max_sub, nvx, th, sub);
+        const int sh = shape_index(s, nvx, th, sub, V);
+        if (sh < 0 || (sub > 1 && shape_index(s, nvx, (th + sub - 1) / sub, 1, V) < 0)) { t.mode = 0; return 0; }
         // planes per item: runs of about zc_int planes, evened out; thin regions (the z boxes) in one run
         const int zc_t = (R.box >= 0 && R.kind == 0) ? zc_gen : zc_int;
         const int nchunk = std::max(1, (nz + zc_t - 1) / zc_t), zc = (nz + nchunk - 1) / nchunk;
@@ -210,7 +222,66 @@ int sj_tma_build_geometry(sj_sim *s) {
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    return upload_schedule(s, replicate_sets(t.geo[0], s->g.n_sets), 0, n_sm * env_int("SJ_TMA_BLK", 1), t.h[0]);
+    return upload_schedule(s, replicate_sets(t.geo[0], s->g.n_sets), 0, n_sm, t.h[0]);
+}
+
+// Fused step: both passes' items in one queue, cut along z into chunks of `wave` planes and ordered H(0), H(1), E(0), H(2),
+// E(1), ... (heaviest first inside a group), so that an E-pass item finds what the H-pass items of its chunk wrote -- and the E
+// planes they read -- in the L2.  Only for a slab that holds the whole grid (the boundary-plane exchange of z-slabs has its
+// own ordering) and only while a few chunks of both passes fit the L2 window; SJ_TMA_WAVE = planes per chunk (0: off).
+static int build_fused(sj_sim *s, const std::vector<WorkItem> &e_items, int n_sm) {
+    TmaState &t = s->tma;
+    free_list(t.f); cudaFree(t.grp); t.grp = NULL; t.wave = 0; t.n_chunks = 0;
+    if (t.n_bnd[0] || t.n_bnd[1] || s->kz0 != 0 || s->kz1 != s->g.n[2] + 1) return 0;
+    const double plane_bytes = (double)s->plane * s->esz * s->g.n_sets * (18.0 + 6.0 * std::max(s->n_slots, 0));   // both passes, one plane
+    // chunk length: measured on the bench workload (17 MB per plane of both passes): DRAM reads per step 2033 MB with two
+    // launches, 1465 MB with 6-plane chunks, 1210 MB with 2-plane chunks -- but short chunks pay more per item (dependency
+    // waits, partial planes, code switches) than the saved bytes are worth, the kernel not being DRAM-bound any more:
+    // 0.57 / 0.49 / 0.47 / 0.48 ms per step with 3 / 6 / 8 / 12 planes.  Planes too large for the L2 to hold a chunk of both
+    // passes stay with two launches per step.
+    int wave = env_int("SJ_TMA_WAVE", -1);
+    if (wave < 0) { wave = std::min(8, (int)(140e6 / plane_bytes)); if (wave < 2) wave = 0; }
+    if (wave <= 0) return 0;
+    const int nz = s->kz1 - s->kz0, nch = (nz + wave - 1) / wave;
+    std::vector<std::vector<WorkItem>> grp[2];
+    grp[0].resize(nch); grp[1].resize(nch);
+    auto cut = [&](const std::vector<WorkItem> &in, int pass) {
+        for (const WorkItem &w : in)
+            for (int kb = w.kb; kb < w.ke;) {
+                const int c = (kb - s->kz0) / wave, ke = std::min(w.ke, s->kz0 + (c + 1) * wave);
+                for (int q = 0; q < s->g.n_sets; ++q) {
+                    WorkItem x = w; x.kb = kb; x.ke = ke; x.set = q; x.shape = (w.shape & 0xff) | (pass ? SJ_EPASS_FLAG : 0) | (c << 16);      // (no boundary items in a whole-grid slab)
+                    grp[pass][c].push_back(x);
+                }
+                kb = ke;
+            }
+    };
+    cut(t.geo[0], 0); cut(e_items, 1);
+    auto cost = [&](const WorkItem &w) { return (long long)(w.ke - w.kb + 1) * item_weight(s, w, (w.shape & SJ_EPASS_FLAG) ? 1 : 0); };
+    std::vector<WorkItem> flat;
+    std::vector<int> need(2 * nch + 1, 0);
+    auto emit = [&](int pass, int c) {
+        std::vector<WorkItem> &g = grp[pass][c];
+        std::stable_sort(g.begin(), g.end(), [&](const WorkItem &a, const WorkItem &b) { return cost(a) > cost(b); });
+        flat.insert(flat.end(), g.begin(), g.end());
+        if (pass == 0) need[c] = (int)g.size();            // one count per finished item (group_done)
+    };
+    // H runs `lead` chunks ahead of E: the E-pass items of a chunk are pulled when the H-pass items they wait for are done
+    const int lead = std::max(1, env_int("SJ_TMA_LEAD", 2));
+    for (int c = 0; c < nch + lead; ++c) {
+        if (c < nch) emit(0, c);
+        if (c - lead >= 0) emit(1, c - lead);
+    }
+    CK(cudaMalloc((void **)&t.grp, need.size() * sizeof(int)));
+    CK(cudaMemcpy(t.grp, need.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice));     // done counters and epoch start at 0
+    const int zero[4] = {0, 0, 0, 0};
+    CK(cudaMalloc((void **)&t.f.items, flat.size() * sizeof(WorkItem)));
+    CK(cudaMalloc((void **)&t.f.first, sizeof zero));
+    CK(cudaMemcpy(t.f.items, flat.data(), flat.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.f.first, zero, sizeof zero, cudaMemcpyHostToDevice));
+    t.f.n_items = (int)flat.size(); t.f.grid = std::max(1, std::min(n_sm, (int)flat.size()));
+    t.wave = wave; t.n_chunks = nch;
+    return 0;
 }
 
 int sj_tma_build_materials(sj_sim *s) {
@@ -243,8 +314,36 @@ int sj_tma_build_materials(sj_sim *s) {
         for (const WorkItem &w : t.geo[1]) if ((w.shape & 0xff) == sh) sub.push_back(w);
         int rc = sj_classify_items(s, sub, t.shapes[sh].tw, t.shapes[sh].th, cls); if (rc) return rc;
     }
+    // a tall tile whose material class stages so many polarisation tiles that two plane loads would not fit the ring is
+    // cut into its two half-height tiles (shape registered by sj_tma_build_geometry), and those are classified again
+    {
+        const int cap = env_int("SJ_TMA_RING_KB", 208) * 1024;
+        std::vector<WorkItem> halves[SJ_TMA_MAX_SHAPES];
+        for (int c = 1; c < 4; ++c) {
+            std::vector<WorkItem> keep;
+            for (const WorkItem &w : cls[c]) {
+                const TShape &sh = t.shapes[w.shape & 0xff];
+                const int ns = c == 1 ? std::max(s->n_slots, 1) : c - 1;
+                const long long len = 3LL * sh.hs + (3 + (w.box >= 0 ? (w.kind == 0 ? 6 : 1) : 0) + 6 * ns) * (long long)sh.os;
+                if (sh.sub == 1 || (ns <= 1 && 2 * len <= cap)) { keep.push_back(w); continue; }     // (the kernels take tall tiles with <= 1 slot)
+                int small = -1;
+                for (int i = 0; i < t.n_shapes; ++i) if (t.shapes[i].nvx == sh.nvx && t.shapes[i].th == sh.ths && t.shapes[i].sub == 1) small = i;
+                if (small < 0) { s->err = "TMA schedule: half-height tile shape missing"; return SJ_ERR_ARG; }
+                for (int j0 = w.j0; j0 < w.j_hi; j0 += sh.ths) {
+                    WorkItem h = w; h.j0 = j0; h.j_hi = std::min(j0 + sh.ths, w.j_hi); h.shape = small | (w.shape & SJ_BND_FLAG);
+                    halves[small].push_back(h);
+                }
+            }
+            cls[c].swap(keep);
+        }
+        for (int sh = 0; sh < t.n_shapes; ++sh) {
+            if (halves[sh].empty()) continue;
+            int rc = sj_classify_items(s, halves[sh], t.shapes[sh].tw, t.shapes[sh].th, cls); if (rc) return rc;
+        }
+    }
+    t.n_bnd[1] = 0;
     for (int c = 0; c < 4; ++c)
-        for (WorkItem w : cls[c]) { w.pad = c; all.push_back(w); }      // pad = material class of the item
-    { int rc = upload_schedule(s, replicate_sets(all, s->g.n_sets), 1, n_sm * env_int("SJ_TMA_BLK", 1), t.e[0][0]); if (rc) return rc; }
-    return 0;
+        for (WorkItem w : cls[c]) { w.pad = c; w.shape |= SJ_EPASS_FLAG; all.push_back(w); if (w.shape & SJ_BND_FLAG) t.n_bnd[1]++; }      // pad = material class of the item
+    { int rc = upload_schedule(s, replicate_sets(all, s->g.n_sets), 1, n_sm, t.e[0][0]); if (rc) return rc; }
+    return build_fused(s, all, n_sm);
 }
