@@ -38,9 +38,6 @@ struct TmaPlan {
     int *grp_done;                        // [chunk] running count of those completions (never reset: target = (epoch + 1) * need)
     int *epoch;                           // launches of the fused kernel so far (advanced by the last block of a launch)
 };
-#ifndef SJ_TMA_BATCH
-#define SJ_TMA_BATCH 1
-#endif
 #define SJ_EPASS_FLAG 0x200               // WorkItem::shape bit: E-pass item of a fused queue; bits 16.. = its z chunk
 #ifdef SJ_TMA_PROF
 #define PROF_T0(v) const long long v = clock64()
@@ -274,9 +271,9 @@ __device__ __forceinline__ void group_done(int *ctr) {
 // =====================================================================================================
 // a plane load: Ex, Ey, Ez boxes with the high-side halo (sh.hs bytes each) | Hx, Hy, Hz tiles (sh.os bytes each) |
 // auxiliaries: none (interior), 1 (the normal B of a face tile), 6 (edge / corner: Bx, By, Bz, Ux, Uy, Uz)
-template <typename T, int NT, int NB>
+template <typename T, int NT, int NB, typename F>
 __device__ __forceinline__ void h_produce_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const SlabLinks<T> &lk,
-                                               const Ring<NB> &r, Producer<NB> &pr, const WorkItem &it, int k_lo, int k_hi) {
+                                               const Ring<NB> &r, Producer<NB> &pr, const WorkItem &it, int k_lo, int k_hi, F &&claim_next) {
     const uint64_t pol_first = l2_evict_first(); (void)pol_first;
     bool first = true;
     const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
@@ -299,6 +296,7 @@ __device__ __forceinline__ void h_produce_item(const KParams<T> &p, const PmlBox
     }
     for (int k = ke; k >= kb; --k) {                  // top down: plane k + 1 is then always the previous load
         const bool partial = (k == ke);               // the plane above the run: Ex, Ey only
+        if (k == kb) claim_next();                    // the next item is claimed while this item's last plane is issued
         const uint32_t d = pr.acquire(r, partial ? 2 * HS : len_full), bar = r.full(pr.c.q);
         if (first) { r.mail[pr.c.q & (NB - 1)] = it; first = false; }     // ordered before the barrier arrival below (release)
         ++pr.c.q;
@@ -572,9 +570,9 @@ __device__ __forceinline__ int item_slots(const KParams<T> &p, const WorkItem &i
     return it.pad == 0 ? 0 : it.pad == 1 ? p.n_slots : it.pad - 1;
 }
 
-template <typename T, int NT, int NB>
+template <typename T, int NT, int NB, typename F>
 __device__ __forceinline__ void e_produce_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const TmaPlan &plan, const SlabLinks<T> &lk,
-                                               const Ring<NB> &r, Producer<NB> &pr, const WorkItem &it, int parity, int k_lo, int k_hi) {
+                                               const Ring<NB> &r, Producer<NB> &pr, const WorkItem &it, int parity, int k_lo, int k_hi, F &&claim_next) {
     constexpr int V = 16 / (int)sizeof(T);
     const uint64_t pol_first = l2_evict_first(); (void)pol_first;
     bool first = true;
@@ -601,6 +599,7 @@ __device__ __forceinline__ void e_produce_item(const KParams<T> &p, const PmlBox
     const int hi0 = it.i0 - V, hj0 = it.j0 - 1;
     for (int k = kb - 1; k < ke; ++k) {
         const bool partial = (k == kb - 1);           // the plane below the run: Hx, Hy only
+        if (k == ke - 1) claim_next();                // the next item is claimed while this item's last plane is issued
         const uint32_t d = pr.acquire(r, partial ? 2 * HS : len_full), bar = r.full(pr.c.q);
         if (first) { r.mail[pr.c.q & (NB - 1)] = it; first = false; }     // ordered before the barrier arrival below (release)
         ++pr.c.q;
@@ -651,35 +650,26 @@ __device__ __forceinline__ void tma_produce(const KParams<T> &p, const PmlBoxSet
     const bool fused = plan.grp_done != nullptr;
     const int epoch = fused ? *plan.epoch : 0;
     int verified = -1;                                     // fused: H-pass items of the chunks <= verified are known to be done
-    // SJ_TMA_BATCH items per pull (1: pulling two neighbours of the queue at a time, to run the same code path twice in
-    // a row against instruction-cache misses after item switches, unbalanced the blocks: 0.48 -> 0.53 ms per step)
-    constexpr int B = SJ_TMA_BATCH;
+    // The next item is claimed (atomic + 48-byte load, ~1.5 us of latency) when the last plane of the current one is being
+    // issued: late enough that a block never sits on an item it will not start for a long time (claiming a whole item ahead
+    // lengthened the tail of every launch by ~8 us), early enough that the ring still holds planes to hide the latency.
     const int last = plan.n_items - 1;
-    int n = atomicAdd(plan.queue, B);
-    WorkItem cur[B];
-#pragma unroll
-    for (int i = 0; i < B; ++i) cur[i] = plan.items[min(n + i, last)];
+    int n = atomicAdd(plan.queue, 1);
+    WorkItem it = plan.items[min(n, last)];
     while (n < plan.n_items) {
-        const int n2 = atomicAdd(plan.queue, B);
-        WorkItem nxt[B];
-#pragma unroll
-        for (int i = 0; i < B; ++i) nxt[i] = plan.items[min(n2 + i, last)];
-#pragma unroll
-        for (int i = 0; i < B; ++i) {
-            if (n + i > last) break;
-            const WorkItem &it = cur[i];
-            ++n_done;
-            if (it.shape & SJ_EPASS_FLAG) {
-                const int chunk = it.shape >> 16;
-                if (fused && chunk > verified) { PROF_T0(tq); wait_group(plan, verified + 1, chunk, epoch, lk.err); PROF_ADD(pr.t_queue, tq); verified = chunk; }
-                e_produce_item<T, NT, NB>(p, bs, plan, lk, r, pr, it, parity, k_lo, k_hi);
-            } else {
-                h_produce_item<T, NT, NB>(p, bs, plan, lk, r, pr, it, k_lo, k_hi);
-            }
+        int n2 = -1;
+        WorkItem it2;
+        auto claim_next = [&]() { n2 = atomicAdd(plan.queue, 1); it2 = plan.items[min(n2, last)]; };
+        ++n_done;
+        if (it.shape & SJ_EPASS_FLAG) {
+            const int chunk = it.shape >> 16;
+            if (fused && chunk > verified) { PROF_T0(tq); wait_group(plan, verified + 1, chunk, epoch, lk.err); PROF_ADD(pr.t_queue, tq); verified = chunk; }
+            e_produce_item<T, NT, NB>(p, bs, plan, lk, r, pr, it, parity, k_lo, k_hi, claim_next);
+        } else {
+            h_produce_item<T, NT, NB>(p, bs, plan, lk, r, pr, it, k_lo, k_hi, claim_next);
         }
-        n = n2;
-#pragma unroll
-        for (int i = 0; i < B; ++i) cur[i] = nxt[i];
+        if (n2 < 0) claim_next();                          // (an item outside [k_lo, k_hi) issues nothing)
+        n = n2; it = it2;
     }
     {   // end of queue: an empty load whose mailbox says so
         pr.acquire(r, 0);
