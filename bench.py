@@ -156,8 +156,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, where the one JSON line belongs
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner (env or nccl.conf) goes to stdout, where the one JSON line belongs
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     st = load_settings()

@@ -962,11 +962,11 @@ extern "C" int sj_sample(sj_sim *s, void *stream) {
     return 0;
 }
 
-// One full time step on stream st.  A slab that holds the whole grid and whose planes fit the L2 window takes one launch:
-// the fused wavefront kernel (step_tma in csrc/sj_tma.cuh); otherwise the H-pass and the E-pass are a launch each.
+// One full time step on stream st.  A slab whose planes fit the L2 window takes one launch: the fused wavefront kernel
+// (step_tma in csrc/sj_tma.cuh); otherwise the H-pass and the E-pass are a launch each.
 static bool fused_step(const sj_sim *s) {
     static const bool on = !(getenv("SJ_TMA_FUSE") && atoi(getenv("SJ_TMA_FUSE")) == 0);
-    return on && tma_step(s) && s->tma.wave > 0 && s->tma.f.n_items > 0 && !s->peer_up.F && !s->peer_down.F;
+    return on && tma_step(s) && s->tma.wave > 0 && s->tma.f.n_items > 0;
 }
 static int do_step(sj_sim *s, cudaStream_t st) {
     if (fused_step(s)) return s->prec == SJ_F64 ? sj_tma_pass_f64(s, 2, st, true) : sj_tma_pass_f32(s, 2, st, true);

@@ -173,7 +173,7 @@ int sj_tma_build_geometry(sj_sim *s) {
         const long long planes = (long long)(s->kz1 - s->kz0) * tiles_xy * s->g.n_sets;
         zc_int = (int)std::min<long long>(s->int_zchunk, std::max<long long>(4, planes / (5LL * n_sm_)));
     }
-    const int sub_int = env_int("SJ_TMA_SUB", 2), sub_face = env_int("SJ_TMA_SUB_FACE", 1);
+    const int sub_int = env_int("SJ_TMA_SUB", 2), sub_face = 1;     // (the kernels take tall tiles for interior items only)
     const int zc_gen = env_int("SJ_TMA_ZCG", 6);       // edge / corner tiles are bound by instruction latency: many short items
     struct Reg { int box, kind, i0, i1, j0, j1, k0, k1; };
     std::vector<Reg> regs;
@@ -225,33 +225,39 @@ int sj_tma_build_geometry(sj_sim *s) {
     return upload_schedule(s, replicate_sets(t.geo[0], s->g.n_sets), 0, n_sm, t.h[0]);
 }
 
-// Fused step: both passes' items in one queue, cut along z into chunks of `wave` planes and ordered H(0), H(1), E(0), H(2),
-// E(1), ... (heaviest first inside a group), so that an E-pass item finds what the H-pass items of its chunk wrote -- and the E
-// planes they read -- in the L2.  Only for a slab that holds the whole grid (the boundary-plane exchange of z-slabs has its
-// own ordering) and only while a few chunks of both passes fit the L2 window; SJ_TMA_WAVE = planes per chunk (0: off).
+// Fused step: both passes' items in one queue, cut along z into chunks of `wave` planes and ordered as a wavefront -- H(0), H(1),
+// H(2), E(0), H(3), E(1), ... (heaviest first inside a group) -- so that an E-pass item finds what the H-pass items of its chunk
+// wrote, and the E planes they read, in the L2.  A slab with z neighbours sweeps from its top chunk down instead: its top H
+// plane (the upper slab's E-pass waits for it) is then the first item of the step and its bottom E plane (the lower slab's
+// next H-pass waits for it) the last, which is the order the boundary-plane exchange needs.  H groups are labelled in queue
+// order; an E-pass item carries the label of the last H group it depends on (bits 16.. of WorkItem::shape).  Only while a
+// few chunks of both passes fit the L2 window; SJ_TMA_WAVE = planes per chunk (0: off).
 static int build_fused(sj_sim *s, const std::vector<WorkItem> &e_items, int n_sm) {
     TmaState &t = s->tma;
     free_list(t.f); cudaFree(t.grp); t.grp = NULL; t.wave = 0; t.n_chunks = 0;
-    if (t.n_bnd[0] || t.n_bnd[1] || s->kz0 != 0 || s->kz1 != s->g.n[2] + 1) return 0;
     const double plane_bytes = (double)s->plane * s->esz * s->g.n_sets * (18.0 + 6.0 * std::max(s->n_slots, 0));   // both passes, one plane
     // chunk length: measured on the bench workload (17 MB per plane of both passes): DRAM reads per step 2033 MB with two
-    // launches, 1465 MB with 6-plane chunks, 1210 MB with 2-plane chunks -- but short chunks pay more per item (dependency
-    // waits, partial planes, code switches) than the saved bytes are worth, the kernel not being DRAM-bound any more:
-    // 0.57 / 0.49 / 0.47 / 0.48 ms per step with 3 / 6 / 8 / 12 planes.  Planes too large for the L2 to hold a chunk of both
-    // passes stay with two launches per step.
+    // launches, 1747 / 1465 / 1210 MB with 8 / 6 / 2-plane chunks -- but short chunks pay more per item (dependency waits,
+    // partial planes, code switches) than the saved bytes are worth: 0.50 / 0.486 / 0.479 / 0.472 / 0.470 ms per step with
+    // 3 / 4 / 5 / 8 / 10 planes.  Planes too large for the L2 to hold a chunk of both passes stay with two launches per step.
     int wave = env_int("SJ_TMA_WAVE", -1);
     if (wave < 0) { wave = std::min(8, (int)(140e6 / plane_bytes)); if (wave < 2) wave = 0; }
     if (wave <= 0) return 0;
+    const bool down = t.n_bnd[0] || t.n_bnd[1];              // a slab with neighbours sweeps top-down
     const int nz = s->kz1 - s->kz0, nch = (nz + wave - 1) / wave;
     std::vector<std::vector<WorkItem>> grp[2];
     grp[0].resize(nch); grp[1].resize(nch);
+    auto label = [&](int c) { return down ? nch - 1 - c : c; };      // position of chunk c in the sweep
     auto cut = [&](const std::vector<WorkItem> &in, int pass) {
         for (const WorkItem &w : in)
             for (int kb = w.kb; kb < w.ke;) {
                 const int c = (kb - s->kz0) / wave, ke = std::min(w.ke, s->kz0 + (c + 1) * wave);
+                // an E-pass item of chunk c needs the H-pass items of the chunks c - 1 and c: the later of the two in the sweep
+                const int lab = pass == 0 ? label(c) : std::max(label(c), c > 0 ? label(c - 1) : 0);
                 for (int q = 0; q < s->g.n_sets; ++q) {
-                    WorkItem x = w; x.kb = kb; x.ke = ke; x.set = q; x.shape = (w.shape & 0xff) | (pass ? SJ_EPASS_FLAG : 0) | (c << 16);      // (no boundary items in a whole-grid slab)
-                    grp[pass][c].push_back(x);
+                    WorkItem x = w; x.kb = kb; x.ke = ke; x.set = q;
+                    x.shape = (w.shape & (0xff | SJ_BND_FLAG)) | (pass ? SJ_EPASS_FLAG : 0) | (lab << 16);
+                    grp[pass][label(c)].push_back(x);
                 }
                 kb = ke;
             }
@@ -260,17 +266,21 @@ static int build_fused(sj_sim *s, const std::vector<WorkItem> &e_items, int n_sm
     auto cost = [&](const WorkItem &w) { return (long long)(w.ke - w.kb + 1) * item_weight(s, w, (w.shape & SJ_EPASS_FLAG) ? 1 : 0); };
     std::vector<WorkItem> flat;
     std::vector<int> need(2 * nch + 1, 0);
-    auto emit = [&](int pass, int c) {
-        std::vector<WorkItem> &g = grp[pass][c];
-        std::stable_sort(g.begin(), g.end(), [&](const WorkItem &a, const WorkItem &b) { return cost(a) > cost(b); });
-        flat.insert(flat.end(), g.begin(), g.end());
-        if (pass == 0) need[c] = (int)g.size();            // one count per finished item (group_done)
+    auto emit = [&](int pass, int g) {
+        std::vector<WorkItem> &v = grp[pass][g];
+        std::stable_sort(v.begin(), v.end(), [&](const WorkItem &a, const WorkItem &b) {
+            const int ba = (a.shape & SJ_BND_FLAG) != 0, bb = (b.shape & SJ_BND_FLAG) != 0;
+            return ba != bb ? (pass == 0 ? ba > bb : ba < bb) : cost(a) > cost(b);     // top H plane first, bottom E plane last
+        });
+        flat.insert(flat.end(), v.begin(), v.end());
+        if (pass == 0) need[g] = (int)v.size();            // one count per finished item (group_done)
     };
-    // H runs `lead` chunks ahead of E: the E-pass items of a chunk are pulled when the H-pass items they wait for are done
-    const int lead = std::max(1, env_int("SJ_TMA_LEAD", 2));
-    for (int c = 0; c < nch + lead; ++c) {
-        if (c < nch) emit(0, c);
-        if (c - lead >= 0) emit(1, c - lead);
+    // the H groups run `lead` (+ 1 when sweeping down: E(c) also needs the group after its own) ahead of the E groups, so that
+    // the E-pass items of a chunk are pulled when the H-pass items they wait for are done
+    const int lead = std::max(1, env_int("SJ_TMA_LEAD", 2)) + (down ? 1 : 0);
+    for (int g = 0; g < nch + lead; ++g) {
+        if (g < nch) emit(0, g);
+        if (g - lead >= 0) emit(1, g - lead);
     }
     CK(cudaMalloc((void **)&t.grp, need.size() * sizeof(int)));
     CK(cudaMemcpy(t.grp, need.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice));     // done counters and epoch start at 0

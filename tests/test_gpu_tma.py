@@ -61,3 +61,39 @@ def test_tma_no_pml_and_odd_sizes():
         s.run(90, 3)
     for c in range(6):
         assert np.array_equal(ref.field(c, 0), g.field(c, 0)), c
+
+
+def _sim_env(env, prec, n):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})      # read when the work lists are built (sj_create / sj_set_materials)
+    try:
+        return _sim(3, prec, n, 2, 1.0, 1.5)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_fused_wavefront_and_tall_tiles_bitwise(prec):
+    """One launch per step (H-pass and E-pass items in one queue, z wavefront with per-chunk dependencies) against two
+    launches per step, tall tiles (two rows per thread) against plain ones, several chunk lengths: identical fields."""
+    n = (52, 47, 44)
+    ref = _sim_env({"SJ_TMA_WAVE": 0, "SJ_TMA_SUB": 1}, prec, n)
+    ref.run(90, 4)
+    l_ref = ref.launches()
+    assert np.abs(ref.field(0, 0)).max() > 1e-3
+    for env in ({"SJ_TMA_WAVE": 0, "SJ_TMA_SUB": 2}, {"SJ_TMA_WAVE": 2, "SJ_TMA_LEAD": 1}, {"SJ_TMA_WAVE": 3, "SJ_TMA_LEAD": 2},
+                {"SJ_TMA_WAVE": 8}, {"SJ_TMA_WAVE": 64}, {}):
+        g = _sim_env(env, prec, n)
+        g.run(90, 4)
+        for c in range(6):
+            for q in range(2):
+                assert np.array_equal(ref.field(c, q), g.field(c, q)), (env, c, q)
+        assert np.array_equal(ref.monitors(), g.monitors())
+        if env.get("SJ_TMA_WAVE", 8) != 0:
+            assert g.launches() < l_ref, "the fused step is one launch"      # (plus the monitor samples)
+        g.close()
+    ref.close()
