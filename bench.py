@@ -39,7 +39,10 @@ import numpy as np  # noqa: E402
 
 SCENE = "Au_graphene_box"
 SAVE_SPAN = 20
+# the same `config` object in both arms (the driver compares them)
 WORKLOAD = "junctions/Au_graphene_box 181^3 cells x 2 field sets (complex), res 10 -> 181/18"
+CONFIG = {"workload": WORKLOAD, "scene": "scenes/Au_graphene_box/params.conf + junc.geom (re-authored, see DESIGN.md) through the own conf/CGS readers",
+          "save_span": SAVE_SPAN, "l2": "fields + auxiliaries of a step (2.4 GB) >> 126 MB L2; no flush needed"}
 
 
 def load_settings():
@@ -132,7 +135,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "yee_cell_updates_per_s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "scene": "scenes/Au_graphene_box/junc.geom (re-authored, see DESIGN.md)"},
+            "config": dict(CONFIG),
             "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "threads_requested": want,
                              "sample": "%d full-grid oracle steps (meep-structured C/OpenMP restatement; meep itself is absent)" % args.steps},
             "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -300,18 +303,18 @@ def run_ours(args):
             cpu = {"value": cells * 2 * k / tc, "unit": "cell-updates/s", "cores": orc.lib().orc_num_threads(), "kind": "port",
                    "sample": "%d full-grid steps of the same 181^3 x 2-set workload (oracle/fdtd_oracle.c, OpenMP)" % k}
     if rank == 0:
-        cfg = {"workload": WORKLOAD, "scene": "scenes/Au_graphene_box/params.conf + junc.geom (re-authored, see DESIGN.md) through the own conf/CGS readers",
-               "save_span": SAVE_SPAN, "repeats": args.repeats, "ms_per_step_all_repeats": [t / K for t in times],
-               "l2": "fields + auxiliaries of a step (2.4 GB) >> 126 MB L2; no flush needed"}
+        cfg = dict(CONFIG)
+        decomposition = None
         if world > 1:
-            cfg["decomposition"] = "%d z-slabs of the same box, %s planes (equal bytes per step); boundary planes written into the neighbour's halo by the step " \
+            decomposition = "%d z-slabs of the same box, %s planes (equal bytes per step); boundary planes written into the neighbour's halo by the step " \
                                    "kernels (peer stores over NVLink, CUDA-IPC mapped), device-side flags, one CUDA graph per step and rank" \
                                    % (world, "/".join(str(b - a) for a, b in all_kz))
         line = {"metric": "yee_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": prec, "data": "synthetic", "config": cfg,
                 "clocks": dict(sampler.summary(), extended_sampling=extended), "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu,
+                "repeats": args.repeats, "ms_per_step_all_repeats": [t / K for t in times], "decomposition": decomposition}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

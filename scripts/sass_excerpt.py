@@ -1,4 +1,4 @@
-"""SASS evidence of the TMA-staged step kernels: python scripts/sass_excerpt.py > profiles/sass_tma_r2.txt
+"""SASS evidence of the TMA-staged step kernels: python scripts/sass_excerpt.py > profiles/sass_tma_r2b.txt
 (cuobjdump on the built object; no GPU needed)."""
 import collections
 import os
@@ -14,7 +14,7 @@ KEY = re.compile(r"\b(UTMALDG[.\w]*|UBLKCP[.\w]*|SYNCS[.\w]*|LDS[.\w]*|STG[.\w]*
 for f in funcs:
     name = f.split("\n", 1)[0].strip()
     dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
-    if "tma<double, 224, 12, 1>" not in dem:
+    if "step_tma<double, 224, 16>" not in dem:
         continue
     lines = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4,}\*/", l)]
     ins = [re.sub(r"\s+", " ", re.sub(r"/\*[0-9a-fx]+\*/", "", l)).strip(" ;") for l in lines]
