@@ -684,7 +684,7 @@ __device__ __forceinline__ void tma_produce(const KParams<T> &p, const PmlBoxSet
 // SUB: rows per thread (tall tiles, PD == 4 only; see h_tma_item)
 template <typename T, int NT, int NB, int NS, int PD, bool SRC, bool UNI, bool LATE, int SUB>
 __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<T> &bs, const SlabLinks<T> &lk, const WorkItem &it,
-                                           const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu) {
+                                           const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu, const long long step) {
     static_assert(SUB == 1 || PD == 4, "tall tiles: interior items only");
     constexpr int V = 16 / (int)sizeof(T);
     constexpr bool POL = NS > 0;
@@ -709,8 +709,7 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
     const int hp = sh.hp;                          // the row below inside a halo box: hcen - hp
     const T C = p.courant;
     const int set = it.set;
-    const long long step = *p.step;
-    const int parity = (int)(step & 1);
+    const int parity = (int)(step & 1);            // step: the device step counter, read once per kernel
     const long long plane = p.plane;
     const long long fcs = p.fcs, fcs2 = 2 * p.fcs;
     const long long sub_step = (long long)sh.ths * p.pitch;
@@ -968,9 +967,9 @@ __device__ __forceinline__ void e_tma_item(const KParams<T> &p, const PmlBoxSet<
 
 template <typename T, int NT, int NB, int NS, bool UNI, bool LATE>
 __device__ __forceinline__ void e_tma_dispatch(const KParams<T> &p, const PmlBoxSet<T> &bs, const SlabLinks<T> &lk, const WorkItem &it,
-                                               const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu) {
+                                               const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu, const long long step) {
     const bool src = src_in_chunk(p, kb, ke);
-#define SJ_E_ITEM(PD_, SRC_, SUB_) e_tma_item<T, NT, NB, NS, PD_, SRC_, UNI, LATE, SUB_>(p, bs, lk, it, sh, r, kb, ke, cu)
+#define SJ_E_ITEM(PD_, SRC_, SUB_) e_tma_item<T, NT, NB, NS, PD_, SRC_, UNI, LATE, SUB_>(p, bs, lk, it, sh, r, kb, ke, cu, step)
     if (it.box < 0) {
         // tall tiles: classes that stage at most one pole slot (the host cuts the others into half-height items)
         if (NS <= 1 && sh.sub == 2) { if (src) SJ_E_ITEM(4, true, (NS <= 1 ? 2 : 1)); else SJ_E_ITEM(4, false, (NS <= 1 ? 2 : 1)); }
@@ -985,12 +984,12 @@ __device__ __forceinline__ void e_tma_dispatch(const KParams<T> &p, const PmlBox
 
 template <typename T, int NT, int NB>
 __device__ __forceinline__ void e_tma_class(const KParams<T> &p, const PmlBoxSet<T> &bs, const SlabLinks<T> &lk, const WorkItem &it,
-                                            const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu) {
-    if (it.pad == 0) e_tma_dispatch<T, NT, NB, 0, true, false>(p, bs, lk, it, sh, r, kb, ke, cu);
-    else if (it.pad == 2) e_tma_dispatch<T, NT, NB, 1, true, false>(p, bs, lk, it, sh, r, kb, ke, cu);
-    else if (it.pad == 3) e_tma_dispatch<T, NT, NB, 2, true, false>(p, bs, lk, it, sh, r, kb, ke, cu);
-    else if (p.n_slots <= 1) e_tma_dispatch<T, NT, NB, 1, false, false>(p, bs, lk, it, sh, r, kb, ke, cu);
-    else e_tma_dispatch<T, NT, NB, 2, false, false>(p, bs, lk, it, sh, r, kb, ke, cu);
+                                            const TShape &sh, const Ring<NB> &r, int kb, int ke, Cursor &cu, const long long step) {
+    if (it.pad == 0) e_tma_dispatch<T, NT, NB, 0, true, false>(p, bs, lk, it, sh, r, kb, ke, cu, step);
+    else if (it.pad == 2) e_tma_dispatch<T, NT, NB, 1, true, false>(p, bs, lk, it, sh, r, kb, ke, cu, step);
+    else if (it.pad == 3) e_tma_dispatch<T, NT, NB, 2, true, false>(p, bs, lk, it, sh, r, kb, ke, cu, step);
+    else if (p.n_slots <= 1) e_tma_dispatch<T, NT, NB, 1, false, false>(p, bs, lk, it, sh, r, kb, ke, cu, step);
+    else e_tma_dispatch<T, NT, NB, 2, false, false>(p, bs, lk, it, sh, r, kb, ke, cu, step);
 }
 
 
@@ -1012,6 +1011,7 @@ __global__ void __launch_bounds__(NT + 32, 1) step_tma(const KParams<T> p, const
         return;
     }
     Cursor cu; cu.q = 0; cu.head = 0;
+    const long long step = *p.step;                                // (advanced by the last block to finish, see below)
 #ifdef SJ_TMA_PROF
     cu.t_full = 0;
     const long long t_c0 = clock64();
@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(NT + 32, 1) step_tma(const KParams<T> p, const
         if (it.box == SJ_ITEM_END) break;
         const int kb = max(it.kb, k_lo), ke = min(it.ke, k_hi);
         const TShape sh = plan.shape[it.shape & 0xff];
-        if (it.shape & SJ_EPASS_FLAG) e_tma_class<T, NT, NB>(p, bs, lk, it, sh, r, kb, ke, cu);
+        if (it.shape & SJ_EPASS_FLAG) e_tma_class<T, NT, NB>(p, bs, lk, it, sh, r, kb, ke, cu, step);
         else h_tma_dispatch<T, NT, NB>(p, bs, lk, it, sh, r, kb, ke, cu, plan.grp_done ? plan.grp_done + (it.shape >> 16) : nullptr);
     }
 #ifdef SJ_TMA_PROF

@@ -248,10 +248,14 @@ static int build_fused(sj_sim *s, const std::vector<WorkItem> &e_items, int n_sm
     std::vector<std::vector<WorkItem>> grp[2];
     grp[0].resize(nch); grp[1].resize(nch);
     auto label = [&](int c) { return down ? nch - 1 - c : c; };      // position of chunk c in the sweep
+    // the last two groups of the step are cut into runs of at most `fine` planes: fine grains even out the end of the launch
+    const int fine = std::max(1, env_int("SJ_TMA_FINE", 3));
     auto cut = [&](const std::vector<WorkItem> &in, int pass) {
         for (const WorkItem &w : in)
             for (int kb = w.kb; kb < w.ke;) {
-                const int c = (kb - s->kz0) / wave, ke = std::min(w.ke, s->kz0 + (c + 1) * wave);
+                const int c = (kb - s->kz0) / wave;
+                int ke = std::min(w.ke, s->kz0 + (c + 1) * wave);
+                if (pass == 1 && label(c) >= nch - 2) ke = std::min(ke, kb + fine);
                 // an E-pass item of chunk c needs the H-pass items of the chunks c - 1 and c: the later of the two in the sweep
                 const int lab = pass == 0 ? label(c) : std::max(label(c), c > 0 ? label(c - 1) : 0);
                 for (int q = 0; q < s->g.n_sets; ++q) {
