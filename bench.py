@@ -251,7 +251,7 @@ def run_ours(args):
                    "and the monitor series is read back to the host" % int(h2d)}
     del bg2
 
-    roofline, cpu, per_rank = None, None, None
+    roofline, cpu, per_rank, fp32 = None, None, None, None
     if world == 1:
         # ---- per-kernel roofline, timed live with CUDA events on a scratch simulation ----
         scratch = make().sim
@@ -288,6 +288,16 @@ def run_ours(args):
                                    "one half-pass, timed alone" if fused_ms > 0 else
                                    "a step is two launches of it (H-pass items, then E-pass items)")}
         del scratch
+        # ---- the same workload in fp32 (the reference tolerates 1e-4: north_star's second precision), device-timed, short ----
+        fp32 = None
+        if prec == "f64" and not args.no_fp32:
+            b32 = BoundGeom(st, None, precision="f32", n_sets=n_sets, device=local)
+            b32.sim.run(W, SAVE_SPAN)
+            ms32 = statistics.median(b32.sim.run_timed(100, SAVE_SPAN) for _ in range(3)) / 100
+            by32 = b32.sim.bytes_per_step()
+            fp32 = {"ms_per_step": ms32, "value": cells * n_sets / (ms32 * 1e-3), "unit": "cell-updates/s",
+                    "step_algorithmic_bytes": by32, "step_frac": by32 / (ms32 * 1e-3) / 1e9 / peak}
+            del b32
         # ---- CPU baseline: the oracle on a bounded sample of the same workload ----
         if not args.no_cpu:
             host_threads()
@@ -314,7 +324,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": prec, "data": "synthetic", "config": cfg,
                 "clocks": dict(sampler.summary(), extended_sampling=extended), "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu,
-                "repeats": args.repeats, "ms_per_step_all_repeats": [t / K for t in times], "decomposition": decomposition}
+                "repeats": args.repeats, "ms_per_step_all_repeats": [t / K for t in times], "decomposition": decomposition,
+                "fp32": fp32}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -330,6 +341,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.repeats = max(args.repeats, 1)

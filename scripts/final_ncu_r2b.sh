@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -k regex:"tma|sample_monitors" -s 30 -c 12 --csv \
-    --log-file gpurun_out/ncu_launches_r2b.csv python bench.py --steps 20 --warmup 5 --repeats 1 --no-cpu > gpurun_out/ncu_launches_bench_r2b.log 2>&1
+    --log-file gpurun_out/ncu_launches_r2b.csv python bench.py --steps 20 --warmup 5 --repeats 1 --no-cpu --no-fp32 > gpurun_out/ncu_launches_bench_r2b.log 2>&1
 SJ_NO_GRAPH=1 ncu --set full --import-source on --clock-control none --cache-control none -k regex:tma --launch-skip 12 --launch-count 1 -f -o /tmp/ncu_full_r2b \
     python scripts/prof_steps.py 30 > gpurun_out/ncu_full_r2b.log 2>&1
 ncu -i /tmp/ncu_full_r2b.ncu-rep --page raw --csv > gpurun_out/ncu_full_r2b_raw.csv 2>> gpurun_out/ncu_full_r2b.log
