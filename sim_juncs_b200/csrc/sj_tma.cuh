@@ -1,17 +1,21 @@
-// sj_tma.cuh -- TMA-staged column kernels of the FDTD hot path (sm_100a).
+// sj_tma.cuh -- the TMA-staged step kernel of the FDTD hot path (sm_100a).
 //
-// One persistent kernel per (half-pass, stage layout).  A thread block owns a list of work items (xy tile x run of
-// z planes, any cell class: interior, single-sigma PML face, PML edge / corner) fixed by the host (LPT schedule), and
-// marches each item along z.  Data movement is Blackwell's: one elected producer thread issues a
-// cp.async.bulk.tensor (TMA) box load per array per plane into a ring of shared-memory stages and signals an mbarrier
-// with the byte count; the consumer warps wait on that barrier, read their cells and the i/j neighbours from the staged
-// boxes (the curl inputs are loaded with a one-vector / one-row halo, so there are no shuffles, no tile-edge loads and
-// no boundary predicates: TMA zero-fills outside the grid), do the arithmetic of sj_kernels.cuh and store with 128-bit
-// st.global.  The ring is released stage by stage through a second set of mbarriers (one arrival per consumer warp), so
-// the producer runs as many planes ahead as the ring holds -- also across the boundary between two items -- whatever the occupancy.
+// One persistent kernel, step_tma: one block per SM pulls work items off a queue in device memory -- an xy tile x a run of z
+// planes of one cell class (interior, single-sigma PML face, PML edge / corner), one half-pass and one material class -- and
+// marches each item along z.  Data movement is Blackwell's: one elected producer thread issues a cp.async.bulk.tensor (TMA)
+// box load per array per plane into a byte-granular ring in shared memory and arms an mbarrier with the byte count; the
+// consumer warps wait on that barrier, read their cells and the i/j neighbours from the staged boxes (the curl inputs are
+// loaded with a one-vector / one-row halo, so there are no shuffles, no tile-edge loads and no boundary predicates: TMA
+// zero-fills outside the grid), do the arithmetic of sj_kernels.cuh and store with 128-bit st.global.  The ring is released
+// load by load through a second set of mbarriers (one arrival per consumer warp), so the producer runs as many planes ahead
+// as the ring holds -- also across the boundary between two items.
+//
+// The queue holds the H-pass items of a slab, its E-pass items, or -- the fused step, one launch per time step -- both, ordered
+// as a wavefront along z with per-chunk dependency counters, so that the E-pass finds the H planes just written in the L2
+// (what each piece is worth is measured in profiles/README.md, round 2).
 //
 // The arithmetic (curl order, UPML forms, ADE) is expression for expression that of the register kernels in
-// sj_kernels.cuh, so both paths give bit-identical fields (tests/test_gpu_tma.py).
+// sj_kernels.cuh, so all paths give bit-identical fields (tests/test_gpu_tma.py).
 #pragma once
 #include <cuda.h>
 
