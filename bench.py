@@ -162,7 +162,19 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # the version banner (env or nccl.conf) goes to stdout, where the one JSON line belongs
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout when the communicator is created; stdout carries the one JSON line, so
+        # file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     st = load_settings()
     n = st.grid_cells()
     prec = args.precision
